@@ -1,0 +1,52 @@
+/*
+ * nvs_log.h -- stderr logging with the reference's line prefix
+ * ("[NVSHARE][LEVEL]: ", reference src/common.h:17-44) because operators and
+ * the reference's README (README.md:284-356) grep scheduler/client logs for it.
+ * A fatal log terminates the process with status 1, like the reference's
+ * log_fatal / true_or_exit (src/common.h:24-28,47-52).
+ */
+#ifndef NVS_LOG_H
+#define NVS_LOG_H
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <errno.h>
+
+extern int nvs_debug_enabled;
+
+#define nvs_log_at(level, ...)                               \
+	do {                                                 \
+		fputs("[NVSHARE][" level "]: ", stderr);     \
+		fprintf(stderr, __VA_ARGS__);                \
+		fputc('\n', stderr);                         \
+	} while (0)
+
+#define nvs_info(...)  nvs_log_at("INFO", __VA_ARGS__)
+#define nvs_warn(...)  nvs_log_at("WARN", __VA_ARGS__)
+#define nvs_debug(...)                                       \
+	do {                                                 \
+		if (nvs_debug_enabled)                       \
+			nvs_log_at("DEBUG", __VA_ARGS__);    \
+	} while (0)
+#define nvs_fatal(...)                                       \
+	do {                                                 \
+		nvs_log_at("FATAL", __VA_ARGS__);            \
+		exit(1);                                     \
+	} while (0)
+#define nvs_fatal_errno(...)                                 \
+	do {                                                 \
+		int e_ = errno;                              \
+		nvs_log_at("FATAL", __VA_ARGS__);            \
+		fprintf(stderr, "errno = %s\n", strerror(e_)); \
+		exit(1);                                     \
+	} while (0)
+
+/* invariant check: failure is fatal for the hosting process (reference semantics) */
+#define nvs_must(cond)                                       \
+	do {                                                 \
+		if (!(cond))                                 \
+			nvs_fatal("Condition failed: %s", #cond); \
+	} while (0)
+
+#endif /* NVS_LOG_H */
