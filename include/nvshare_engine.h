@@ -1,0 +1,156 @@
+/*
+ * nvshare_engine.h -- C-ABI of the B200 swap engine: the explicit
+ * prefetch/evict data path that replaces the reference's one-line data path
+ *
+ *     real_cuMemAllocManaged(dptr, bytesize, CU_MEM_ATTACH_GLOBAL)
+ *                                              (reference src/hook.c:673)
+ *
+ * and everything NVIDIA's UVM driver does behind it (GPU page fault ->
+ * migrate 4 KiB..2 MiB -> LRU-evict some context's pages).  Exported by
+ * libnvshare.so (where the LD_PRELOAD hook and the client runtime are its only
+ * callers) and by libnvs_engine.so (the same object without the interposer,
+ * for ctypes-driven parity tests and bench.py).  Plain C: pointers and sizes
+ * only, no CUDA SDK types, no torch types.
+ *
+ * Reference interface each entry point replaces (file:line in /root/reference):
+ *   nvs_alloc        src/hook.c:646-682  cuMemAlloc hook body (after the cap
+ *                    check, which stays in the hook): cuMemAllocManaged +
+ *                    insert_cuda_allocation (src/hook.c:273-288)
+ *   nvs_free         src/hook.c:685-695  real_cuMemFree + remove_cuda_allocation
+ *                    (src/hook.c:291-305)
+ *   nvs_fetch_all    what UVM does implicitly after LOCK_OK opens the gate
+ *                    (src/client.c:298-307 -> first touch faults); here it runs
+ *                    BEFORE own_lock is set
+ *   nvs_evict        what UVM does implicitly while another context faults its
+ *                    pages in; here it runs after cuda_sync_context() on
+ *                    DROP_LOCK (src/client.c:308-317) and on early release
+ *                    (src/client.c:472-476)
+ *   nvs_get_stats    no counterpart (the reference has no counters)
+ *   nvs_copy_slabs / nvs_pattern_fill / nvs_pattern_verify
+ *                    no counterpart: raw access to the sm_100a kernels for the
+ *                    parity tests and the roofline measurement
+ *
+ * Return values: 0 on success, otherwise a CUresult value from the driver
+ * (2 = CUDA_ERROR_OUT_OF_MEMORY, 3 = CUDA_ERROR_NOT_INITIALIZED, ...) or one
+ * of the negative NVS_E_* codes below.  Nothing in here falls back to a CPU
+ * path: if the driver or the kernel image cannot be loaded, creation fails.
+ */
+#ifndef NVSHARE_ENGINE_H
+#define NVSHARE_ENGINE_H
+
+#include <stdint.h>
+#include "nvs_copy_desc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVS_E_NOT_OURS   (-2) /* pointer was not allocated by this engine          */
+#define NVS_E_BAD_ARG    (-3)
+#define NVS_E_NO_DRIVER  (-4) /* libcuda.so.1 or a required entry point is missing */
+#define NVS_E_NO_KERNEL  (-5) /* embedded sm_100a image failed to load             */
+#define NVS_E_TIMEOUT    (-6) /* HBM did not become available in time              */
+#define NVS_E_HOST_OOM   (-7) /* backing tier exhausted                            */
+
+#define NVS_MAX_PEERS 7
+
+typedef struct nvs_engine nvs_engine;
+
+/* Resolves a driver entry point by its exported ELF name (e.g. "cuMemCreate",
+ * "cuMemAlloc_v2").  libnvshare.so passes a resolver built on the REAL dlsym
+ * so the engine never sees the interposed symbols. */
+typedef void *(*nvs_resolve_fn)(const char *symbol);
+
+typedef struct nvs_engine_config {
+	uint32_t struct_size;        /* sizeof(nvs_engine_config), for ABI growth          */
+	int32_t  device;             /* CUDA ordinal; -1 = device of the current context   */
+	nvs_resolve_fn resolve;      /* NULL = dlopen("libcuda.so.1") + dlsym              */
+	uint64_t chunk_bytes;        /* physical mapping unit, multiple of 2 MiB (64 MiB)  */
+	uint64_t small_alloc_bytes;  /* smaller requests stay plain cuMemAlloc (1 MiB)     */
+	uint64_t batch_bytes;        /* pipeline batch: copy(b+1) overlaps (un)map(b)      */
+	uint64_t host_arena_bytes;   /* pinned-host growth unit (1 GiB)                    */
+	uint32_t evict_variant;      /* enum nvs_copy_variant                              */
+	uint32_t fetch_variant;      /* enum nvs_copy_variant                              */
+	uint32_t copy_grid;          /* CTAs per copy launch                               */
+	uint32_t tma_warps;          /* warps per CTA (TMA variant)                        */
+	uint32_t tma_stages;         /* ring depth per warp                                */
+	uint32_t tma_tile_bytes;     /* bytes per stage                                    */
+	uint32_t ldg_threads;        /* threads per CTA (LDG variant)                      */
+	uint32_t oom_wait_ms;        /* how long fetch/alloc wait for HBM to be released   */
+	uint32_t prepin;             /* 1 = grow the pinned pool in the background on alloc */
+	int32_t  n_peers;            /* peer-HBM backing tier: devices, in striping order  */
+	int32_t  peers[NVS_MAX_PEERS];
+	uint64_t peer_capacity_bytes; /* per peer; 0 = none                                */
+	const char *stats_path;      /* JSON lines, one per evict/fetch; NULL = off        */
+} nvs_engine_config;
+
+typedef struct nvs_xfer_report {
+	uint64_t bytes;        /* payload bytes moved (algorithmic: 2 MiB per slab, once) */
+	uint64_t slabs;
+	uint64_t chunks;       /* physical chunks (un)mapped                              */
+	uint64_t launches;     /* copy kernel launches (or CE calls)                      */
+	double   wall_ms;      /* whole call                                              */
+	double   copy_ms;      /* CUDA-event time, first launch start -> last launch end  */
+	double   map_ms;       /* host time in cuMemCreate/Map/SetAccess or Unmap/Release */
+	double   wait_ms;      /* host time spent waiting for HBM (OOM retries)           */
+	uint64_t host_bytes;   /* of `bytes`, how much went to / came from the host tier  */
+	uint64_t peer_bytes;   /* ... the peer-HBM tier                                   */
+} nvs_xfer_report;
+
+typedef struct nvs_stats {
+	uint64_t n_allocs;
+	uint64_t requested_bytes;   /* sum of sizes the application asked for            */
+	uint64_t va_bytes;          /* reserved virtual range (2 MiB rounded)            */
+	uint64_t resident_bytes;    /* chunks currently mapped to HBM                    */
+	uint64_t swapped_bytes;     /* chunks whose only copy is in the backing tier     */
+	uint64_t unbacked_bytes;    /* chunks never materialised (no copy needed)        */
+	uint64_t passthrough_bytes; /* small allocations left to plain cuMemAlloc        */
+	uint64_t host_pool_bytes;   /* pinned host memory owned by the pool              */
+	uint64_t host_pool_used;
+	uint64_t peer_pool_bytes;
+	uint64_t peer_pool_used;
+	uint64_t n_evicts, n_fetches;
+	uint64_t evicted_bytes_total, fetched_bytes_total;
+	uint64_t kernel_launches_total; /* nvs_slab_copy_* launches since creation       */
+} nvs_stats;
+
+/* Fill *cfg with defaults, then apply NVSHARE_* environment overrides
+ * (NVSHARE_CHUNK_MIB, NVSHARE_COPY_VARIANT, NVSHARE_COPY_GRID, NVSHARE_PEERS, ...). */
+int nvs_engine_default_config(nvs_engine_config *cfg);
+
+/* Requires a current CUDA context on the calling thread; the engine keeps using it. */
+int nvs_engine_create(const nvs_engine_config *cfg, nvs_engine **out);
+void nvs_engine_destroy(nvs_engine *e);
+
+int nvs_alloc(nvs_engine *e, uint64_t *dptr, uint64_t bytes);
+int nvs_free(nvs_engine *e, uint64_t dptr);
+/* same, also reporting the size the application had asked for (the hook's
+ * sum_allocated bookkeeping, reference src/hook.c:298) */
+int nvs_free_sized(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes);
+
+/* Tell the engine whether its owner currently holds the GPU lock: new
+ * allocations are materialised immediately when it does, deferred otherwise. */
+void nvs_set_resident_mode(nvs_engine *e, int holds_lock);
+
+int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep);
+/* Evict at least `min_bytes` (0 = everything) of resident chunks, least
+ * recently fetched first, and release their physical HBM. */
+int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep);
+
+int nvs_get_stats(nvs_engine *e, nvs_stats *out);
+
+/* Raw kernel access (parity tests, roofline).  All addresses must be
+ * device-accessible in the engine's context.  *ms = CUDA-event time. */
+int nvs_copy_slabs(nvs_engine *e, const nvs_copy_desc *descs, uint32_t n, uint32_t variant,
+		   uint32_t grid, float *ms);
+int nvs_pattern_fill(nvs_engine *e, uint64_t addr, uint64_t n_words, uint64_t first_index, uint64_t seed);
+int nvs_pattern_verify(nvs_engine *e, uint64_t addr, uint64_t n_words, uint64_t first_index, uint64_t seed,
+		       uint64_t *mismatches);
+
+const char *nvs_strerror(int rc);
+const char *nvs_engine_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVSHARE_ENGINE_H */

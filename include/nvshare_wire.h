@@ -81,6 +81,8 @@ _Static_assert(offsetof(struct nvs_msg, data) == 517, "data offset");
 #define NVS_HINT_NEED_PREFIX    'n'
 #define NVS_HINT_WAITERS_PREFIX 'w'
 
+/* helpers shared by the daemon, the CLI and the client library (not exported from libnvshare.so) */
+#pragma GCC visibility push(hidden)
 const char *nvs_msg_type_name(unsigned type);
 
 /* Fills `out` (size >= 108) with the scheduler socket path; honours NVS_ENV_SOCK_DIR. */
@@ -93,6 +95,7 @@ int nvs_accept(int lfd);                                /* -> nonblocking fd, -1
 int nvs_connect(const char *path);                      /* -> blocking fd or -1              */
 ssize_t nvs_write_all(int fd, const void *buf, size_t n); /* n on success, -1 on error       */
 ssize_t nvs_read_all(int fd, void *buf, size_t n);        /* bytes read (< n on EOF), -1     */
+#pragma GCC visibility pop
 
 #ifdef __cplusplus
 }

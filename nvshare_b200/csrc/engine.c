@@ -1,0 +1,1533 @@
+/*
+ * engine.c -- the B200 swap engine (host side, plain C on the CUDA driver API).
+ *
+ * The reference has no such component: its whole data path is one call,
+ * real_cuMemAllocManaged() (reference src/hook.c:673), after which NVIDIA's
+ * UVM driver migrates pages on GPU faults.  This file is that data path made
+ * explicit and B200-shaped:
+ *
+ *   allocation  cuMemAddressReserve for the application's pointer (stable for
+ *               the allocation's life) + cuMemCreate/cuMemMap/cuMemSetAccess
+ *               per CHUNK (default 64 MiB = 32 slabs).  Measured on B200
+ *               (profiles/r01_probe_b200.txt): mapping 8 GiB costs 221 ms in
+ *               2 MiB units but 6.7 ms in 64 MiB units; unmap+release 716 ms vs
+ *               12 ms.  Copy and accounting granularity stays one SLAB (2 MiB).
+ *   backing     tier 1: HBM of peer GPUs (cuMemCreate on the peer, mapped into
+ *               this context; striped per chunk; no NCCL).  tier 0: pinned host
+ *               DRAM arenas (cuMemHostAlloc PORTABLE|DEVICEMAP, 1 GiB units,
+ *               bitmap sub-allocation, grown in the background because pinning
+ *               runs at only ~3.8 GB/s on this box).
+ *   evict       resident chunks, least recently fetched first -> descriptors
+ *               -> nvs_slab_copy_tma on a side stream, batch b+1 copying
+ *               while batch b is unmapped and its HBM released.
+ *   fetch       the mirror image: map batch b+1 while batch b copies.  HBM may
+ *               still be held by the client that is evicting in another
+ *               process: cuMemCreate is retried until it is released.
+ *
+ * Chunk states:  UNBACKED (virtual only; contents undefined like fresh
+ * cuMemAlloc memory, nothing to copy) -> RESIDENT <-> SWAPPED.
+ *
+ * Nothing here falls back to a CPU copy: no driver / no kernel image -> error.
+ */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <dlfcn.h>
+#include <errno.h>
+#include <inttypes.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "../../include/nvshare_engine.h"
+#include "cuda_min.h"
+#include "nvs_log.h"
+#include "slab_copy_cubin.h" /* generated: nvs_slab_copy_cubin[], nvs_slab_copy_cubin_len */
+
+#define SLAB NVS_SLAB_BYTES
+#define N_SLOTS 3 /* pipeline depth (batches in flight) */
+
+enum { CH_UNBACKED = 0, CH_RESIDENT = 1, CH_SWAPPED = 2 };
+enum { TIER_NONE = 0, TIER_HOST = 1, TIER_PEER0 = 2 /* TIER_PEER0 + peer index */ };
+
+/* ----------------------------------------------------------- driver ---- */
+
+struct drv {
+	CUresult (*GetErrorName)(CUresult, const char **);
+	CUresult (*CtxGetCurrent)(CUcontext *);
+	CUresult (*CtxPushCurrent)(CUcontext);
+	CUresult (*CtxPopCurrent)(CUcontext *);
+	CUresult (*CtxGetDevice)(CUdevice *);
+	CUresult (*DeviceGetAttribute)(int *, int, CUdevice);
+	CUresult (*DeviceCanAccessPeer)(int *, CUdevice, CUdevice);
+	CUresult (*MemGetInfo)(size_t *, size_t *);
+	CUresult (*MemAlloc)(CUdeviceptr *, size_t);
+	CUresult (*MemFree)(CUdeviceptr);
+	CUresult (*MemHostAlloc)(void **, size_t, unsigned);
+	CUresult (*MemFreeHost)(void *);
+	CUresult (*MemHostGetDevicePointer)(CUdeviceptr *, void *, unsigned);
+	CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long);
+	CUresult (*MemAddressFree)(CUdeviceptr, size_t);
+	CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *,
+			      unsigned long long);
+	CUresult (*MemRelease)(CUmemGenericAllocationHandle);
+	CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+	CUresult (*MemUnmap)(CUdeviceptr, size_t);
+	CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t);
+	CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, int);
+	CUresult (*MemcpyAsync)(CUdeviceptr, CUdeviceptr, size_t, CUstream);
+	CUresult (*MemsetD32Async)(CUdeviceptr, unsigned, size_t, CUstream);
+	CUresult (*StreamCreate)(CUstream *, unsigned);
+	CUresult (*StreamDestroy)(CUstream);
+	CUresult (*StreamSynchronize)(CUstream);
+	CUresult (*EventCreate)(CUevent *, unsigned);
+	CUresult (*EventDestroy)(CUevent);
+	CUresult (*EventRecord)(CUevent, CUstream);
+	CUresult (*EventSynchronize)(CUevent);
+	CUresult (*EventElapsedTime)(float *, CUevent, CUevent);
+	CUresult (*ModuleLoadData)(CUmodule *, const void *);
+	CUresult (*ModuleUnload)(CUmodule);
+	CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
+	CUresult (*FuncSetAttribute)(CUfunction, int, int);
+	CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+				 unsigned, CUstream, void **, void **);
+};
+
+static const struct {
+	const char *name;
+	size_t off;
+} DRV_SYMS[] = {
+#define S(field, sym) {sym, offsetof(struct drv, field)}
+	S(GetErrorName, "cuGetErrorName"),
+	S(CtxGetCurrent, "cuCtxGetCurrent"),
+	S(CtxPushCurrent, "cuCtxPushCurrent_v2"),
+	S(CtxPopCurrent, "cuCtxPopCurrent_v2"),
+	S(CtxGetDevice, "cuCtxGetDevice"),
+	S(DeviceGetAttribute, "cuDeviceGetAttribute"),
+	S(DeviceCanAccessPeer, "cuDeviceCanAccessPeer"),
+	S(MemGetInfo, "cuMemGetInfo_v2"),
+	S(MemAlloc, "cuMemAlloc_v2"),
+	S(MemFree, "cuMemFree_v2"),
+	S(MemHostAlloc, "cuMemHostAlloc"),
+	S(MemFreeHost, "cuMemFreeHost"),
+	S(MemHostGetDevicePointer, "cuMemHostGetDevicePointer_v2"),
+	S(MemAddressReserve, "cuMemAddressReserve"),
+	S(MemAddressFree, "cuMemAddressFree"),
+	S(MemCreate, "cuMemCreate"),
+	S(MemRelease, "cuMemRelease"),
+	S(MemMap, "cuMemMap"),
+	S(MemUnmap, "cuMemUnmap"),
+	S(MemSetAccess, "cuMemSetAccess"),
+	S(MemGetAllocationGranularity, "cuMemGetAllocationGranularity"),
+	S(MemcpyAsync, "cuMemcpyAsync"),
+	S(MemsetD32Async, "cuMemsetD32Async"),
+	S(StreamCreate, "cuStreamCreate"),
+	S(StreamDestroy, "cuStreamDestroy_v2"),
+	S(StreamSynchronize, "cuStreamSynchronize"),
+	S(EventCreate, "cuEventCreate"),
+	S(EventDestroy, "cuEventDestroy_v2"),
+	S(EventRecord, "cuEventRecord"),
+	S(EventSynchronize, "cuEventSynchronize"),
+	S(EventElapsedTime, "cuEventElapsedTime"),
+	S(ModuleLoadData, "cuModuleLoadData"),
+	S(ModuleUnload, "cuModuleUnload"),
+	S(ModuleGetFunction, "cuModuleGetFunction"),
+	S(FuncSetAttribute, "cuFuncSetAttribute"),
+	S(LaunchKernel, "cuLaunchKernel"),
+#undef S
+};
+
+static void *default_resolve(const char *symbol)
+{
+	static void *lib;
+	if (!lib)
+		lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+	return lib ? dlsym(lib, symbol) : NULL;
+}
+
+/* ------------------------------------------------------------- types ---- */
+
+struct chunk {
+	uint64_t va;
+	uint64_t bytes;
+	CUmemGenericAllocationHandle handle; /* valid while RESIDENT */
+	uint64_t backing;                    /* device-accessible address of the backing range, 0 = none */
+	uint64_t epoch;                      /* engine epoch at which it last became resident */
+	struct alloc *owner;
+	uint8_t state;
+	uint8_t tier;
+};
+
+struct alloc {
+	uint64_t va;
+	uint64_t req_bytes;
+	uint64_t va_bytes;
+	uint32_t n_chunks;
+	int passthrough;
+	struct chunk *chunks;
+	struct alloc *hnext;       /* hash bucket chain          */
+	struct alloc *prev, *next; /* allocation order           */
+};
+
+struct arena {
+	uint64_t dev_base;  /* device-accessible base address              */
+	void *host_base;    /* host tier: pointer to free; NULL for peers  */
+	CUmemGenericAllocationHandle handle; /* peer tier                   */
+	uint64_t bytes;
+	uint32_t n_slabs, used;
+	uint32_t hint;      /* first word worth scanning                   */
+	uint64_t *bitmap;   /* 1 = slab in use                             */
+	struct arena *next;
+};
+
+struct pool {
+	struct arena *arenas;
+	uint64_t bytes, used;
+	uint64_t capacity; /* 0 = unlimited */
+	int device;        /* peer ordinal, -1 for the host tier */
+};
+
+struct slot {
+	nvs_copy_desc *descs; /* pinned, device-mapped */
+	uint64_t descs_dev;
+	uint32_t n_descs, cap_descs;
+	struct chunk **chunks;
+	uint32_t n_chunks, cap_chunks;
+	CUevent done;
+	int busy;
+};
+
+#define HASH_BITS 12
+#define HASH_SIZE (1u << HASH_BITS)
+
+struct nvs_engine {
+	struct drv d;
+	nvs_engine_config cfg;
+	CUcontext ctx;
+	int device;
+	int n_sms;
+	CUmodule module;
+	CUfunction fn_tma, fn_ldg, fn_fill, fn_verify;
+	CUstream stream;
+	CUevent ev_begin, ev_end;
+	CUdeviceptr counters; /* u32[N_COUNTERS], device memory */
+	uint32_t counter_next;
+	CUdeviceptr scratch;  /* u64 mismatch counter           */
+	struct slot slots[N_SLOTS];
+
+	pthread_mutex_t api_mu; /* outer: serialises the public entry points                   */
+	pthread_mutex_t mu;     /* inner: table, pools, stats (shared with the pinning thread) */
+	struct alloc *buckets[HASH_SIZE];
+	struct alloc *head, *tail;
+	struct pool host_pool;
+	struct pool peer_pools[NVS_MAX_PEERS];
+	uint32_t peer_rr;
+	uint64_t epoch;
+	int resident_mode;
+	nvs_stats st;
+
+	/* background pinning */
+	pthread_t pin_thread;
+	int pin_thread_started;
+	pthread_cond_t pin_cv;
+	int stopping;
+	uint64_t pin_target; /* bytes of host pool we want to have */
+
+	FILE *stats_file;
+};
+#define N_COUNTERS 1024u
+
+static double now_ms(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+static double wall_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_REALTIME, &ts);
+	return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
+static const char *cu_name(nvs_engine *e, CUresult r)
+{
+	const char *n = NULL;
+	if (e->d.GetErrorName && e->d.GetErrorName(r, &n) == CUDA_SUCCESS && n)
+		return n;
+	return "CUDA_ERROR_?";
+}
+
+#define CK(e, call)                                                                        \
+	do {                                                                               \
+		CUresult r_ = (call);                                                      \
+		if (r_ != CUDA_SUCCESS) {                                                  \
+			nvs_warn("engine: %s returned %s (%d) at %s:%d", #call, cu_name(e, r_), \
+				 (int)r_, __FILE__, __LINE__);                             \
+			rc = (int)r_;                                                      \
+			goto out;                                                          \
+		}                                                                          \
+	} while (0)
+
+const char *nvs_engine_version(void)
+{
+	return "nvshare_b200 engine r1 (sm_100a slab copy: tma|ldg|ce)";
+}
+
+const char *nvs_strerror(int rc)
+{
+	switch (rc) {
+	case 0: return "success";
+	case NVS_E_NOT_OURS: return "pointer not owned by the engine";
+	case NVS_E_BAD_ARG: return "bad argument";
+	case NVS_E_NO_DRIVER: return "CUDA driver (libcuda.so.1) or a required entry point is missing";
+	case NVS_E_NO_KERNEL: return "embedded sm_100a kernel image failed to load";
+	case NVS_E_TIMEOUT: return "timed out waiting for HBM to be released";
+	case NVS_E_HOST_OOM: return "backing tier exhausted";
+	case CUDA_ERROR_OUT_OF_MEMORY: return "CUDA_ERROR_OUT_OF_MEMORY";
+	case CUDA_ERROR_NOT_INITIALIZED: return "CUDA_ERROR_NOT_INITIALIZED";
+	default: return rc > 0 ? "CUDA driver error" : "unknown engine error";
+	}
+}
+
+/* ------------------------------------------------------------ config ---- */
+
+static uint64_t env_u64(const char *name, uint64_t dflt)
+{
+	const char *v = getenv(name);
+	if (!v || !*v)
+		return dflt;
+	char *end = NULL;
+	unsigned long long x = strtoull(v, &end, 0);
+	return end == v ? dflt : (uint64_t)x;
+}
+
+static uint32_t parse_variant(const char *v, uint32_t dflt)
+{
+	if (!v || !*v)
+		return dflt;
+	if (!strcasecmp(v, "tma"))
+		return NVS_COPY_TMA;
+	if (!strcasecmp(v, "ldg"))
+		return NVS_COPY_LDG;
+	if (!strcasecmp(v, "ce"))
+		return NVS_COPY_CE;
+	return dflt;
+}
+
+int nvs_engine_default_config(nvs_engine_config *cfg)
+{
+	if (!cfg)
+		return NVS_E_BAD_ARG;
+	memset(cfg, 0, sizeof(*cfg));
+	cfg->struct_size = sizeof(*cfg);
+	cfg->device = -1;
+	cfg->chunk_bytes = env_u64("NVSHARE_CHUNK_MIB", 64) << 20;
+	cfg->small_alloc_bytes = env_u64("NVSHARE_SMALL_ALLOC_KIB", 1024) << 10;
+	cfg->batch_bytes = env_u64("NVSHARE_BATCH_MIB", 1024) << 20;
+	cfg->host_arena_bytes = env_u64("NVSHARE_HOST_ARENA_MIB", 1024) << 20;
+	cfg->evict_variant = parse_variant(getenv("NVSHARE_EVICT_VARIANT"),
+					   parse_variant(getenv("NVSHARE_COPY_VARIANT"), NVS_COPY_TMA));
+	cfg->fetch_variant = parse_variant(getenv("NVSHARE_FETCH_VARIANT"),
+					   parse_variant(getenv("NVSHARE_COPY_VARIANT"), NVS_COPY_TMA));
+	/* B200 probe: 2 CTAs already saturate PCIe Gen5 x16 in one direction
+	 * (52.7 GB/s); 8 leaves head-room when SMs are shared; the peer tier
+	 * (NVLink 5) wants ~74. */
+	cfg->copy_grid = (uint32_t)env_u64("NVSHARE_COPY_GRID", 0);
+	cfg->tma_warps = (uint32_t)env_u64("NVSHARE_TMA_WARPS", 1);
+	cfg->tma_stages = (uint32_t)env_u64("NVSHARE_TMA_STAGES", 6);
+	cfg->tma_tile_bytes = (uint32_t)env_u64("NVSHARE_TMA_TILE_KIB", 32) << 10;
+	cfg->ldg_threads = (uint32_t)env_u64("NVSHARE_LDG_THREADS", 512);
+	cfg->oom_wait_ms = (uint32_t)env_u64("NVSHARE_OOM_WAIT_MS", 120000);
+	cfg->prepin = (uint32_t)env_u64("NVSHARE_PREPIN", 1);
+	cfg->peer_capacity_bytes = env_u64("NVSHARE_PEER_CAPACITY_MIB", 0) << 20;
+	cfg->stats_path = getenv("NVSHARE_STATS_FILE");
+	const char *peers = getenv("NVSHARE_PEERS"); /* "1,2,3" */
+	if (peers && *peers) {
+		char buf[128];
+		snprintf(buf, sizeof(buf), "%s", peers);
+		for (char *tok = strtok(buf, ","); tok && cfg->n_peers < NVS_MAX_PEERS; tok = strtok(NULL, ","))
+			cfg->peers[cfg->n_peers++] = atoi(tok);
+	}
+	return 0;
+}
+
+/* --------------------------------------------------------- ctx guard ---- */
+
+static int ctx_enter(nvs_engine *e)
+{
+	return e->d.CtxPushCurrent(e->ctx) == CUDA_SUCCESS ? 0 : -1;
+}
+
+static void ctx_leave(nvs_engine *e)
+{
+	CUcontext junk;
+	e->d.CtxPopCurrent(&junk);
+}
+
+/* -------------------------------------------------------------- pool ---- */
+
+static int arena_take(struct arena *a, uint32_t n, uint64_t *addr)
+{
+	if (a->n_slabs - a->used < n)
+		return -1;
+	/* first fit over the bitmap; runs never straddle arenas */
+	uint32_t run = 0;
+	for (uint32_t i = a->hint * 64; i < a->n_slabs; ++i) {
+		if (a->bitmap[i >> 6] & (1ull << (i & 63))) {
+			run = 0;
+			continue;
+		}
+		if (++run == n) {
+			uint32_t first = i + 1 - n;
+			for (uint32_t k = first; k <= i; ++k)
+				a->bitmap[k >> 6] |= 1ull << (k & 63);
+			a->used += n;
+			while (a->hint < (a->n_slabs + 63) / 64 && a->bitmap[a->hint] == ~0ull)
+				a->hint++;
+			*addr = a->dev_base + (uint64_t)first * SLAB;
+			return 0;
+		}
+	}
+	return -1;
+}
+
+static int pool_take(struct pool *p, uint32_t n, uint64_t *addr)
+{
+	for (struct arena *a = p->arenas; a; a = a->next)
+		if (arena_take(a, n, addr) == 0) {
+			p->used += (uint64_t)n * SLAB;
+			return 0;
+		}
+	return -1;
+}
+
+static void pool_give(struct pool *p, uint64_t addr, uint32_t n)
+{
+	for (struct arena *a = p->arenas; a; a = a->next) {
+		if (addr < a->dev_base || addr >= a->dev_base + a->bytes)
+			continue;
+		uint32_t first = (uint32_t)((addr - a->dev_base) / SLAB);
+		for (uint32_t k = first; k < first + n; ++k)
+			a->bitmap[k >> 6] &= ~(1ull << (k & 63));
+		a->used -= n;
+		if ((first >> 6) < a->hint)
+			a->hint = first >> 6;
+		p->used -= (uint64_t)n * SLAB;
+		return;
+	}
+}
+
+static struct arena *arena_new(uint64_t bytes)
+{
+	struct arena *a = calloc(1, sizeof(*a));
+	if (!a)
+		return NULL;
+	a->bytes = bytes;
+	a->n_slabs = (uint32_t)(bytes / SLAB);
+	a->bitmap = calloc((a->n_slabs + 63) / 64, sizeof(uint64_t));
+	if (!a->bitmap) {
+		free(a);
+		return NULL;
+	}
+	return a;
+}
+
+/* Pin one more host arena.  Called WITHOUT e->mu (pinning is slow); ctx must be current. */
+static int host_pool_grow(nvs_engine *e)
+{
+	struct arena *a = arena_new(e->cfg.host_arena_bytes);
+	if (!a)
+		return NVS_E_HOST_OOM;
+	void *p = NULL;
+	CUresult r = e->d.MemHostAlloc(&p, a->bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP);
+	if (r != CUDA_SUCCESS) {
+		nvs_warn("engine: cuMemHostAlloc(%" PRIu64 " MiB) failed: %s", a->bytes >> 20, cu_name(e, r));
+		free(a->bitmap);
+		free(a);
+		return NVS_E_HOST_OOM;
+	}
+	CUdeviceptr dp = 0;
+	if (e->d.MemHostGetDevicePointer(&dp, p, 0) != CUDA_SUCCESS)
+		dp = (CUdeviceptr)(uintptr_t)p; /* UVA: identical */
+	a->host_base = p;
+	a->dev_base = dp;
+	pthread_mutex_lock(&e->mu);
+	a->next = e->host_pool.arenas;
+	e->host_pool.arenas = a;
+	e->host_pool.bytes += a->bytes;
+	e->st.host_pool_bytes = e->host_pool.bytes;
+	pthread_mutex_unlock(&e->mu);
+	return 0;
+}
+
+/* Create one arena of peer HBM mapped into this context.  Called with e->mu held. */
+static int peer_pool_grow(nvs_engine *e, int pi)
+{
+	struct pool *p = &e->peer_pools[pi];
+	uint64_t bytes = e->cfg.host_arena_bytes;
+	if (p->capacity && p->bytes + bytes > p->capacity)
+		return NVS_E_HOST_OOM;
+	struct arena *a = arena_new(bytes);
+	if (!a)
+		return NVS_E_HOST_OOM;
+	CUmemAllocationProp prop;
+	memset(&prop, 0, sizeof(prop));
+	prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+	prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	prop.location.id = p->device;
+	CUmemAccessDesc acc[2];
+	memset(acc, 0, sizeof(acc));
+	acc[0].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	acc[0].location.id = e->device;
+	acc[0].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	acc[1].location = prop.location;
+	acc[1].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	CUdeviceptr va = 0;
+	if (e->d.MemCreate(&a->handle, bytes, &prop, 0) != CUDA_SUCCESS)
+		goto fail;
+	if (e->d.MemAddressReserve(&va, bytes, 0, 0, 0) != CUDA_SUCCESS) {
+		e->d.MemRelease(a->handle);
+		goto fail;
+	}
+	if (e->d.MemMap(va, bytes, 0, a->handle, 0) != CUDA_SUCCESS ||
+	    e->d.MemSetAccess(va, bytes, acc, 2) != CUDA_SUCCESS) {
+		e->d.MemUnmap(va, bytes);
+		e->d.MemAddressFree(va, bytes);
+		e->d.MemRelease(a->handle);
+		goto fail;
+	}
+	a->dev_base = va;
+	a->next = p->arenas;
+	p->arenas = a;
+	p->bytes += bytes;
+	e->st.peer_pool_bytes += bytes;
+	return 0;
+fail:
+	free(a->bitmap);
+	free(a);
+	return NVS_E_HOST_OOM;
+}
+
+/* Find backing for a chunk: peers first (striped), then pinned host.  e->mu held. */
+static int backing_assign(nvs_engine *e, struct chunk *c)
+{
+	if (c->backing)
+		return 0;
+	const uint32_t n = (uint32_t)(c->bytes / SLAB);
+	for (int t = 0; t < e->cfg.n_peers; ++t) {
+		int pi = (int)((e->peer_rr + (uint32_t)t) % (uint32_t)e->cfg.n_peers);
+		struct pool *p = &e->peer_pools[pi];
+		if (pool_take(p, n, &c->backing) == 0 ||
+		    (peer_pool_grow(e, pi) == 0 && pool_take(p, n, &c->backing) == 0)) {
+			c->tier = (uint8_t)(TIER_PEER0 + pi);
+			e->peer_rr = (uint32_t)pi + 1;
+			e->st.peer_pool_used += c->bytes;
+			return 0;
+		}
+	}
+	while (pool_take(&e->host_pool, n, &c->backing) != 0) {
+		/* pool empty: pin inline (slow path; the background thread normally keeps ahead) */
+		pthread_mutex_unlock(&e->mu);
+		int rc = host_pool_grow(e);
+		pthread_mutex_lock(&e->mu);
+		if (rc != 0)
+			return rc;
+	}
+	c->tier = TIER_HOST;
+	e->st.host_pool_used = e->host_pool.used;
+	return 0;
+}
+
+static void backing_release(nvs_engine *e, struct chunk *c)
+{
+	if (!c->backing)
+		return;
+	const uint32_t n = (uint32_t)(c->bytes / SLAB);
+	if (c->tier == TIER_HOST) {
+		pool_give(&e->host_pool, c->backing, n);
+		e->st.host_pool_used = e->host_pool.used;
+	} else if (c->tier >= TIER_PEER0) {
+		pool_give(&e->peer_pools[c->tier - TIER_PEER0], c->backing, n);
+		e->st.peer_pool_used -= c->bytes;
+	}
+	c->backing = 0;
+	c->tier = TIER_NONE;
+}
+
+static void *pin_thread_main(void *arg)
+{
+	nvs_engine *e = arg;
+	if (ctx_enter(e) != 0)
+		return NULL;
+	pthread_mutex_lock(&e->mu);
+	while (!e->stopping) {
+		if (e->host_pool.bytes >= e->pin_target) {
+			pthread_cond_wait(&e->pin_cv, &e->mu);
+			continue;
+		}
+		pthread_mutex_unlock(&e->mu);
+		int rc = host_pool_grow(e);
+		pthread_mutex_lock(&e->mu);
+		if (rc != 0) /* out of pinnable memory: stop trying, evict will report it */
+			e->pin_target = e->host_pool.bytes;
+	}
+	pthread_mutex_unlock(&e->mu);
+	ctx_leave(e);
+	return NULL;
+}
+
+/* ----------------------------------------------------------- table ------ */
+
+static unsigned hash_va(uint64_t va)
+{
+	return (unsigned)((va >> NVS_SLAB_SHIFT) * 0x9E3779B97F4A7C15ull >> (64 - HASH_BITS));
+}
+
+static struct alloc *table_find(nvs_engine *e, uint64_t va)
+{
+	for (struct alloc *a = e->buckets[hash_va(va)]; a; a = a->hnext)
+		if (a->va == va)
+			return a;
+	return NULL;
+}
+
+static void table_insert(nvs_engine *e, struct alloc *a)
+{
+	unsigned h = hash_va(a->va);
+	a->hnext = e->buckets[h];
+	e->buckets[h] = a;
+	a->prev = e->tail;
+	a->next = NULL;
+	if (e->tail)
+		e->tail->next = a;
+	else
+		e->head = a;
+	e->tail = a;
+	e->st.n_allocs++;
+	e->st.requested_bytes += a->req_bytes;
+}
+
+static void table_remove(nvs_engine *e, struct alloc *a)
+{
+	struct alloc **pp = &e->buckets[hash_va(a->va)];
+	while (*pp && *pp != a)
+		pp = &(*pp)->hnext;
+	if (*pp)
+		*pp = a->hnext;
+	if (a->prev)
+		a->prev->next = a->next;
+	else
+		e->head = a->next;
+	if (a->next)
+		a->next->prev = a->prev;
+	else
+		e->tail = a->prev;
+	e->st.n_allocs--;
+	e->st.requested_bytes -= a->req_bytes;
+}
+
+/* ------------------------------------------------------- map / unmap ---- */
+
+static void state_account(nvs_engine *e, struct chunk *c, int new_state)
+{
+	uint64_t *from = c->state == CH_RESIDENT ? &e->st.resident_bytes
+			 : c->state == CH_SWAPPED ? &e->st.swapped_bytes
+						  : &e->st.unbacked_bytes;
+	uint64_t *to = new_state == CH_RESIDENT ? &e->st.resident_bytes
+		       : new_state == CH_SWAPPED ? &e->st.swapped_bytes
+						 : &e->st.unbacked_bytes;
+	*from -= c->bytes;
+	*to += c->bytes;
+	c->state = (uint8_t)new_state;
+}
+
+/* Give a chunk physical HBM.  Retries while another process is still releasing. */
+static int chunk_map(nvs_engine *e, struct chunk *c, double *wait_ms)
+{
+	CUmemAllocationProp prop;
+	memset(&prop, 0, sizeof(prop));
+	prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+	prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	prop.location.id = e->device;
+	CUmemAccessDesc acc;
+	memset(&acc, 0, sizeof(acc));
+	acc.location = prop.location;
+	acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+
+	double t0 = now_ms(), warned = 0;
+	for (;;) {
+		CUresult r = e->d.MemCreate(&c->handle, c->bytes, &prop, 0);
+		if (r == CUDA_SUCCESS)
+			break;
+		if (r != CUDA_ERROR_OUT_OF_MEMORY) {
+			nvs_warn("engine: cuMemCreate failed: %s", cu_name(e, r));
+			return (int)r;
+		}
+		double waited = now_ms() - t0;
+		if (waited > e->cfg.oom_wait_ms) {
+			nvs_warn("engine: HBM still exhausted after %.0f ms", waited);
+			return NVS_E_TIMEOUT;
+		}
+		if (!warned && waited > 2000) {
+			nvs_debug("engine: waiting for HBM to be released by another client");
+			warned = 1;
+		}
+		usleep(500);
+	}
+	if (wait_ms)
+		*wait_ms += now_ms() - t0;
+	CUresult r = e->d.MemMap(c->va, c->bytes, 0, c->handle, 0);
+	if (r == CUDA_SUCCESS)
+		r = e->d.MemSetAccess(c->va, c->bytes, &acc, 1);
+	if (r != CUDA_SUCCESS) {
+		nvs_warn("engine: cuMemMap/cuMemSetAccess failed: %s", cu_name(e, r));
+		e->d.MemUnmap(c->va, c->bytes);
+		e->d.MemRelease(c->handle);
+		return (int)r;
+	}
+	return 0;
+}
+
+static int chunk_unmap(nvs_engine *e, struct chunk *c)
+{
+	CUresult r = e->d.MemUnmap(c->va, c->bytes);
+	if (r == CUDA_SUCCESS)
+		r = e->d.MemRelease(c->handle);
+	if (r != CUDA_SUCCESS)
+		nvs_warn("engine: cuMemUnmap/cuMemRelease failed: %s", cu_name(e, r));
+	c->handle = 0;
+	return (int)r;
+}
+
+/* ------------------------------------------------------------ launch ---- */
+
+static uint32_t grid_for(nvs_engine *e, uint32_t want, int peer_traffic)
+{
+	if (want)
+		return want;
+	if (e->cfg.copy_grid)
+		return e->cfg.copy_grid;
+	return peer_traffic ? (uint32_t)(e->n_sms / 2) : 8u;
+}
+
+/* Enqueue one copy of n descriptors (device-visible array) on e->stream. */
+static int launch_descs(nvs_engine *e, uint64_t descs_dev, const nvs_copy_desc *descs_host, uint32_t n,
+			uint32_t variant, uint32_t grid)
+{
+	int rc = 0;
+	if (n == 0)
+		return 0;
+	if (variant == NVS_COPY_CE) {
+		for (uint32_t i = 0; i < n; ++i)
+			CK(e, e->d.MemcpyAsync(descs_host[i].dst, descs_host[i].src, descs_host[i].bytes, e->stream));
+		return 0;
+	}
+	if (e->counter_next == N_COUNTERS) {
+		CK(e, e->d.MemsetD32Async(e->counters, 0, N_COUNTERS, e->stream));
+		e->counter_next = 0;
+	}
+	CUdeviceptr counter = e->counters + 4ull * e->counter_next++;
+	uint32_t n_descs = n;
+	if (variant == NVS_COPY_TMA) {
+		uint32_t tile = e->cfg.tma_tile_bytes, stages = e->cfg.tma_stages, warps = e->cfg.tma_warps;
+		void *params[] = {&descs_dev, &n_descs, &counter, &tile, &stages};
+		CK(e, e->d.LaunchKernel(e->fn_tma, grid, 1, 1, 32 * warps, 1, 1, warps * stages * tile,
+					e->stream, params, NULL));
+	} else {
+		void *params[] = {&descs_dev, &n_descs, &counter};
+		CK(e, e->d.LaunchKernel(e->fn_ldg, grid, 1, 1, e->cfg.ldg_threads, 1, 1, 0, e->stream, params,
+					NULL));
+	}
+	e->st.kernel_launches_total++;
+out:
+	return rc;
+}
+
+static void slot_reset(struct slot *s)
+{
+	s->n_descs = 0;
+	s->n_chunks = 0;
+}
+
+static int slot_push_chunk(struct slot *s, struct chunk *c, int to_backing, uint32_t variant)
+{
+	if (s->n_chunks == s->cap_chunks)
+		return -1;
+	s->chunks[s->n_chunks++] = c;
+	if (variant == NVS_COPY_CE) {
+		/* backing of a chunk is contiguous: one copy-engine call per chunk */
+		if (s->n_descs == s->cap_descs)
+			return -1;
+		nvs_copy_desc *d = &s->descs[s->n_descs++];
+		d->src = to_backing ? c->va : c->backing;
+		d->dst = to_backing ? c->backing : c->va;
+		d->bytes = c->bytes;
+		d->tag = c->va >> NVS_SLAB_SHIFT;
+		return 0;
+	}
+	for (uint64_t off = 0; off < c->bytes; off += SLAB) {
+		if (s->n_descs == s->cap_descs)
+			return -1;
+		nvs_copy_desc *d = &s->descs[s->n_descs++];
+		d->src = (to_backing ? c->va : c->backing) + off;
+		d->dst = (to_backing ? c->backing : c->va) + off;
+		d->bytes = SLAB;
+		d->tag = (c->va + off) >> NVS_SLAB_SHIFT;
+	}
+	return 0;
+}
+
+/* ------------------------------------------------------------- evict ---- */
+
+static int cmp_chunk_lru(const void *a, const void *b)
+{
+	const struct chunk *x = *(struct chunk *const *)a, *y = *(struct chunk *const *)b;
+	if (x->epoch != y->epoch)
+		return x->epoch < y->epoch ? -1 : 1;
+	return x->va < y->va ? -1 : x->va > y->va;
+}
+
+static void report_emit(nvs_engine *e, const char *what, const nvs_xfer_report *r)
+{
+	nvs_debug("engine: %s %" PRIu64 " MiB in %.1f ms (copy %.1f ms = %.1f GB/s, map %.1f ms, wait %.1f ms)",
+		  what, r->bytes >> 20, r->wall_ms, r->copy_ms,
+		  r->copy_ms > 0 ? r->bytes / 1e6 / r->copy_ms : 0.0, r->map_ms, r->wait_ms);
+	if (!e->stats_file)
+		return;
+	fprintf(e->stats_file,
+		"{\"op\":\"%s\",\"t\":%.6f,\"pid\":%d,\"bytes\":%" PRIu64 ",\"slabs\":%" PRIu64
+		",\"chunks\":%" PRIu64 ",\"launches\":%" PRIu64 ",\"wall_ms\":%.3f,\"copy_ms\":%.3f,"
+		"\"map_ms\":%.3f,\"wait_ms\":%.3f,\"host_bytes\":%" PRIu64 ",\"peer_bytes\":%" PRIu64 "}\n",
+		what, wall_s(), (int)getpid(), r->bytes, r->slabs, r->chunks, r->launches, r->wall_ms, r->copy_ms,
+		r->map_ms, r->wait_ms, r->host_bytes, r->peer_bytes);
+	fflush(e->stats_file);
+}
+
+/* wait for a slot's copy, then give its chunks' HBM back */
+static int evict_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
+{
+	int rc = 0;
+	if (!s->busy)
+		return 0;
+	CK(e, e->d.EventSynchronize(s->done));
+	double t0 = now_ms();
+	for (uint32_t i = 0; i < s->n_chunks; ++i) {
+		struct chunk *c = s->chunks[i];
+		int r = chunk_unmap(e, c);
+		if (r != 0 && rc == 0)
+			rc = r;
+		state_account(e, c, CH_SWAPPED);
+		rep->chunks++;
+	}
+	rep->map_ms += now_ms() - t0;
+out:
+	s->busy = 0;
+	slot_reset(s);
+	return rc;
+}
+
+int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
+{
+	nvs_xfer_report rep;
+	memset(&rep, 0, sizeof(rep));
+	if (!e)
+		return NVS_E_BAD_ARG;
+	int rc = 0;
+	struct chunk **victims = NULL;
+	double t_begin = now_ms();
+	if (ctx_enter(e) != 0)
+		return CUDA_ERROR_INVALID_CONTEXT;
+	pthread_mutex_lock(&e->api_mu);
+	pthread_mutex_lock(&e->mu);
+
+	/* victims: resident chunks, least recently fetched first */
+	size_t n_res = 0, n_vict = 0;
+	for (struct alloc *a = e->head; a; a = a->next)
+		if (!a->passthrough)
+			n_res += a->n_chunks;
+	victims = malloc((n_res ? n_res : 1) * sizeof(*victims));
+	if (!victims) {
+		rc = NVS_E_HOST_OOM;
+		goto out;
+	}
+	for (struct alloc *a = e->head; a; a = a->next) {
+		if (a->passthrough)
+			continue;
+		for (uint32_t i = 0; i < a->n_chunks; ++i)
+			if (a->chunks[i].state == CH_RESIDENT)
+				victims[n_vict++] = &a->chunks[i];
+	}
+	qsort(victims, n_vict, sizeof(*victims), cmp_chunk_lru);
+	if (min_bytes) {
+		uint64_t acc = 0;
+		size_t k = 0;
+		while (k < n_vict && acc < min_bytes)
+			acc += victims[k++]->bytes;
+		n_vict = k;
+	}
+
+	const uint32_t variant = e->cfg.evict_variant;
+	int started = 0;
+	unsigned batch_no = 0;
+	size_t i = 0;
+	while (i < n_vict) {
+		struct slot *s = &e->slots[batch_no % N_SLOTS];
+		if ((rc = evict_retire(e, s, &rep)) != 0)
+			goto out;
+		uint64_t batch = 0;
+		int peer_traffic = 0;
+		while (i < n_vict && batch < e->cfg.batch_bytes) {
+			struct chunk *c = victims[i];
+			if ((rc = backing_assign(e, c)) != 0)
+				goto out;
+			if (slot_push_chunk(s, c, 1, variant) != 0)
+				break;
+			batch += c->bytes;
+			peer_traffic |= c->tier >= TIER_PEER0;
+			if (c->tier == TIER_HOST)
+				rep.host_bytes += c->bytes;
+			else
+				rep.peer_bytes += c->bytes;
+			++i;
+		}
+		if (!started) {
+			CK(e, e->d.EventRecord(e->ev_begin, e->stream));
+			started = 1;
+		}
+		if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, variant,
+				       grid_for(e, 0, peer_traffic))) != 0)
+			goto out;
+		CK(e, e->d.EventRecord(s->done, e->stream));
+		s->busy = 1;
+		rep.launches += variant == NVS_COPY_CE ? s->n_descs : 1;
+		rep.bytes += batch;
+		rep.slabs += batch / SLAB;
+		batch_no++;
+	}
+	if (started)
+		CK(e, e->d.EventRecord(e->ev_end, e->stream));
+	for (unsigned k = 0; k < N_SLOTS; ++k) {
+		int r = evict_retire(e, &e->slots[(batch_no + k) % N_SLOTS], &rep);
+		if (r != 0 && rc == 0)
+			rc = r;
+	}
+	if (started && rc == 0) {
+		float ms = 0;
+		CK(e, e->d.EventSynchronize(e->ev_end));
+		CK(e, e->d.EventElapsedTime(&ms, e->ev_begin, e->ev_end));
+		rep.copy_ms = ms;
+	}
+	if (min_bytes == 0)
+		e->resident_mode = 0; /* everything is out: the owner no longer holds the GPU */
+	e->st.n_evicts++;
+	e->st.evicted_bytes_total += rep.bytes;
+out:
+	if (rc != 0) /* never leave copies in flight behind an error */
+		e->d.StreamSynchronize(e->stream);
+	for (unsigned k = 0; k < N_SLOTS; ++k) {
+		e->slots[k].busy = 0;
+		slot_reset(&e->slots[k]);
+	}
+	rep.wall_ms = now_ms() - t_begin;
+	pthread_mutex_unlock(&e->mu);
+	pthread_mutex_unlock(&e->api_mu);
+	ctx_leave(e);
+	free(victims);
+	if (rc == 0 && rep.bytes)
+		report_emit(e, "evict", &rep);
+	if (rep_out)
+		*rep_out = rep;
+	return rc;
+}
+
+/* ------------------------------------------------------------- fetch ---- */
+
+int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
+{
+	nvs_xfer_report rep;
+	memset(&rep, 0, sizeof(rep));
+	if (!e)
+		return NVS_E_BAD_ARG;
+	int rc = 0;
+	double t_begin = now_ms();
+	if (ctx_enter(e) != 0)
+		return CUDA_ERROR_INVALID_CONTEXT;
+	pthread_mutex_lock(&e->api_mu);
+	pthread_mutex_lock(&e->mu);
+	e->epoch++;
+
+	const uint32_t variant = e->cfg.fetch_variant;
+	int started = 0;
+	unsigned batch_no = 0;
+	struct alloc *a = e->head;
+	uint32_t ci = 0;
+	for (;;) {
+		/* next batch of non-resident chunks, allocation order */
+		struct slot *s = &e->slots[batch_no % N_SLOTS];
+		if (s->busy) {
+			CK(e, e->d.EventSynchronize(s->done));
+			s->busy = 0;
+		}
+		slot_reset(s);
+		uint64_t batch = 0, copy_bytes = 0;
+		int peer_traffic = 0;
+		double t0 = now_ms();
+		while (a && batch < e->cfg.batch_bytes) {
+			if (a->passthrough || ci >= a->n_chunks) {
+				a = a->next;
+				ci = 0;
+				continue;
+			}
+			struct chunk *c = &a->chunks[ci];
+			if (c->state == CH_RESIDENT) {
+				++ci;
+				continue;
+			}
+			if (s->n_chunks == s->cap_chunks || s->n_descs + c->bytes / SLAB > s->cap_descs)
+				break;
+			double w = 0;
+			if ((rc = chunk_map(e, c, &w)) != 0)
+				goto out;
+			rep.wait_ms += w;
+			rep.chunks++;
+			if (c->state == CH_SWAPPED) {
+				slot_push_chunk(s, c, 0, variant);
+				copy_bytes += c->bytes;
+				peer_traffic |= c->tier >= TIER_PEER0;
+				if (c->tier == TIER_HOST)
+					rep.host_bytes += c->bytes;
+				else
+					rep.peer_bytes += c->bytes;
+			} /* UNBACKED: map only, nothing to copy */
+			c->epoch = e->epoch;
+			state_account(e, c, CH_RESIDENT);
+			batch += c->bytes;
+			++ci;
+		}
+		rep.map_ms += now_ms() - t0;
+		if (batch == 0) {
+			if (a) /* a chunk that cannot fit an empty slot: geometry bug */
+				rc = NVS_E_BAD_ARG;
+			break;
+		}
+		if (s->n_descs) {
+			if (!started) {
+				CK(e, e->d.EventRecord(e->ev_begin, e->stream));
+				started = 1;
+			}
+			if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, variant,
+					       grid_for(e, 0, peer_traffic))) != 0)
+				goto out;
+			CK(e, e->d.EventRecord(s->done, e->stream));
+			s->busy = 1;
+			rep.launches += variant == NVS_COPY_CE ? s->n_descs : 1;
+			rep.bytes += copy_bytes;
+			rep.slabs += copy_bytes / SLAB;
+		}
+		batch_no++;
+	}
+	if (started) {
+		float ms = 0;
+		CK(e, e->d.EventRecord(e->ev_end, e->stream));
+		CK(e, e->d.EventSynchronize(e->ev_end));
+		CK(e, e->d.EventElapsedTime(&ms, e->ev_begin, e->ev_end));
+		rep.copy_ms = ms;
+	}
+	e->resident_mode = 1;
+	e->st.n_fetches++;
+	e->st.fetched_bytes_total += rep.bytes;
+out:
+	if (rc != 0)
+		e->d.StreamSynchronize(e->stream);
+	for (unsigned k = 0; k < N_SLOTS; ++k) {
+		e->slots[k].busy = 0;
+		slot_reset(&e->slots[k]);
+	}
+	rep.map_ms -= rep.wait_ms;
+	if (rep.map_ms < 0)
+		rep.map_ms = 0;
+	rep.wall_ms = now_ms() - t_begin;
+	pthread_mutex_unlock(&e->mu);
+	pthread_mutex_unlock(&e->api_mu);
+	ctx_leave(e);
+	if (rc == 0 && (rep.bytes || rep.chunks))
+		report_emit(e, "fetch", &rep);
+	if (rep_out)
+		*rep_out = rep;
+	return rc;
+}
+
+/* ------------------------------------------------------ alloc / free ---- */
+
+void nvs_set_resident_mode(nvs_engine *e, int holds_lock)
+{
+	if (!e)
+		return;
+	pthread_mutex_lock(&e->mu);
+	e->resident_mode = holds_lock != 0;
+	pthread_mutex_unlock(&e->mu);
+}
+
+int nvs_alloc(nvs_engine *e, uint64_t *dptr, uint64_t bytes)
+{
+	if (!e || !dptr)
+		return NVS_E_BAD_ARG;
+	if (bytes == 0)
+		return CUDA_ERROR_INVALID_VALUE;
+	int rc = 0;
+	struct alloc *a = calloc(1, sizeof(*a));
+	if (!a)
+		return CUDA_ERROR_OUT_OF_MEMORY;
+	if (ctx_enter(e) != 0) {
+		free(a);
+		return CUDA_ERROR_INVALID_CONTEXT;
+	}
+	pthread_mutex_lock(&e->api_mu);
+	pthread_mutex_lock(&e->mu);
+	a->req_bytes = bytes;
+
+	if (bytes < e->cfg.small_alloc_bytes) {
+		/* not worth a 2 MiB granule: stays ordinary (always resident) device memory */
+		CUdeviceptr p = 0;
+		CUresult r = e->d.MemAlloc(&p, bytes);
+		if (r != CUDA_SUCCESS) {
+			rc = (int)r;
+			goto out;
+		}
+		a->va = p;
+		a->va_bytes = bytes;
+		a->passthrough = 1;
+		e->st.passthrough_bytes += bytes;
+		table_insert(e, a);
+		*dptr = p;
+		a = NULL;
+		goto out;
+	}
+
+	a->va_bytes = (bytes + SLAB - 1) & ~(SLAB - 1);
+	a->n_chunks = (uint32_t)((a->va_bytes + e->cfg.chunk_bytes - 1) / e->cfg.chunk_bytes);
+	a->chunks = calloc(a->n_chunks, sizeof(struct chunk));
+	if (!a->chunks) {
+		rc = CUDA_ERROR_OUT_OF_MEMORY;
+		goto out;
+	}
+	CUdeviceptr va = 0;
+	CUresult r = e->d.MemAddressReserve(&va, a->va_bytes, 0, 0, 0);
+	if (r != CUDA_SUCCESS) {
+		rc = (int)r;
+		goto out;
+	}
+	a->va = va;
+	for (uint32_t i = 0; i < a->n_chunks; ++i) {
+		struct chunk *c = &a->chunks[i];
+		c->va = va + (uint64_t)i * e->cfg.chunk_bytes;
+		uint64_t left = a->va_bytes - (uint64_t)i * e->cfg.chunk_bytes;
+		c->bytes = left < e->cfg.chunk_bytes ? left : e->cfg.chunk_bytes;
+		c->owner = a;
+		c->state = CH_UNBACKED;
+		e->st.unbacked_bytes += c->bytes;
+	}
+	if (e->resident_mode) {
+		for (uint32_t i = 0; i < a->n_chunks; ++i) {
+			struct chunk *c = &a->chunks[i];
+			if ((rc = chunk_map(e, c, NULL)) != 0) {
+				for (uint32_t k = 0; k < i; ++k) {
+					chunk_unmap(e, &a->chunks[k]);
+					state_account(e, &a->chunks[k], CH_UNBACKED);
+				}
+				for (uint32_t k = 0; k < a->n_chunks; ++k)
+					e->st.unbacked_bytes -= a->chunks[k].bytes;
+				e->d.MemAddressFree(va, a->va_bytes);
+				if (rc == NVS_E_TIMEOUT)
+					rc = CUDA_ERROR_OUT_OF_MEMORY;
+				goto out;
+			}
+			c->epoch = e->epoch;
+			state_account(e, c, CH_RESIDENT);
+		}
+	}
+	e->st.va_bytes += a->va_bytes;
+	table_insert(e, a);
+	*dptr = va;
+	/* keep the pinned pool ahead of what may have to be swapped out */
+	if (e->cfg.prepin && e->cfg.n_peers == 0) {
+		e->pin_target += a->va_bytes;
+		pthread_cond_signal(&e->pin_cv);
+	}
+	a = NULL;
+out:
+	pthread_mutex_unlock(&e->mu);
+	pthread_mutex_unlock(&e->api_mu);
+	ctx_leave(e);
+	if (a) {
+		free(a->chunks);
+		free(a);
+	}
+	return rc;
+}
+
+int nvs_free(nvs_engine *e, uint64_t dptr)
+{
+	return nvs_free_sized(e, dptr, NULL);
+}
+
+int nvs_free_sized(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes)
+{
+	if (!e)
+		return NVS_E_BAD_ARG;
+	int rc = 0;
+	if (ctx_enter(e) != 0)
+		return CUDA_ERROR_INVALID_CONTEXT;
+	pthread_mutex_lock(&e->api_mu);
+	pthread_mutex_lock(&e->mu);
+	struct alloc *a = table_find(e, dptr);
+	if (!a) {
+		rc = NVS_E_NOT_OURS;
+		goto out;
+	}
+	if (req_bytes)
+		*req_bytes = a->req_bytes;
+	if (a->passthrough) {
+		CUresult r = e->d.MemFree(a->va);
+		if (r != CUDA_SUCCESS) {
+			rc = (int)r;
+			goto out;
+		}
+		e->st.passthrough_bytes -= a->req_bytes;
+	} else {
+		for (uint32_t i = 0; i < a->n_chunks; ++i) {
+			struct chunk *c = &a->chunks[i];
+			if (c->state == CH_RESIDENT)
+				chunk_unmap(e, c);
+			backing_release(e, c);
+			uint64_t *ctr = c->state == CH_RESIDENT ? &e->st.resident_bytes
+					: c->state == CH_SWAPPED ? &e->st.swapped_bytes
+								 : &e->st.unbacked_bytes;
+			*ctr -= c->bytes;
+		}
+		e->d.MemAddressFree(a->va, a->va_bytes);
+		e->st.va_bytes -= a->va_bytes;
+		if (e->cfg.prepin && e->cfg.n_peers == 0 && e->pin_target >= a->va_bytes)
+			e->pin_target -= a->va_bytes;
+	}
+	table_remove(e, a);
+	free(a->chunks);
+	free(a);
+out:
+	pthread_mutex_unlock(&e->mu);
+	pthread_mutex_unlock(&e->api_mu);
+	ctx_leave(e);
+	return rc;
+}
+
+int nvs_get_stats(nvs_engine *e, nvs_stats *out)
+{
+	if (!e || !out)
+		return NVS_E_BAD_ARG;
+	pthread_mutex_lock(&e->mu);
+	e->st.host_pool_bytes = e->host_pool.bytes;
+	e->st.host_pool_used = e->host_pool.used;
+	*out = e->st;
+	pthread_mutex_unlock(&e->mu);
+	return 0;
+}
+
+/* ------------------------------------------------- raw kernel access ---- */
+
+int nvs_copy_slabs(nvs_engine *e, const nvs_copy_desc *descs, uint32_t n, uint32_t variant, uint32_t grid,
+		   float *ms_out)
+{
+	if (!e || (!descs && n))
+		return NVS_E_BAD_ARG;
+	for (uint32_t i = 0; i < n; ++i) {
+		if ((descs[i].src | descs[i].dst) & 15ull)
+			return NVS_E_BAD_ARG;
+		if (variant == NVS_COPY_TMA && (descs[i].bytes & 15ull))
+			return NVS_E_BAD_ARG;
+	}
+	int rc = 0;
+	void *staging = NULL;
+	if (ctx_enter(e) != 0)
+		return CUDA_ERROR_INVALID_CONTEXT;
+	pthread_mutex_lock(&e->api_mu);
+	pthread_mutex_lock(&e->mu);
+	const size_t bytes = (size_t)n * sizeof(nvs_copy_desc);
+	CUdeviceptr dev = 0;
+	if (n) {
+		CK(e, e->d.MemHostAlloc(&staging, bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+		memcpy(staging, descs, bytes);
+		if (e->d.MemHostGetDevicePointer(&dev, staging, 0) != CUDA_SUCCESS)
+			dev = (CUdeviceptr)(uintptr_t)staging;
+	}
+	CK(e, e->d.EventRecord(e->ev_begin, e->stream));
+	if ((rc = launch_descs(e, dev, staging, n, variant, grid_for(e, grid, 0))) != 0)
+		goto out;
+	CK(e, e->d.EventRecord(e->ev_end, e->stream));
+	CK(e, e->d.EventSynchronize(e->ev_end));
+	if (ms_out)
+		CK(e, e->d.EventElapsedTime(ms_out, e->ev_begin, e->ev_end));
+out:
+	if (rc != 0)
+		e->d.StreamSynchronize(e->stream);
+	if (staging)
+		e->d.MemFreeHost(staging);
+	pthread_mutex_unlock(&e->mu);
+	pthread_mutex_unlock(&e->api_mu);
+	ctx_leave(e);
+	return rc;
+}
+
+int nvs_pattern_fill(nvs_engine *e, uint64_t addr, uint64_t n_words, uint64_t first_index, uint64_t seed)
+{
+	if (!e || (addr & 7))
+		return NVS_E_BAD_ARG;
+	int rc = 0;
+	if (ctx_enter(e) != 0)
+		return CUDA_ERROR_INVALID_CONTEXT;
+	pthread_mutex_lock(&e->api_mu);
+	pthread_mutex_lock(&e->mu);
+	void *params[] = {&addr, &n_words, &first_index, &seed};
+	CK(e, e->d.LaunchKernel(e->fn_fill, (unsigned)e->n_sms * 8, 1, 1, 256, 1, 1, 0, e->stream, params, NULL));
+	CK(e, e->d.StreamSynchronize(e->stream));
+out:
+	pthread_mutex_unlock(&e->mu);
+	pthread_mutex_unlock(&e->api_mu);
+	ctx_leave(e);
+	return rc;
+}
+
+int nvs_pattern_verify(nvs_engine *e, uint64_t addr, uint64_t n_words, uint64_t first_index, uint64_t seed,
+		       uint64_t *mismatches)
+{
+	if (!e || (addr & 7) || !mismatches)
+		return NVS_E_BAD_ARG;
+	int rc = 0;
+	if (ctx_enter(e) != 0)
+		return CUDA_ERROR_INVALID_CONTEXT;
+	pthread_mutex_lock(&e->api_mu);
+	pthread_mutex_lock(&e->mu);
+	CUdeviceptr out = e->scratch;
+	uint64_t *host = NULL;
+	CK(e, e->d.MemHostAlloc((void **)&host, 8, CU_MEMHOSTALLOC_PORTABLE));
+	CK(e, e->d.MemsetD32Async(out, 0, 2, e->stream));
+	void *params[] = {&addr, &n_words, &first_index, &seed, &out};
+	CK(e, e->d.LaunchKernel(e->fn_verify, (unsigned)e->n_sms * 8, 1, 1, 256, 1, 1, 0, e->stream, params, NULL));
+	CK(e, e->d.MemcpyAsync((CUdeviceptr)(uintptr_t)host, out, 8, e->stream));
+	CK(e, e->d.StreamSynchronize(e->stream));
+	*mismatches = *host;
+out:
+	if (host)
+		e->d.MemFreeHost(host);
+	pthread_mutex_unlock(&e->mu);
+	pthread_mutex_unlock(&e->api_mu);
+	ctx_leave(e);
+	return rc;
+}
+
+/* ---------------------------------------------------- create/destroy ---- */
+
+static void slots_free(nvs_engine *e)
+{
+	for (unsigned k = 0; k < N_SLOTS; ++k) {
+		struct slot *s = &e->slots[k];
+		if (s->descs)
+			e->d.MemFreeHost(s->descs);
+		if (s->done)
+			e->d.EventDestroy(s->done);
+		free(s->chunks);
+		memset(s, 0, sizeof(*s));
+	}
+}
+
+int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
+{
+	if (!out)
+		return NVS_E_BAD_ARG;
+	*out = NULL;
+	nvs_engine *e = calloc(1, sizeof(*e));
+	if (!e)
+		return CUDA_ERROR_OUT_OF_MEMORY;
+	int rc = 0;
+	int ctx_pushed = 0;
+	if (cfg_in && cfg_in->struct_size == sizeof(e->cfg))
+		e->cfg = *cfg_in;
+	else if (cfg_in)
+		{ free(e); return NVS_E_BAD_ARG; }
+	else
+		nvs_engine_default_config(&e->cfg);
+	if (getenv("NVSHARE_DEBUG"))
+		nvs_debug_enabled = 1;
+
+	/* sanity of geometry */
+	if (e->cfg.chunk_bytes < SLAB || (e->cfg.chunk_bytes & (SLAB - 1)) || e->cfg.host_arena_bytes < e->cfg.chunk_bytes ||
+	    (e->cfg.host_arena_bytes & (SLAB - 1)) || e->cfg.tma_warps == 0 || e->cfg.tma_warps > 8 ||
+	    e->cfg.tma_stages < 2 || e->cfg.tma_stages > 8 || (e->cfg.tma_tile_bytes & 15) || e->cfg.tma_tile_bytes == 0 ||
+	    (uint64_t)e->cfg.tma_warps * e->cfg.tma_stages * e->cfg.tma_tile_bytes > 200u * 1024u ||
+	    e->cfg.ldg_threads == 0 || e->cfg.ldg_threads > 1024 || (e->cfg.ldg_threads & 31) ||
+	    e->cfg.n_peers < 0 || e->cfg.n_peers > NVS_MAX_PEERS) {
+		free(e);
+		return NVS_E_BAD_ARG;
+	}
+	if (e->cfg.batch_bytes < e->cfg.chunk_bytes)
+		e->cfg.batch_bytes = e->cfg.chunk_bytes;
+
+	nvs_resolve_fn resolve = e->cfg.resolve ? e->cfg.resolve : default_resolve;
+	for (size_t i = 0; i < sizeof(DRV_SYMS) / sizeof(DRV_SYMS[0]); ++i) {
+		void *p = resolve(DRV_SYMS[i].name);
+		if (!p) {
+			nvs_warn("engine: driver entry point %s not found", DRV_SYMS[i].name);
+			free(e);
+			return NVS_E_NO_DRIVER;
+		}
+		memcpy((char *)&e->d + DRV_SYMS[i].off, &p, sizeof(p));
+	}
+	pthread_mutex_init(&e->api_mu, NULL);
+	pthread_mutex_init(&e->mu, NULL);
+	pthread_cond_init(&e->pin_cv, NULL);
+
+	CK(e, e->d.CtxGetCurrent(&e->ctx));
+	if (!e->ctx) {
+		rc = CUDA_ERROR_INVALID_CONTEXT;
+		goto out;
+	}
+	CK(e, e->d.CtxPushCurrent(e->ctx));
+	ctx_pushed = 1;
+	CUdevice dev;
+	CK(e, e->d.CtxGetDevice(&dev));
+	e->device = e->cfg.device >= 0 ? e->cfg.device : (int)dev;
+	CK(e, e->d.DeviceGetAttribute(&e->n_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+
+	if (e->d.ModuleLoadData(&e->module, nvs_slab_copy_cubin) != CUDA_SUCCESS ||
+	    e->d.ModuleGetFunction(&e->fn_tma, e->module, "nvs_slab_copy_tma") != CUDA_SUCCESS ||
+	    e->d.ModuleGetFunction(&e->fn_ldg, e->module, "nvs_slab_copy_ldg") != CUDA_SUCCESS ||
+	    e->d.ModuleGetFunction(&e->fn_fill, e->module, "nvs_slab_fill") != CUDA_SUCCESS ||
+	    e->d.ModuleGetFunction(&e->fn_verify, e->module, "nvs_slab_verify") != CUDA_SUCCESS) {
+		nvs_warn("engine: the embedded sm_100a image could not be loaded on this device");
+		rc = NVS_E_NO_KERNEL;
+		goto out;
+	}
+	CK(e, e->d.FuncSetAttribute(e->fn_tma, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024));
+	CK(e, e->d.StreamCreate(&e->stream, CU_STREAM_NON_BLOCKING));
+	CK(e, e->d.EventCreate(&e->ev_begin, CU_EVENT_DEFAULT));
+	CK(e, e->d.EventCreate(&e->ev_end, CU_EVENT_DEFAULT));
+	CK(e, e->d.MemAlloc(&e->counters, 4 * N_COUNTERS));
+	CK(e, e->d.MemAlloc(&e->scratch, 64));
+	CK(e, e->d.MemsetD32Async(e->counters, 0, N_COUNTERS, e->stream));
+	CK(e, e->d.StreamSynchronize(e->stream));
+
+	{
+		/* one slot holds one batch: batch_bytes / SLAB descriptors (+ one chunk of slack) */
+		uint32_t cap_descs = (uint32_t)((e->cfg.batch_bytes + e->cfg.chunk_bytes) / SLAB);
+		uint32_t cap_chunks = cap_descs; /* worst case: every chunk is a single slab */
+		for (unsigned k = 0; k < N_SLOTS; ++k) {
+			struct slot *s = &e->slots[k];
+			CK(e, e->d.MemHostAlloc((void **)&s->descs, (size_t)cap_descs * sizeof(nvs_copy_desc),
+						CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+			CUdeviceptr dp = 0;
+			if (e->d.MemHostGetDevicePointer(&dp, s->descs, 0) != CUDA_SUCCESS)
+				dp = (CUdeviceptr)(uintptr_t)s->descs;
+			s->descs_dev = dp;
+			s->cap_descs = cap_descs;
+			s->chunks = calloc(cap_chunks, sizeof(*s->chunks));
+			s->cap_chunks = cap_chunks;
+			if (!s->chunks) {
+				rc = CUDA_ERROR_OUT_OF_MEMORY;
+				goto out;
+			}
+			CK(e, e->d.EventCreate(&s->done, CU_EVENT_DISABLE_TIMING));
+		}
+	}
+
+	e->host_pool.device = -1;
+	for (int i = 0; i < e->cfg.n_peers; ++i) {
+		int can = 0;
+		e->peer_pools[i].device = e->cfg.peers[i];
+		e->peer_pools[i].capacity = e->cfg.peer_capacity_bytes;
+		if (e->cfg.peers[i] == e->device ||
+		    e->d.DeviceCanAccessPeer(&can, e->device, e->cfg.peers[i]) != CUDA_SUCCESS || !can) {
+			nvs_warn("engine: device %d cannot be used as a peer backing tier from device %d",
+				 e->cfg.peers[i], e->device);
+			rc = NVS_E_BAD_ARG;
+			goto out;
+		}
+	}
+	if (e->cfg.stats_path && *e->cfg.stats_path)
+		e->stats_file = fopen(e->cfg.stats_path, "a");
+	if (e->cfg.prepin && e->cfg.n_peers == 0) {
+		if (pthread_create(&e->pin_thread, NULL, pin_thread_main, e) == 0)
+			e->pin_thread_started = 1;
+	}
+	nvs_debug("engine: ready on device %d (%d SMs): chunk %" PRIu64 " MiB, evict=%u fetch=%u, peers=%d",
+		  e->device, e->n_sms, e->cfg.chunk_bytes >> 20, e->cfg.evict_variant, e->cfg.fetch_variant,
+		  e->cfg.n_peers);
+out:
+	if (ctx_pushed)
+		ctx_leave(e);
+	if (rc != 0) {
+		nvs_engine_destroy(e);
+		return rc;
+	}
+	*out = e;
+	return 0;
+}
+
+void nvs_engine_destroy(nvs_engine *e)
+{
+	if (!e)
+		return;
+	if (e->pin_thread_started) {
+		pthread_mutex_lock(&e->mu);
+		e->stopping = 1;
+		pthread_cond_broadcast(&e->pin_cv);
+		pthread_mutex_unlock(&e->mu);
+		pthread_join(e->pin_thread, NULL);
+	}
+	int have_ctx = e->ctx && e->d.CtxPushCurrent && ctx_enter(e) == 0;
+	if (have_ctx) {
+		if (e->stream)
+			e->d.StreamSynchronize(e->stream);
+		while (e->head)
+			nvs_free(e, e->head->va);
+		for (struct arena *a = e->host_pool.arenas, *nx; a; a = nx) {
+			nx = a->next;
+			e->d.MemFreeHost(a->host_base);
+			free(a->bitmap);
+			free(a);
+		}
+		for (int i = 0; i < NVS_MAX_PEERS; ++i)
+			for (struct arena *a = e->peer_pools[i].arenas, *nx; a; a = nx) {
+				nx = a->next;
+				e->d.MemUnmap(a->dev_base, a->bytes);
+				e->d.MemAddressFree(a->dev_base, a->bytes);
+				e->d.MemRelease(a->handle);
+				free(a->bitmap);
+				free(a);
+			}
+		slots_free(e);
+		if (e->counters)
+			e->d.MemFree(e->counters);
+		if (e->scratch)
+			e->d.MemFree(e->scratch);
+		if (e->ev_begin)
+			e->d.EventDestroy(e->ev_begin);
+		if (e->ev_end)
+			e->d.EventDestroy(e->ev_end);
+		if (e->stream)
+			e->d.StreamDestroy(e->stream);
+		if (e->module)
+			e->d.ModuleUnload(e->module);
+		ctx_leave(e);
+	}
+	if (e->stats_file)
+		fclose(e->stats_file);
+	pthread_mutex_destroy(&e->mu);
+	pthread_mutex_destroy(&e->api_mu);
+	pthread_cond_destroy(&e->pin_cv);
+	free(e);
+}

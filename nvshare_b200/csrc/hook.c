@@ -1,0 +1,768 @@
+/*
+ * hook.c -- libnvshare.so's LD_PRELOAD interposer.
+ *
+ * Drop-in boundary kept from the reference (src/hook.c), with its lines:
+ *   - exported `dlsym` under GLIBC_2.2.5 and GLIBC_2.34, the real one obtained
+ *     with dlvsym(RTLD_NEXT, ...)                                 :381-415,432-508,974-975
+ *   - exported driver symbols cuInit, cuGetProcAddress{,_v2}, cuMemAlloc_v2,
+ *     cuMemFree_v2, cuMemGetInfo_v2, cuLaunchKernel, cuMemcpy{,Async},
+ *     cuMemcpy{HtoD,DtoH,DtoD}{,Async}_v2; the same set is what the hooked
+ *     dlsym / cuGetProcAddress answer for                         :436-466,545-574
+ *   - initialisation only from cuInit / cuGetProcAddress{,_v2}; every other
+ *     hook returns CUDA_ERROR_NOT_INITIALIZED (3) before that     :539-540,654,756-757
+ *   - cuMemGetInfo: free = total - 1536 MiB                       :698-746
+ *   - cuMemAlloc: per-process cap = that "free"; over the cap ->
+ *     CUDA_ERROR_OUT_OF_MEMORY (2) unless NVSHARE_ENABLE_SINGLE_OVERSUB
+ *                                                                 :646-682
+ *   - launches and memcpys wait for the GPU lock; launches run the adaptive
+ *     cuCtxSynchronize window 1..2048 (x2 under 1 s, /2 from 1 s, reset from
+ *     10 s)                                                       :766-840
+ *   - driver errors are logged as "<fn> returned <name>: <string>" and returned
+ *     unchanged                                                   :333-343
+ *
+ * What is different by design:
+ *   - cuMemAlloc does NOT become cuMemAllocManaged.  It goes to the swap engine
+ *     (engine.c): a VMM reservation whose 64 MiB chunks are mapped, copied out
+ *     and unmapped explicitly around lock hand-offs.  The reference's path is
+ *     still there as a mode (NVSHARE_ENGINE=uvm, and always when
+ *     NVSHARE_ENABLE_SINGLE_OVERSUB is set, since a single process larger than
+ *     HBM needs demand paging).
+ *   - the interposed set is data: one table drives dlsym, cuGetProcAddress and
+ *     the bootstrap, instead of three hand-written if-chains.
+ *   - the gate also covers entry points a 2025 CUDA stack uses and the
+ *     reference lets through ungated: cuLaunchKernelEx, cuLaunchCooperativeKernel,
+ *     cuGraphLaunch, cuMemsetD*, cuMemcpy2D/3D/Peer -- with VMM memory an
+ *     ungated touch of an evicted slab is a fatal fault, not a slow page-in.
+ *   - cuGetProcAddress honours the per-thread-default-stream flag (each gated
+ *     entry has a legacy and a per-thread forwarder) and answers
+ *     "cuGetProcAddress" with the v2 hook when asked by a >= 12.0 runtime.
+ *   - the allocation table is thread-safe (the reference's list is not).
+ */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <dlfcn.h>
+#include <inttypes.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "../../include/nvshare_engine.h"
+#include "../../include/nvshare_wire.h"
+#include "client.h"
+#include "cuda_min.h"
+#include "nvs_log.h"
+
+#define EXPORT __attribute__((visibility("default")))
+
+#define MEMINFO_RESERVE_BYTES (1536ull << 20) /* reference src/hook.c:45 */
+#define SYNC_RESET_SECONDS 10                 /* reference src/hook.c:46 */
+#define SYNC_STEPDOWN_SECONDS 1               /* reference src/hook.c:47 */
+#define SYNC_WINDOW_MAX 2048                  /* reference src/hook.c:48 */
+#define PTDS_FLAG 0x2ull /* CU_GET_PROC_ADDRESS_PER_THREAD_DEFAULT_STREAM */
+
+/* ------------------------------------------------------------- state ---- */
+
+static pthread_once_t once_lib = PTHREAD_ONCE_INIT;
+static pthread_once_t once_client = PTHREAD_ONCE_INIT;
+static void *cuda_lib;
+static int single_oversub;
+static int uvm_mode; /* reference mechanism instead of the swap engine */
+
+static CUresult (*real_cuInit)(unsigned);
+static CUresult (*real_cuGetProcAddress)(const char *, void **, int, cuuint64_t);
+static CUresult (*real_cuGetProcAddress_v2)(const char *, void **, int, cuuint64_t,
+					     CUdriverProcAddressQueryResult *);
+static CUresult (*real_cuMemAllocManaged)(CUdeviceptr *, size_t, unsigned);
+static CUresult (*real_cuMemAlloc)(CUdeviceptr *, size_t);
+static CUresult (*real_cuMemFree)(CUdeviceptr);
+static CUresult (*real_cuMemGetInfo)(size_t *, size_t *);
+static CUresult (*real_cuGetErrorString)(CUresult, const char **);
+static CUresult (*real_cuGetErrorName)(CUresult, const char **);
+static CUresult (*real_cuCtxSetCurrent)(CUcontext);
+static CUresult (*real_cuCtxGetCurrent)(CUcontext *);
+static CUresult (*real_cuCtxSynchronize)(void);
+
+static pthread_mutex_t acct_mu = PTHREAD_MUTEX_INITIALIZER;
+static size_t cap_bytes;     /* what cuMemGetInfo reports as free: the per-process cap */
+static int cap_known;
+static size_t sum_allocated; /* bytes the application currently holds via cuMemAlloc    */
+
+static pthread_mutex_t window_mu = PTHREAD_MUTEX_INITIALIZER;
+static int launches_since_sync;
+static int sync_window = 1;
+
+static pthread_mutex_t engine_mu = PTHREAD_MUTEX_INITIALIZER;
+static nvs_engine *engine;
+static int holds_lock;
+
+/* ------------------------------------------------- the real dlsym ------- */
+
+typedef void *(*dlsym_fn)(void *, const char *);
+
+static void *real_dlsym_ver(int which, void *handle, const char *symbol)
+{
+	static const char *const versions[2] = {"GLIBC_2.2.5", "GLIBC_2.34"};
+	static dlsym_fn cached[2];
+	if (!cached[which]) {
+		cached[which] = (dlsym_fn)dlvsym(RTLD_NEXT, "dlsym", versions[which]);
+		if (!cached[which])
+			nvs_fatal("cannot find the real dlsym@%s: %s", versions[which], dlerror());
+	}
+	return cached[which](handle, symbol);
+}
+
+static void *real_dlsym(void *handle, const char *symbol)
+{
+	static dlsym_fn f;
+	if (!f) {
+		f = (dlsym_fn)dlvsym(RTLD_NEXT, "dlsym", "GLIBC_2.2.5");
+		if (!f)
+			f = (dlsym_fn)dlvsym(RTLD_NEXT, "dlsym", "GLIBC_2.34");
+		if (!f)
+			nvs_fatal("cannot find the real dlsym: %s", dlerror());
+	}
+	return f(handle, symbol);
+}
+
+static void warn_if_error(CUresult r, const char *fn)
+{
+	if (r == CUDA_SUCCESS)
+		return;
+	const char *name = "?", *text = "?";
+	if (real_cuGetErrorName)
+		real_cuGetErrorName(r, &name);
+	if (real_cuGetErrorString)
+		real_cuGetErrorString(r, &text);
+	nvs_warn("%s returned %s: %s", fn, name, text);
+}
+
+/* ------------------------------------------------- gated forwarders ----- */
+
+/*
+ * Each gated entry point gets two forwarders, [0] for the legacy default
+ * stream and [1] for the per-thread default stream flavour the driver hands
+ * out when cuGetProcAddress is called with PTDS_FLAG.  They differ only in
+ * which real function they call.
+ */
+enum gate_id {
+	G_cuLaunchKernel, G_cuLaunchKernelEx, G_cuLaunchCooperativeKernel, G_cuGraphLaunch,
+	G_cuMemcpy, G_cuMemcpyAsync, G_cuMemcpyHtoD, G_cuMemcpyHtoDAsync, G_cuMemcpyDtoH,
+	G_cuMemcpyDtoHAsync, G_cuMemcpyDtoD, G_cuMemcpyDtoDAsync,
+	G_cuMemcpyPeer, G_cuMemcpyPeerAsync, G_cuMemcpy2D, G_cuMemcpy2DUnaligned, G_cuMemcpy2DAsync,
+	G_cuMemcpy3D, G_cuMemcpy3DAsync, G_cuMemcpy3DPeer, G_cuMemcpy3DPeerAsync,
+	G_cuMemsetD8, G_cuMemsetD16, G_cuMemsetD32, G_cuMemsetD8Async, G_cuMemsetD16Async, G_cuMemsetD32Async,
+	G_cuMemsetD2D8, G_cuMemsetD2D16, G_cuMemsetD2D32, G_cuMemsetD2D8Async, G_cuMemsetD2D16Async,
+	G_cuMemsetD2D32Async,
+	G_COUNT
+};
+static void *gate_real[G_COUNT][2];
+
+static void after_launch(void);
+
+#define GATED(name, is_launch, params, args)                                         \
+	static CUresult gate_##name##_impl(int flavour_, NVS_UNPAREN params)                \
+	{                                                                            \
+		typedef CUresult (*fn_t) params;                                     \
+		fn_t real = (fn_t)gate_real[G_##name][flavour_];                            \
+		if (!real)                                                           \
+			real = (fn_t)gate_real[G_##name][0];                         \
+		if (!real)                                                           \
+			return CUDA_ERROR_NOT_INITIALIZED;                           \
+		continue_with_lock();                                                \
+		CUresult r = real args;                                              \
+		warn_if_error(r, #name);                                             \
+		if (is_launch)                                                       \
+			after_launch();                                              \
+		return r;                                                            \
+	}                                                                            \
+	static CUresult gate_##name##_0 params { return gate_##name##_impl NVS_PREPEND(0, args); } \
+	static CUresult gate_##name##_1 params { return gate_##name##_impl NVS_PREPEND(1, args); }
+
+#define NVS_UNPAREN(...) __VA_ARGS__
+#define NVS_PREPEND(x, ...) NVS_PREPEND_(x, NVS_UNPAREN __VA_ARGS__)
+#define NVS_PREPEND_(x, ...) (x, __VA_ARGS__)
+
+typedef unsigned int u32;
+
+GATED(cuLaunchKernel, 1,
+      (CUfunction f, u32 gx, u32 gy, u32 gz, u32 bx, u32 by, u32 bz, u32 smem, CUstream s, void **kp, void **extra),
+      (f, gx, gy, gz, bx, by, bz, smem, s, kp, extra))
+GATED(cuLaunchKernelEx, 1, (const void *config, CUfunction f, void **kp, void **extra), (config, f, kp, extra))
+GATED(cuLaunchCooperativeKernel, 1,
+      (CUfunction f, u32 gx, u32 gy, u32 gz, u32 bx, u32 by, u32 bz, u32 smem, CUstream s, void **kp),
+      (f, gx, gy, gz, bx, by, bz, smem, s, kp))
+GATED(cuGraphLaunch, 1, (CUgraphExec g, CUstream s), (g, s))
+GATED(cuMemcpy, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n), (dst, src, n))
+GATED(cuMemcpyAsync, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
+GATED(cuMemcpyHtoD, 0, (CUdeviceptr dst, const void *src, size_t n), (dst, src, n))
+GATED(cuMemcpyHtoDAsync, 0, (CUdeviceptr dst, const void *src, size_t n, CUstream s), (dst, src, n, s))
+GATED(cuMemcpyDtoH, 0, (void *dst, CUdeviceptr src, size_t n), (dst, src, n))
+GATED(cuMemcpyDtoHAsync, 0, (void *dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
+GATED(cuMemcpyDtoD, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n), (dst, src, n))
+GATED(cuMemcpyDtoDAsync, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
+GATED(cuMemcpyPeer, 0, (CUdeviceptr dst, CUcontext dc, CUdeviceptr src, CUcontext sc, size_t n), (dst, dc, src, sc, n))
+GATED(cuMemcpyPeerAsync, 0, (CUdeviceptr dst, CUcontext dc, CUdeviceptr src, CUcontext sc, size_t n, CUstream s),
+      (dst, dc, src, sc, n, s))
+GATED(cuMemcpy2D, 0, (const void *p), (p))
+GATED(cuMemcpy2DUnaligned, 0, (const void *p), (p))
+GATED(cuMemcpy2DAsync, 0, (const void *p, CUstream s), (p, s))
+GATED(cuMemcpy3D, 0, (const void *p), (p))
+GATED(cuMemcpy3DAsync, 0, (const void *p, CUstream s), (p, s))
+GATED(cuMemcpy3DPeer, 0, (const void *p), (p))
+GATED(cuMemcpy3DPeerAsync, 0, (const void *p, CUstream s), (p, s))
+GATED(cuMemsetD8, 0, (CUdeviceptr d, unsigned char v, size_t n), (d, v, n))
+GATED(cuMemsetD16, 0, (CUdeviceptr d, unsigned short v, size_t n), (d, v, n))
+GATED(cuMemsetD32, 0, (CUdeviceptr d, u32 v, size_t n), (d, v, n))
+GATED(cuMemsetD8Async, 0, (CUdeviceptr d, unsigned char v, size_t n, CUstream s), (d, v, n, s))
+GATED(cuMemsetD16Async, 0, (CUdeviceptr d, unsigned short v, size_t n, CUstream s), (d, v, n, s))
+GATED(cuMemsetD32Async, 0, (CUdeviceptr d, u32 v, size_t n, CUstream s), (d, v, n, s))
+GATED(cuMemsetD2D8, 0, (CUdeviceptr d, size_t pitch, unsigned char v, size_t w, size_t h), (d, pitch, v, w, h))
+GATED(cuMemsetD2D16, 0, (CUdeviceptr d, size_t pitch, unsigned short v, size_t w, size_t h), (d, pitch, v, w, h))
+GATED(cuMemsetD2D32, 0, (CUdeviceptr d, size_t pitch, u32 v, size_t w, size_t h), (d, pitch, v, w, h))
+GATED(cuMemsetD2D8Async, 0, (CUdeviceptr d, size_t pitch, unsigned char v, size_t w, size_t h, CUstream s),
+      (d, pitch, v, w, h, s))
+GATED(cuMemsetD2D16Async, 0, (CUdeviceptr d, size_t pitch, unsigned short v, size_t w, size_t h, CUstream s),
+      (d, pitch, v, w, h, s))
+GATED(cuMemsetD2D32Async, 0, (CUdeviceptr d, size_t pitch, u32 v, size_t w, size_t h, CUstream s),
+      (d, pitch, v, w, h, s))
+
+/* ------------------------------------------------- interposed table ----- */
+
+EXPORT CUresult cuInit(unsigned flags);
+EXPORT CUresult cuGetProcAddress(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags);
+EXPORT CUresult cuGetProcAddress_v2(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags,
+				    CUdriverProcAddressQueryResult *status);
+EXPORT CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize);
+EXPORT CUresult cuMemFree_v2(CUdeviceptr dptr);
+EXPORT CUresult cuMemGetInfo_v2(size_t *free_b, size_t *total_b);
+
+struct entry {
+	const char *base; /* name cuGetProcAddress is asked for          */
+	const char *elf;  /* exported / dlsym name in libcuda            */
+	void *hook[2];    /* [legacy, per-thread default stream]         */
+	int gate;         /* index into gate_real, or -1                 */
+	int reference;    /* 1: part of the reference's interposed set   */
+	const char *ptds_suffix; /* "_ptsz", "_ptds" or NULL             */
+};
+
+#define E_GATE(name, elfname, ref, sfx) {#name, elfname, {(void *)gate_##name##_0, (void *)gate_##name##_1}, G_##name, ref, sfx}
+#define E_PLAIN(name, elfname, fn) {#name, elfname, {(void *)fn, (void *)fn}, -1, 1, NULL}
+
+static const struct entry ENTRIES[] = {
+	E_PLAIN(cuInit, "cuInit", cuInit),
+	E_PLAIN(cuGetProcAddress, "cuGetProcAddress", cuGetProcAddress),
+	E_PLAIN(cuGetProcAddress_v2, "cuGetProcAddress_v2", cuGetProcAddress_v2),
+	E_PLAIN(cuMemAlloc, "cuMemAlloc_v2", cuMemAlloc_v2),
+	E_PLAIN(cuMemFree, "cuMemFree_v2", cuMemFree_v2),
+	E_PLAIN(cuMemGetInfo, "cuMemGetInfo_v2", cuMemGetInfo_v2),
+	E_GATE(cuLaunchKernel, "cuLaunchKernel", 1, "_ptsz"),
+	E_GATE(cuMemcpy, "cuMemcpy", 1, "_ptds"),
+	E_GATE(cuMemcpyAsync, "cuMemcpyAsync", 1, "_ptsz"),
+	E_GATE(cuMemcpyHtoD, "cuMemcpyHtoD_v2", 1, "_ptds"),
+	E_GATE(cuMemcpyHtoDAsync, "cuMemcpyHtoDAsync_v2", 1, "_ptsz"),
+	E_GATE(cuMemcpyDtoH, "cuMemcpyDtoH_v2", 1, "_ptds"),
+	E_GATE(cuMemcpyDtoHAsync, "cuMemcpyDtoHAsync_v2", 1, "_ptsz"),
+	E_GATE(cuMemcpyDtoD, "cuMemcpyDtoD_v2", 1, "_ptds"),
+	E_GATE(cuMemcpyDtoDAsync, "cuMemcpyDtoDAsync_v2", 1, "_ptsz"),
+	/* beyond the reference's set */
+	E_GATE(cuLaunchKernelEx, "cuLaunchKernelEx", 0, "_ptsz"),
+	E_GATE(cuLaunchCooperativeKernel, "cuLaunchCooperativeKernel", 0, "_ptsz"),
+	E_GATE(cuGraphLaunch, "cuGraphLaunch", 0, "_ptsz"),
+	E_GATE(cuMemcpyPeer, "cuMemcpyPeer", 0, "_ptds"),
+	E_GATE(cuMemcpyPeerAsync, "cuMemcpyPeerAsync", 0, "_ptsz"),
+	E_GATE(cuMemcpy2D, "cuMemcpy2D_v2", 0, "_ptds"),
+	E_GATE(cuMemcpy2DUnaligned, "cuMemcpy2DUnaligned_v2", 0, "_ptds"),
+	E_GATE(cuMemcpy2DAsync, "cuMemcpy2DAsync_v2", 0, "_ptsz"),
+	E_GATE(cuMemcpy3D, "cuMemcpy3D_v2", 0, "_ptds"),
+	E_GATE(cuMemcpy3DAsync, "cuMemcpy3DAsync_v2", 0, "_ptsz"),
+	E_GATE(cuMemcpy3DPeer, "cuMemcpy3DPeer", 0, "_ptds"),
+	E_GATE(cuMemcpy3DPeerAsync, "cuMemcpy3DPeerAsync", 0, "_ptsz"),
+	E_GATE(cuMemsetD8, "cuMemsetD8_v2", 0, "_ptds"),
+	E_GATE(cuMemsetD16, "cuMemsetD16_v2", 0, "_ptds"),
+	E_GATE(cuMemsetD32, "cuMemsetD32_v2", 0, "_ptds"),
+	E_GATE(cuMemsetD8Async, "cuMemsetD8Async", 0, "_ptsz"),
+	E_GATE(cuMemsetD16Async, "cuMemsetD16Async", 0, "_ptsz"),
+	E_GATE(cuMemsetD32Async, "cuMemsetD32Async", 0, "_ptsz"),
+	E_GATE(cuMemsetD2D8, "cuMemsetD2D8_v2", 0, "_ptds"),
+	E_GATE(cuMemsetD2D16, "cuMemsetD2D16_v2", 0, "_ptds"),
+	E_GATE(cuMemsetD2D32, "cuMemsetD2D32_v2", 0, "_ptds"),
+	E_GATE(cuMemsetD2D8Async, "cuMemsetD2D8Async", 0, "_ptsz"),
+	E_GATE(cuMemsetD2D16Async, "cuMemsetD2D16Async", 0, "_ptsz"),
+	E_GATE(cuMemsetD2D32Async, "cuMemsetD2D32Async", 0, "_ptsz"),
+};
+#define N_ENTRIES (sizeof(ENTRIES) / sizeof(ENTRIES[0]))
+
+static const struct entry *find_by_elf(const char *name)
+{
+	for (size_t i = 0; i < N_ENTRIES; ++i)
+		if (strcmp(ENTRIES[i].elf, name) == 0)
+			return &ENTRIES[i];
+	return NULL;
+}
+
+static const struct entry *find_by_base(const char *name)
+{
+	for (size_t i = 0; i < N_ENTRIES; ++i)
+		if (strcmp(ENTRIES[i].base, name) == 0)
+			return &ENTRIES[i];
+	return NULL;
+}
+
+/* ------------------------------------------------------- bootstrap ------ */
+
+static void *must_sym(const char *name)
+{
+	dlerror();
+	void *p = real_dlsym(cuda_lib, name);
+	const char *err = dlerror();
+	if (err || !p)
+		nvs_fatal("%s", err ? err : name);
+	return p;
+}
+
+static void *engine_resolver(const char *symbol)
+{
+	return real_dlsym(cuda_lib, symbol);
+}
+
+static struct nvs_client_driver client_drv;
+
+static void bootstrap(void)
+{
+	if (getenv(NVS_ENV_DEBUG))
+		nvs_debug_enabled = 1;
+	if (getenv("NVSHARE_ENABLE_SINGLE_OVERSUB")) {
+		single_oversub = 1;
+		uvm_mode = 1; /* a single process bigger than HBM needs demand paging */
+		nvs_warn("Enabling GPU memory oversubscription for this application");
+	}
+	const char *mode = getenv("NVSHARE_ENGINE");
+	if (mode && strcmp(mode, "uvm") == 0)
+		uvm_mode = 1;
+
+	void *nvml = dlopen("libnvidia-ml.so.1", RTLD_LAZY);
+	if (nvml) {
+		client_drv.nvmlInit = (nvmlReturn_t(*)(void))real_dlsym(nvml, "nvmlInit_v2");
+		client_drv.nvmlDeviceGetHandleByIndex =
+			(nvmlReturn_t(*)(unsigned, nvmlDevice_t *))real_dlsym(nvml, "nvmlDeviceGetHandleByIndex_v2");
+		client_drv.nvmlDeviceGetUtilizationRates =
+			(nvmlReturn_t(*)(nvmlDevice_t, nvmlUtilization_t *))real_dlsym(nvml, "nvmlDeviceGetUtilizationRates");
+	}
+	if (client_drv.nvmlInit && client_drv.nvmlDeviceGetHandleByIndex && client_drv.nvmlDeviceGetUtilizationRates) {
+		nvs_debug("Found NVML");
+	} else {
+		client_drv.nvmlInit = NULL;
+		nvs_debug("Could not find NVML");
+	}
+
+	cuda_lib = dlopen("libcuda.so.1", RTLD_LAZY);
+	if (!cuda_lib)
+		cuda_lib = dlopen("libcuda.so", RTLD_LAZY);
+	if (!cuda_lib)
+		nvs_fatal("%s", dlerror());
+
+	real_cuInit = must_sym("cuInit");
+	real_cuMemAllocManaged = must_sym("cuMemAllocManaged");
+	real_cuMemAlloc = must_sym("cuMemAlloc_v2");
+	real_cuMemFree = must_sym("cuMemFree_v2");
+	real_cuMemGetInfo = must_sym("cuMemGetInfo_v2");
+	real_cuGetErrorString = must_sym("cuGetErrorString");
+	real_cuGetErrorName = must_sym("cuGetErrorName");
+	real_cuCtxSetCurrent = must_sym("cuCtxSetCurrent");
+	real_cuCtxGetCurrent = must_sym("cuCtxGetCurrent");
+	real_cuCtxSynchronize = must_sym("cuCtxSynchronize");
+	/* optional: runtimes < 11.3 / < 12.0 never ask for them */
+	real_cuGetProcAddress = real_dlsym(cuda_lib, "cuGetProcAddress");
+	real_cuGetProcAddress_v2 = real_dlsym(cuda_lib, "cuGetProcAddress_v2");
+
+	for (size_t i = 0; i < N_ENTRIES; ++i) {
+		const struct entry *e = &ENTRIES[i];
+		if (e->gate < 0)
+			continue;
+		/* the reference's set is mandatory (src/hook.c:224-268); the wider set is best effort */
+		gate_real[e->gate][0] = e->reference ? must_sym(e->elf) : real_dlsym(cuda_lib, e->elf);
+		if (e->ptds_suffix) {
+			char name[96];
+			snprintf(name, sizeof(name), "%s%s", e->elf, e->ptds_suffix);
+			gate_real[e->gate][1] = real_dlsym(cuda_lib, name);
+		}
+	}
+	dlerror();
+
+	client_drv.cuInit = real_cuInit;
+	client_drv.cuCtxGetCurrent = real_cuCtxGetCurrent;
+	client_drv.cuCtxSetCurrent = real_cuCtxSetCurrent;
+	client_drv.cuCtxSynchronize = real_cuCtxSynchronize;
+}
+
+/* ----------------------------------------------- data path adapters ----- */
+
+static int dp_fetch_all(void)
+{
+	pthread_mutex_lock(&engine_mu);
+	nvs_engine *e = engine;
+	pthread_mutex_unlock(&engine_mu);
+	if (!e)
+		return 0;
+	nvs_xfer_report rep;
+	int rc = nvs_fetch_all(e, &rep);
+	if (rc != 0)
+		nvs_warn("fetch failed: %s", nvs_strerror(rc));
+	return rc;
+}
+
+static int dp_evict(uint64_t min_bytes)
+{
+	pthread_mutex_lock(&engine_mu);
+	nvs_engine *e = engine;
+	pthread_mutex_unlock(&engine_mu);
+	if (!e)
+		return 0;
+	nvs_xfer_report rep;
+	int rc = nvs_evict(e, min_bytes, &rep);
+	if (rc != 0)
+		nvs_warn("evict failed: %s", nvs_strerror(rc));
+	return rc;
+}
+
+static uint64_t dp_nonresident_mib(void)
+{
+	pthread_mutex_lock(&engine_mu);
+	nvs_engine *e = engine;
+	pthread_mutex_unlock(&engine_mu);
+	nvs_stats st;
+	if (!e || nvs_get_stats(e, &st) != 0)
+		return 0;
+	return (st.swapped_bytes + st.unbacked_bytes) >> 20;
+}
+
+static void dp_lock_state(int v)
+{
+	pthread_mutex_lock(&engine_mu);
+	holds_lock = v;
+	if (engine)
+		nvs_set_resident_mode(engine, v);
+	pthread_mutex_unlock(&engine_mu);
+}
+
+static void reset_sync_window(void)
+{
+	pthread_mutex_lock(&window_mu);
+	sync_window = 1;
+	pthread_mutex_unlock(&window_mu);
+}
+
+static void start_client(void)
+{
+	static const struct nvs_client_datapath dp = {dp_fetch_all, dp_evict, dp_nonresident_mib, dp_lock_state};
+	nvs_client_on_context_sync = reset_sync_window;
+	nvs_client_start(&client_drv, uvm_mode ? NULL : &dp);
+}
+
+static void ensure_init(void)
+{
+	nvs_must(pthread_once(&once_lib, bootstrap) == 0);
+	nvs_must(pthread_once(&once_client, start_client) == 0);
+}
+
+/* The engine binds to the application's context, so it can only be created
+ * once the application has one (its first cuMemAlloc).  NULL: no context yet. */
+static nvs_engine *engine_get(void)
+{
+	pthread_mutex_lock(&engine_mu);
+	if (!engine) {
+		CUcontext ctx = NULL;
+		if (real_cuCtxGetCurrent(&ctx) == CUDA_SUCCESS && ctx != NULL) {
+			nvs_engine_config cfg;
+			nvs_engine_default_config(&cfg);
+			cfg.resolve = engine_resolver;
+			int rc = nvs_engine_create(&cfg, &engine);
+			if (rc != 0)
+				nvs_fatal("swap engine could not start (%s); set NVSHARE_ENGINE=uvm to run with "
+					  "the reference's managed-memory mechanism instead", nvs_strerror(rc));
+			nvs_set_resident_mode(engine, holds_lock);
+		}
+	}
+	nvs_engine *e = engine;
+	pthread_mutex_unlock(&engine_mu);
+	return e;
+}
+
+/* ------------------------------------------------- launch window -------- */
+
+/* Reference src/hook.c:782-838: keep the amount of queued GPU work bounded so a
+ * DROP_LOCK can be honoured quickly. */
+static void after_launch(void)
+{
+	pthread_mutex_lock(&window_mu);
+	if (++launches_since_sync >= sync_window) {
+		struct timespec a, b;
+		clock_gettime(CLOCK_MONOTONIC, &a);
+		CUresult r = real_cuCtxSynchronize();
+		warn_if_error(r, "cuCtxSynchronize");
+		clock_gettime(CLOCK_MONOTONIC, &b);
+		long secs = b.tv_sec - a.tv_sec - (b.tv_nsec < a.tv_nsec ? 1 : 0);
+		if (secs >= SYNC_RESET_SECONDS)
+			sync_window = 1;
+		else if (secs >= SYNC_STEPDOWN_SECONDS)
+			sync_window = sync_window / 2 > 1 ? sync_window / 2 : 1;
+		else
+			sync_window = sync_window * 2 < SYNC_WINDOW_MAX ? sync_window * 2 : SYNC_WINDOW_MAX;
+		nvs_debug("Pending Kernel Window is %d.", sync_window);
+		launches_since_sync = 0;
+	}
+	pthread_mutex_unlock(&window_mu);
+}
+
+/* ------------------------------------------- UVM-mode allocation list --- */
+
+struct uvm_alloc {
+	CUdeviceptr ptr;
+	size_t size;
+	struct uvm_alloc *next;
+};
+static struct uvm_alloc *uvm_buckets[256];
+
+static void uvm_insert(CUdeviceptr p, size_t n)
+{
+	struct uvm_alloc *a = malloc(sizeof(*a));
+	nvs_must(a != NULL);
+	a->ptr = p;
+	a->size = n;
+	unsigned h = (unsigned)((p >> 9) * 2654435761u) >> 24;
+	a->next = uvm_buckets[h];
+	uvm_buckets[h] = a;
+}
+
+static size_t uvm_remove(CUdeviceptr p)
+{
+	unsigned h = (unsigned)((p >> 9) * 2654435761u) >> 24;
+	for (struct uvm_alloc **pp = &uvm_buckets[h]; *pp; pp = &(*pp)->next)
+		if ((*pp)->ptr == p) {
+			struct uvm_alloc *a = *pp;
+			size_t n = a->size;
+			*pp = a->next;
+			free(a);
+			return n;
+		}
+	return 0;
+}
+
+/* ------------------------------------------------- exported hooks ------- */
+
+CUresult cuInit(unsigned flags)
+{
+	ensure_init();
+	CUresult r = real_cuInit(flags);
+	warn_if_error(r, "cuInit");
+	return r;
+}
+
+CUresult cuMemGetInfo_v2(size_t *free_b, size_t *total_b)
+{
+	if (!real_cuMemGetInfo)
+		return CUDA_ERROR_NOT_INITIALIZED;
+	CUresult r = real_cuMemGetInfo(free_b, total_b);
+	warn_if_error(r, "cuMemGetInfo_v2");
+	nvs_debug("real_cuMemGetInfo returned free=%.2f MiB, total=%.2f MiB", *free_b / 1048576.0,
+		  *total_b / 1048576.0);
+	/* hide a fixed slice for contexts and libraries, whatever is really free */
+	*free_b = *total_b - (size_t)MEMINFO_RESERVE_BYTES;
+	nvs_debug("nvshare's cuMemGetInfo returning free=%.2f MiB, total=%.2f MiB", *free_b / 1048576.0,
+		  *total_b / 1048576.0);
+	return r;
+}
+
+CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize)
+{
+	if (!real_cuMemAllocManaged)
+		return CUDA_ERROR_NOT_INITIALIZED;
+	pthread_mutex_lock(&acct_mu);
+	if (!cap_known) {
+		size_t total = 0;
+		CUresult r = cuMemGetInfo_v2(&cap_bytes, &total);
+		warn_if_error(r, "cuMemGetInfo_v2");
+		cap_known = 1;
+	}
+	if (sum_allocated + bytesize > cap_bytes) {
+		if (!single_oversub) {
+			pthread_mutex_unlock(&acct_mu);
+			return CUDA_ERROR_OUT_OF_MEMORY;
+		}
+		nvs_warn("Memory allocations exceeded physical GPU memory capacity. This can cause extreme"
+			 " performance degradation!");
+	}
+	pthread_mutex_unlock(&acct_mu);
+
+	nvs_debug("cuMemAlloc requested %zu bytes", bytesize);
+	CUresult r;
+	nvs_engine *e = uvm_mode ? NULL : engine_get();
+	if (uvm_mode) {
+		r = real_cuMemAllocManaged(dptr, bytesize, CU_MEM_ATTACH_GLOBAL);
+		warn_if_error(r, "cuMemAllocManaged");
+	} else if (e) {
+		uint64_t p = 0;
+		int rc = nvs_alloc(e, &p, bytesize);
+		r = rc >= 0 ? (CUresult)rc : CUDA_ERROR_UNKNOWN;
+		if (r == CUDA_SUCCESS)
+			*dptr = p;
+		else
+			nvs_warn("cuMemAlloc_v2 (swap engine) returned %d: %s", (int)r, nvs_strerror(rc));
+	} else {
+		/* no current context: let the driver produce its own error */
+		r = real_cuMemAlloc(dptr, bytesize);
+		warn_if_error(r, "cuMemAlloc_v2");
+		if (r == CUDA_SUCCESS)
+			nvs_warn("allocation made without a current context is not swappable");
+	}
+	if (r == CUDA_SUCCESS) {
+		pthread_mutex_lock(&acct_mu);
+		sum_allocated += bytesize;
+		if (uvm_mode || !e)
+			uvm_insert(*dptr, bytesize);
+		nvs_debug("Total allocated memory on GPU is %.2f MiB", sum_allocated / 1048576.0);
+		pthread_mutex_unlock(&acct_mu);
+	}
+	return r;
+}
+
+CUresult cuMemFree_v2(CUdeviceptr dptr)
+{
+	if (!real_cuMemFree)
+		return CUDA_ERROR_NOT_INITIALIZED;
+	pthread_mutex_lock(&engine_mu);
+	nvs_engine *e = engine;
+	pthread_mutex_unlock(&engine_mu);
+	if (e) {
+		uint64_t bytes = 0;
+		int rc = nvs_free_sized(e, dptr, &bytes);
+		if (rc == 0) {
+			pthread_mutex_lock(&acct_mu);
+			sum_allocated -= bytes;
+			nvs_debug("Total allocated memory on GPU is %.2f MiB", sum_allocated / 1048576.0);
+			pthread_mutex_unlock(&acct_mu);
+			return CUDA_SUCCESS;
+		}
+		if (rc != NVS_E_NOT_OURS)
+			return rc > 0 ? (CUresult)rc : CUDA_ERROR_UNKNOWN;
+	}
+	CUresult r = real_cuMemFree(dptr);
+	if (r == CUDA_SUCCESS) {
+		pthread_mutex_lock(&acct_mu);
+		sum_allocated -= uvm_remove(dptr);
+		pthread_mutex_unlock(&acct_mu);
+	}
+	return r;
+}
+
+/* reference-exported names of the gated set: the legacy-stream forwarders */
+EXPORT CUresult cuLaunchKernel(CUfunction f, u32 gx, u32 gy, u32 gz, u32 bx, u32 by, u32 bz, u32 smem, CUstream s,
+			       void **kp, void **extra)
+{
+	return gate_cuLaunchKernel_0(f, gx, gy, gz, bx, by, bz, smem, s, kp, extra);
+}
+EXPORT CUresult cuMemcpy(CUdeviceptr dst, CUdeviceptr src, size_t n) { return gate_cuMemcpy_0(dst, src, n); }
+EXPORT CUresult cuMemcpyAsync(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s) { return gate_cuMemcpyAsync_0(dst, src, n, s); }
+EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void *src, size_t n) { return gate_cuMemcpyHtoD_0(dst, src, n); }
+EXPORT CUresult cuMemcpyHtoDAsync_v2(CUdeviceptr dst, const void *src, size_t n, CUstream s) { return gate_cuMemcpyHtoDAsync_0(dst, src, n, s); }
+EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) { return gate_cuMemcpyDtoH_0(dst, src, n); }
+EXPORT CUresult cuMemcpyDtoHAsync_v2(void *dst, CUdeviceptr src, size_t n, CUstream s) { return gate_cuMemcpyDtoHAsync_0(dst, src, n, s); }
+EXPORT CUresult cuMemcpyDtoD_v2(CUdeviceptr dst, CUdeviceptr src, size_t n) { return gate_cuMemcpyDtoD_0(dst, src, n); }
+EXPORT CUresult cuMemcpyDtoDAsync_v2(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s) { return gate_cuMemcpyDtoDAsync_0(dst, src, n, s); }
+/* wider set, exported for pure driver-API applications */
+EXPORT CUresult cuLaunchKernelEx(const void *c, CUfunction f, void **kp, void **extra) { return gate_cuLaunchKernelEx_0(c, f, kp, extra); }
+EXPORT CUresult cuLaunchCooperativeKernel(CUfunction f, u32 gx, u32 gy, u32 gz, u32 bx, u32 by, u32 bz, u32 smem,
+					  CUstream s, void **kp)
+{
+	return gate_cuLaunchCooperativeKernel_0(f, gx, gy, gz, bx, by, bz, smem, s, kp);
+}
+EXPORT CUresult cuGraphLaunch(CUgraphExec g, CUstream s) { return gate_cuGraphLaunch_0(g, s); }
+EXPORT CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { return gate_cuMemsetD8_0(d, v, n); }
+EXPORT CUresult cuMemsetD16_v2(CUdeviceptr d, unsigned short v, size_t n) { return gate_cuMemsetD16_0(d, v, n); }
+EXPORT CUresult cuMemsetD32_v2(CUdeviceptr d, u32 v, size_t n) { return gate_cuMemsetD32_0(d, v, n); }
+EXPORT CUresult cuMemsetD8Async(CUdeviceptr d, unsigned char v, size_t n, CUstream s) { return gate_cuMemsetD8Async_0(d, v, n, s); }
+EXPORT CUresult cuMemsetD16Async(CUdeviceptr d, unsigned short v, size_t n, CUstream s) { return gate_cuMemsetD16Async_0(d, v, n, s); }
+EXPORT CUresult cuMemsetD32Async(CUdeviceptr d, u32 v, size_t n, CUstream s) { return gate_cuMemsetD32Async_0(d, v, n, s); }
+
+/* ------------------------------------------------- symbol lookup -------- */
+
+CUresult cuGetProcAddress_v2(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags,
+			     CUdriverProcAddressQueryResult *status)
+{
+	ensure_init();
+	if (!real_cuGetProcAddress_v2)
+		return CUDA_ERROR_NOT_INITIALIZED;
+	const struct entry *e = find_by_base(symbol);
+	if (!e)
+		return real_cuGetProcAddress_v2(symbol, pfn, cudaVersion, flags, status);
+	const int v = (flags & PTDS_FLAG) ? 1 : 0;
+	if (e->gate >= 0 && !gate_real[e->gate][v]) {
+		/* learn the real function for this flavour from the driver itself */
+		void *p = NULL;
+		CUdriverProcAddressQueryResult st = CU_GET_PROC_ADDRESS_SUCCESS;
+		CUresult r = real_cuGetProcAddress_v2(symbol, &p, cudaVersion, flags, &st);
+		if (r != CUDA_SUCCESS || !p) { /* this driver does not have it: say so */
+			*pfn = p;
+			if (status)
+				*status = st;
+			return r;
+		}
+		gate_real[e->gate][v] = p;
+	}
+	if (e->hook[0] == (void *)cuGetProcAddress && cudaVersion >= 12000)
+		*pfn = (void *)cuGetProcAddress_v2; /* what a 12.x runtime means by "cuGetProcAddress" */
+	else
+		*pfn = e->hook[v];
+	if (status)
+		*status = CU_GET_PROC_ADDRESS_SUCCESS;
+	return CUDA_SUCCESS;
+}
+
+CUresult cuGetProcAddress(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags)
+{
+	ensure_init();
+	if (!real_cuGetProcAddress)
+		return CUDA_ERROR_NOT_INITIALIZED;
+	const struct entry *e = find_by_base(symbol);
+	if (!e)
+		return real_cuGetProcAddress(symbol, pfn, cudaVersion, flags);
+	const int v = (flags & PTDS_FLAG) ? 1 : 0;
+	if (e->gate >= 0 && !gate_real[e->gate][v]) {
+		void *p = NULL;
+		CUresult r = real_cuGetProcAddress(symbol, &p, cudaVersion, flags);
+		if (r != CUDA_SUCCESS || !p) {
+			*pfn = p;
+			return r;
+		}
+		gate_real[e->gate][v] = p;
+	}
+	*pfn = e->hook[v];
+	return CUDA_SUCCESS;
+}
+
+static void *hooked_dlsym(int version, void *handle, const char *symbol)
+{
+	if (symbol && symbol[0] == 'c' && symbol[1] == 'u') {
+		const struct entry *e = find_by_elf(symbol);
+		if (e)
+			return e->hook[0];
+	}
+	return real_dlsym_ver(version, handle, symbol);
+}
+
+EXPORT void *nvs_dlsym_225(void *handle, const char *symbol)
+{
+	return hooked_dlsym(0, handle, symbol);
+}
+
+EXPORT void *nvs_dlsym_234(void *handle, const char *symbol)
+{
+	return hooked_dlsym(1, handle, symbol);
+}
+
+__asm__(".symver nvs_dlsym_225, dlsym@@GLIBC_2.2.5");
+__asm__(".symver nvs_dlsym_234, dlsym@GLIBC_2.34");

@@ -13,7 +13,7 @@
 #include <string.h>
 #include <errno.h>
 
-extern int nvs_debug_enabled;
+extern int nvs_debug_enabled __attribute__((visibility("hidden")));
 
 #define nvs_log_at(level, ...)                               \
 	do {                                                 \

@@ -21,8 +21,6 @@
 #include "../../include/nvshare_wire.h"
 #include "nvs_log.h"
 
-int nvs_debug_enabled = 0;
-
 const char *nvs_msg_type_name(unsigned type)
 {
 	static const char *const names[] = {
