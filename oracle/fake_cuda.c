@@ -34,6 +34,7 @@
 #include <time.h>
 #include <unistd.h>
 #include <sys/mman.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
 
 typedef int CUresult;
@@ -69,6 +70,12 @@ static void setup_once(void)
 	if (done)
 		return;
 	done = 1;
+	/* one memfd per mapped chunk: lift the descriptor limit as far as allowed */
+	struct rlimit rl;
+	if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) {
+		rl.rlim_cur = rl.rlim_max;
+		setrlimit(RLIMIT_NOFILE, &rl);
+	}
 	const char *t = getenv("FAKE_CUDA_TOTAL_MIB");
 	g_total = (t ? strtoull(t, NULL, 0) : 4096ull) << 20;
 	const char *tr = getenv("FAKE_CUDA_TRACE");

@@ -1,0 +1,109 @@
+"""Whole stack on CPU: nvshare-scheduler + N unmodified driver-API applications
+(tests/apps/driver_app.c) with libnvshare.so injected by LD_PRELOAD, against
+oracle/fake_cuda.c with a SHARED physical-memory ledger so that the clients are
+genuinely oversubscribed: client B cannot map its working set until client A
+has released HBM, and an access to an evicted slab is a SIGSEGV.
+
+Also the interoperability matrix: our library under the reference daemon and
+the reference library under our daemon (wire compatibility both ways).
+"""
+from __future__ import annotations
+
+import re
+import subprocess
+
+import pytest
+
+from nvs_testlib import ORACLE, Daemon, fake_env, preload
+
+
+def run_clients(daemon_impl, lib_impl, sock_dir, tmp_path, n_clients=2, mib=40, nbuf=3, seconds=4.0, total_mib=200,
+                tq=1, extra=None):
+    d = Daemon(daemon_impl, sock_dir, log_path=tmp_path / "sched.log")
+    try:
+        d.ctl("-T", str(tq))
+        procs = []
+        for i in range(n_clients):
+            env = fake_env(total_mib=total_mib, ledger=tmp_path / "ledger",
+                           extra={"NVSHARE_HOST_ARENA_MIB": 64, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_BATCH_MIB": 32,
+                                  "NVSHARE_DEBUG": 1, **(extra or {})})
+            env["LD_PRELOAD"] = preload(lib_impl)
+            if daemon_impl == "ours":
+                env["NVSHARE_SOCK_DIR"] = str(sock_dir)
+            procs.append(subprocess.Popen([str(ORACLE / "driver_app"), str(mib), str(seconds), str(i + 1), str(nbuf)],
+                                          env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=120) for p in procs]
+        return d.read_log(), [(p.returncode, o, e) for p, (o, e) in zip(procs, outs)]
+    finally:
+        d.stop()
+
+
+def check(results):
+    for rc, out, err in results:
+        assert rc == 0, out + err[-2000:]
+        assert re.search(r"RESULT PASS iters=\d+ mismatches=0", out), out
+
+
+def test_two_clients_oversubscribed(artefacts, sock_dir, tmp_path):
+    # 2 x 120 MiB of allocations on a 200 MiB "GPU": 1.2x oversubscribed
+    log, results = run_clients("ours", "ours", sock_dir, tmp_path)
+    check(results)
+    assert log.count("Sent DROP_LOCK") >= 3
+    evicts = [len(re.findall(r"engine: evict", err)) for _, _, err in results]
+    fetches = [len(re.findall(r"engine: fetch", err)) for _, _, err in results]
+    assert min(evicts) >= 1 and min(fetches) >= 2           # both clients were swapped out and came back
+
+
+def test_three_clients_late_release_order(artefacts, sock_dir, tmp_path):
+    # eviction completes BEFORE LOCK_RELEASED (no overlap): the conservative ordering must work too
+    log, results = run_clients("ours", "ours", sock_dir, tmp_path, n_clients=3, mib=30, seconds=5.0,
+                               extra={"NVSHARE_EARLY_RELEASE": 0})
+    check(results)
+
+
+@pytest.mark.parametrize("variant", ["ldg", "ce"])
+def test_other_copy_variants(artefacts, sock_dir, tmp_path, variant):
+    log, results = run_clients("ours", "ours", sock_dir, tmp_path, seconds=3.0,
+                               extra={"NVSHARE_COPY_VARIANT": variant})
+    check(results)
+
+
+def test_uvm_mode_two_clients(artefacts, sock_dir, tmp_path):
+    # the reference's mechanism, kept as a mode: managed memory never touches the ledger
+    log, results = run_clients("ours", "ours", sock_dir, tmp_path, seconds=3.0, extra={"NVSHARE_ENGINE": "uvm"})
+    check(results)
+    assert all("engine:" not in err for _, _, err in results)
+
+
+@pytest.mark.reference
+def test_our_library_under_reference_daemon(artefacts, default_sock_lock, tmp_path):
+    log, results = run_clients("reference", "ours", default_sock_lock, tmp_path, seconds=3.0)
+    check(results)
+    assert log.count("Sent DROP_LOCK") >= 2
+
+
+@pytest.mark.reference
+def test_reference_library_under_our_daemon(artefacts, default_sock_lock, tmp_path):
+    # the reference library only knows /var/run/nvshare: run OUR daemon there
+    import os
+    d = None
+    old = os.environ.get("NVSHARE_SOCK_DIR")
+    os.environ["NVSHARE_SOCK_DIR"] = str(default_sock_lock)
+    try:
+        log, results = run_clients("ours", "reference", default_sock_lock, tmp_path, seconds=3.0)
+    finally:
+        if old is None:
+            os.environ.pop("NVSHARE_SOCK_DIR", None)
+        else:
+            os.environ["NVSHARE_SOCK_DIR"] = old
+    check(results)
+    assert log.count("Sent DROP_LOCK") >= 2
+
+
+def test_client_exits_when_scheduler_is_absent(artefacts, sock_dir, tmp_path):
+    env = fake_env(extra={"NVSHARE_SOCK_DIR": sock_dir})
+    env["LD_PRELOAD"] = preload("ours")
+    r = subprocess.run([str(ORACLE / "driver_app"), "4", "0.1", "1"], env=env, capture_output=True, text=True,
+                       timeout=30)
+    assert r.returncode == 1                                 # reference: exit(1) in the host app (client.c:250)
+    assert "[NVSHARE][FATAL]" in r.stderr

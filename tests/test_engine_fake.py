@@ -1,0 +1,282 @@
+"""Host logic of the swap engine (nvshare_b200/csrc/engine.c) through its C-ABI
+(include/nvshare_engine.h), on CPU against oracle/fake_cuda.c.  The fake driver
+executes the copy kernels' byte semantics, so these tests cover descriptor
+generation, chunk state machine, LRU order, pools and error paths -- NOT the
+CUDA kernels themselves (tests/test_gpu_*.py do that on a B200).
+
+Checker: oracle/nvshare_oracle.c (liboracle.so) -- oracle_slab_move,
+oracle_pattern_*.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from nvs_testlib import FAKE_DIR, ORACLE, ROOT
+
+MiB = 1 << 20
+SLAB = 2 * MiB
+
+
+@pytest.fixture(scope="module")
+def fake(artefacts):
+    lib = C.CDLL(str(FAKE_DIR / "libcuda.so.1"), mode=C.RTLD_GLOBAL)
+    lib.fake_cuda_phys_used.restype = C.c_uint64
+    assert lib.cuInit(0) == 0
+    ctx = C.c_void_p()
+    assert lib.cuDevicePrimaryCtxRetain(C.byref(ctx), 0) == 0
+    assert lib.cuCtxSetCurrent(ctx) == 0
+    return lib
+
+
+@pytest.fixture(scope="module")
+def oracle(artefacts):
+    lib = C.CDLL(str(ORACLE / "liboracle.so"))
+    lib.oracle_pattern.restype = C.c_uint64
+    lib.oracle_pattern.argtypes = [C.c_uint64, C.c_uint64]
+    lib.oracle_pattern_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+    lib.oracle_pattern_mismatches.restype = C.c_uint64
+    lib.oracle_pattern_mismatches.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+    lib.oracle_slab_move.argtypes = [C.c_void_p, C.c_uint32]
+    return lib
+
+
+@pytest.fixture()
+def engine(fake):
+    from nvshare_b200 import engine as E
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, batch_bytes=24 * MiB, oom_wait_ms=300)
+    yield e
+    e.close()
+
+
+def view(ptr, nbytes):
+    return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr))
+
+
+def test_version_and_default_config(fake):
+    from nvshare_b200 import engine as E
+    assert b"sm_100a" in E.load().nvs_engine_version()
+    cfg = E.default_config()
+    assert cfg.chunk_bytes == 64 * MiB and cfg.host_arena_bytes == 1024 * MiB
+    assert cfg.tma_stages == 6 and cfg.tma_tile_bytes == 32768 and cfg.tma_warps == 1
+
+
+def test_alloc_is_virtual_until_fetched(engine, fake):
+    base = fake.fake_cuda_phys_used()
+    p = engine.alloc(20 * MiB + 5)           # rounds up to 22 MiB of VA: 3 chunks of 8+8+6
+    st = engine.stats()
+    assert st["va_bytes"] == 22 * MiB and st["unbacked_bytes"] == 22 * MiB and st["resident_bytes"] == 0
+    assert fake.fake_cuda_phys_used() == base
+    rep = engine.fetch_all()
+    assert rep["chunks"] == 3 and rep["bytes"] == 0          # nothing to copy for fresh memory
+    assert fake.fake_cuda_phys_used() == base + 22 * MiB
+    assert engine.stats()["resident_bytes"] == 22 * MiB
+    engine.free(p)
+    assert fake.fake_cuda_phys_used() == base
+
+
+def test_round_trips_are_bit_exact_against_oracle(engine, fake, oracle):
+    sizes = [2 * MiB, 7 * MiB, 8 * MiB, 33 * MiB]            # single slab, ragged, exact chunk, multi-chunk
+    ptrs = [engine.alloc(s) for s in sizes]
+    engine.fetch_all()
+    for k, (p, s) in enumerate(zip(ptrs, sizes)):
+        engine.pattern_fill(p, s // 8, first_index=k << 32, seed=42 + k)
+    for cycle in range(3):
+        rep = engine.evict(0)
+        assert rep["bytes"] == sum((s + SLAB - 1) // SLAB * SLAB for s in sizes)
+        assert engine.stats()["resident_bytes"] == 0
+        rep = engine.fetch_all()
+        assert rep["bytes"] == sum((s + SLAB - 1) // SLAB * SLAB for s in sizes)
+        for k, (p, s) in enumerate(zip(ptrs, sizes)):
+            # checker 1: the oracle's own pattern check on the raw bytes
+            assert oracle.oracle_pattern_mismatches(p, s // 8, k << 32, 42 + k) == 0
+            # checker 2: the engine's verify kernel agrees
+            assert engine.pattern_verify(p, s // 8, first_index=k << 32, seed=42 + k) == 0
+    # the oracle would notice a swapped pair of slabs
+    a = view(ptrs[3], 4 * MiB).copy()
+    view(ptrs[3], 2 * MiB)[:] = a[2 * MiB:]
+    view(ptrs[3] + 2 * MiB, 2 * MiB)[:] = a[:2 * MiB]
+    assert oracle.oracle_pattern_mismatches(ptrs[3], sizes[3] // 8, 3 << 32, 45) > 0
+    for p in ptrs:
+        engine.free(p)
+
+
+@pytest.mark.parametrize("variant", ["tma", "ldg", "ce"])
+def test_copy_slabs_matches_oracle_move(engine, oracle, variant):
+    rng = np.random.default_rng(7)
+    n, size = 9, 3 * SLAB
+    src = np.frombuffer(rng.bytes(size), dtype=np.uint8).copy()
+    dst_eng = np.zeros(size, dtype=np.uint8)
+    dst_orc = np.zeros(size, dtype=np.uint8)
+    # ragged descriptors: 16-byte multiples, shuffled, non-overlapping
+    cuts = sorted(set([0, size] + [int(x) & ~15 for x in rng.integers(16, size - 16, n - 1)]))
+    pieces = [(cuts[i], cuts[i + 1] - cuts[i]) for i in range(len(cuts) - 1) if cuts[i + 1] - cuts[i] <= SLAB]
+    rng.shuffle(pieces)
+    from nvshare_b200.engine import CopyDesc
+    descs = [(src.ctypes.data + off, dst_eng.ctypes.data + off, ln) for off, ln in pieces]
+    ms = engine.copy_slabs(descs, variant=variant, grid=4)
+    assert ms > 0
+    arr = (CopyDesc * len(pieces))()
+    for i, (off, ln) in enumerate(pieces):
+        arr[i].src, arr[i].dst, arr[i].bytes = src.ctypes.data + off, dst_orc.ctypes.data + off, ln
+    oracle.oracle_slab_move(arr, len(pieces))
+    assert np.array_equal(dst_eng, dst_orc)
+
+
+def test_copy_slabs_rejects_misaligned(engine):
+    from nvshare_b200.engine import EngineError
+    buf = np.zeros(4096, dtype=np.uint8)
+    with pytest.raises(EngineError):
+        engine.copy_slabs([(buf.ctypes.data + 8, buf.ctypes.data + 1024, 64)], variant="tma")
+    with pytest.raises(EngineError):
+        engine.copy_slabs([(buf.ctypes.data, buf.ctypes.data + 1024, 24)], variant="tma")
+    assert engine.copy_slabs([], variant="tma") >= 0         # empty list is fine
+
+
+def test_partial_eviction_takes_least_recently_fetched_first(engine):
+    a = engine.alloc(16 * MiB)
+    engine.fetch_all()                      # epoch 1: a
+    b = engine.alloc(16 * MiB)              # resident mode: mapped at once, same epoch as a's
+    engine.evict(0)
+    engine.fetch_all()                      # epoch 2: a and b
+    c = engine.alloc(16 * MiB)
+    st0 = engine.stats()
+    assert st0["resident_bytes"] == 48 * MiB
+    rep = engine.evict(10 * MiB)            # needs two 8 MiB chunks; a's and b's are tied, lowest VA first
+    assert rep["bytes"] == 16 * MiB
+    st = engine.stats()
+    assert st["resident_bytes"] == 32 * MiB and st["swapped_bytes"] == 16 * MiB
+    rep = engine.fetch_all()
+    assert rep["bytes"] == 16 * MiB         # only what was out comes back
+    for p in (a, b, c):
+        engine.free(p)
+
+
+def test_free_while_swapped_returns_backing(engine):
+    p = engine.alloc(24 * MiB)
+    engine.fetch_all()
+    engine.pattern_fill(p, 24 * MiB // 8)
+    engine.evict(0)
+    used = engine.stats()["host_pool_used"]
+    assert used == 24 * MiB
+    engine.free(p)
+    st = engine.stats()
+    assert st["host_pool_used"] == 0 and st["swapped_bytes"] == 0 and st["n_allocs"] == 0
+    q = engine.alloc(24 * MiB)              # pool is reused, not grown
+    engine.fetch_all(); engine.evict(0)
+    assert engine.stats()["host_pool_bytes"] == 64 * MiB
+    engine.free(q)
+
+
+def test_small_allocations_pass_through(engine, fake):
+    base = fake.fake_cuda_phys_used()
+    p = engine.alloc(1000)
+    st = engine.stats()
+    assert st["passthrough_bytes"] == 1000 and st["va_bytes"] == 0
+    assert fake.fake_cuda_phys_used() == base + 1000        # plain device memory, resident for life
+    engine.evict(0)
+    view(p, 1000)[:] = 7                                    # still accessible
+    engine.free(p)
+
+
+def test_free_of_foreign_pointer(engine):
+    from nvshare_b200.engine import EngineError
+    with pytest.raises(EngineError) as ei:
+        engine.free(0x1000)
+    assert ei.value.rc == -2                                # NVS_E_NOT_OURS: the hook falls through to cuMemFree
+
+
+def test_alloc_zero_is_invalid_value(engine):
+    from nvshare_b200.engine import EngineError
+    with pytest.raises(EngineError) as ei:
+        engine.alloc(0)
+    assert ei.value.rc == 1                                 # CUDA_ERROR_INVALID_VALUE
+
+
+def test_fetch_times_out_when_hbm_never_frees(fake, tmp_path):
+    from nvshare_b200 import engine as E
+    ledger = tmp_path / "ledger"
+    code = textwrap.dedent(f"""
+        import ctypes as C, sys
+        sys.path.insert(0, {str(ROOT)!r})
+        fake = C.CDLL({str(FAKE_DIR / 'libcuda.so.1')!r}, mode=C.RTLD_GLOBAL)
+        fake.cuInit(0); ctx = C.c_void_p(); fake.cuDevicePrimaryCtxRetain(C.byref(ctx), 0); fake.cuCtxSetCurrent(ctx)
+        from nvshare_b200 import engine as E
+        e = E.Engine(chunk_bytes=8 << 20, host_arena_bytes=64 << 20, oom_wait_ms=200)
+        p = e.alloc(64 << 20)
+        try:
+            e.fetch_all()
+            print("UNEXPECTED")
+        except E.EngineError as ex:
+            print("RC", ex.rc)
+    """)
+    env = dict(__import__("os").environ, FAKE_CUDA_TOTAL_MIB="32", FAKE_CUDA_LEDGER=str(ledger))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=60)
+    assert "RC -6" in r.stdout, r.stdout + r.stderr         # NVS_E_TIMEOUT
+
+
+def test_evicted_memory_is_unmapped(artefacts):
+    """An access to an evicted slab must fault (fake driver: SIGSEGV), i.e. the
+    physical memory really went away."""
+    code = textwrap.dedent(f"""
+        import ctypes as C, sys
+        sys.path.insert(0, {str(ROOT)!r})
+        fake = C.CDLL({str(FAKE_DIR / 'libcuda.so.1')!r}, mode=C.RTLD_GLOBAL)
+        fake.cuInit(0); ctx = C.c_void_p(); fake.cuDevicePrimaryCtxRetain(C.byref(ctx), 0); fake.cuCtxSetCurrent(ctx)
+        from nvshare_b200 import engine as E
+        e = E.Engine(chunk_bytes=8 << 20, host_arena_bytes=64 << 20)
+        p = e.alloc(16 << 20); e.fetch_all()
+        C.memset(p, 1, 16 << 20); print("resident ok", flush=True)
+        e.evict(0)
+        C.memset(p, 1, 4096); print("STILL MAPPED", flush=True)
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+    assert "resident ok" in r.stdout and "STILL MAPPED" not in r.stdout
+    assert r.returncode == -11
+
+
+def test_peer_tier_is_preferred_and_striped(fake):
+    from nvshare_b200 import engine as E
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=32 * MiB, peers=[1, 2], peer_capacity_bytes=32 * MiB,
+                 prepin=0)
+    try:
+        p = e.alloc(80 * MiB)
+        e.fetch_all()
+        e.pattern_fill(p, 80 * MiB // 8, seed=5)
+        rep = e.evict(0)
+        # two peers x 32 MiB capacity take 64 MiB, the remaining 16 MiB spill to pinned host memory
+        assert rep["peer_bytes"] == 64 * MiB and rep["host_bytes"] == 16 * MiB
+        st = e.stats()
+        assert st["peer_pool_used"] == 64 * MiB and st["host_pool_used"] == 16 * MiB
+        rep = e.fetch_all()
+        assert rep["peer_bytes"] == 64 * MiB and rep["host_bytes"] == 16 * MiB
+        assert e.pattern_verify(p, 80 * MiB // 8, seed=5) == 0
+        e.free(p)
+    finally:
+        e.close()
+
+
+def test_bad_geometry_is_rejected(fake):
+    from nvshare_b200 import engine as E
+    with pytest.raises(E.EngineError):
+        E.Engine(chunk_bytes=3 * MiB)                       # not a multiple of the 2 MiB slab
+    with pytest.raises(E.EngineError):
+        E.Engine(tma_stages=1)
+    with pytest.raises(E.EngineError):
+        E.Engine(tma_warps=4, tma_stages=6, tma_tile_bytes=32768)   # 768 KiB of shared memory
+
+
+def test_stats_file(fake, tmp_path):
+    import json
+    from nvshare_b200 import engine as E
+    path = tmp_path / "stats.jsonl"
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, stats_path=str(path))
+    p = e.alloc(16 * MiB); e.fetch_all(); e.evict(0); e.fetch_all(); e.free(p); e.close()
+    recs = [json.loads(l) for l in path.read_text().splitlines()]
+    assert [r["op"] for r in recs] == ["fetch", "evict", "fetch"]
+    assert recs[1]["bytes"] == 16 * MiB and recs[1]["slabs"] == 8 and recs[1]["launches"] >= 1
