@@ -1,0 +1,275 @@
+"""Measurement harness for BASELINE configs #2/#3: N co-located clients of
+nvshare_b200/workloads.py under a libnvshare.so + nvshare-scheduler pair (ours
+or the reference's), and the analysis that turns their per-iteration logs into
+the headline numbers.  Used by bench.py for BOTH arms, so the two are measured
+by identical code.
+
+Definitions (SURVEY 8d / BASELINE.md section 2):
+  hand-off     a change of the client that is completing iterations
+  tau          steady iteration time of a client with its working set resident
+               (10th percentile of its iteration durations)
+  lost time    window wall time minus (iterations completed in the window) x tau,
+               summed over the clients; divided by the number of hand-offs in the
+               window it is the stall per hand-off.  Slow post-resume iterations
+               (the reference's fault storm) count in full.
+  algorithmic bytes per hand-off
+               what MUST cross the link so that the next client is resident:
+               (n_clients * F - C_avail) in, the same amount out, where F is a
+               client's footprint and C_avail the HBM the clients share
+  e2e swap GB/s = algorithmic bytes per hand-off / stall per hand-off
+"""
+from __future__ import annotations
+
+import json
+import os
+import signal
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+BUILD = ROOT / "nvshare_b200" / "_build"
+REF = ROOT / "oracle" / "_ref"
+
+
+def impl_paths(impl: str):
+    base = BUILD if impl == "ours" else REF
+    return {"lib": base / "libnvshare.so", "sched": base / "nvshare-scheduler", "ctl": base / "nvsharectl"}
+
+
+# ----------------------------------------------------------------- analysis --
+
+def load_iters(path):
+    """[(t_complete, index)] for one client, plus its setup/summary records."""
+    iters, meta = [], {}
+    for line in Path(path).read_text().splitlines():
+        try:
+            r = json.loads(line)
+        except json.JSONDecodeError:
+            continue
+        if r.get("event") == "iter":
+            iters.append(r["t"])
+        elif r.get("event") in ("setup_done", "summary"):
+            meta[r["event"]] = r
+    return iters, meta
+
+
+def steady_tau(ts):
+    d = sorted(b - a for a, b in zip(ts, ts[1:]) if b > a)
+    if not d:
+        return float("nan")
+    return d[max(0, len(d) // 10)]
+
+
+def merged_timeline(clients):
+    """clients: {name: [t...]} -> sorted [(t, name)]"""
+    ev = [(t, n) for n, ts in clients.items() for t in ts]
+    ev.sort()
+    return ev
+
+
+def handoff_boundaries(timeline):
+    """Times at which the completing client changes: (t_last_of_previous, prev, nxt)."""
+    out = []
+    for (t0, a), (t1, b) in zip(timeline, timeline[1:]):
+        if a != b:
+            out.append((t0, a, b))
+    return out
+
+
+def analyse(clients, warmup, steps):
+    """clients: {name: [iteration completion times]}.  Returns the window metrics
+    over exactly `steps` hand-offs after `warmup` hand-offs, or raises."""
+    tl = merged_timeline(clients)
+    bounds = handoff_boundaries(tl)
+    if len(bounds) < warmup + steps + 1:
+        raise RuntimeError(f"only {len(bounds)} hand-offs observed, need {warmup + steps + 1}")
+    t_start = bounds[warmup][0]
+    t_end = bounds[warmup + steps][0]
+    taus = {n: steady_tau(ts) for n, ts in clients.items()}
+    n_iters = {n: sum(1 for t in ts if t_start < t <= t_end) for n, ts in clients.items()}
+    busy = sum(n_iters[n] * taus[n] for n in clients)
+    wall = t_end - t_start
+    lost = max(wall - busy, 0.0)
+    # per-hand-off gap: last iteration of the leaving client -> first iteration of the arriving one
+    gaps = []
+    for k in range(warmup, warmup + steps):
+        t_last, a, b = bounds[k]
+        t_first = next(t for t, n in tl if t > t_last and n == b)
+        gaps.append(t_first - t_last - taus[b])
+    return {
+        "window_s": wall, "t_start": t_start, "t_end": t_end, "handoffs": steps,
+        "iters": n_iters, "tau_s": taus, "iter_per_s": sum(n_iters.values()) / wall,
+        "iter_per_s_resident": {n: 1.0 / taus[n] for n in clients},
+        "lost_s": lost, "stall_per_handoff_s": lost / steps, "first_iter_gap_s": gaps,
+        "gpu_busy_frac": busy / wall,
+    }
+
+
+def engine_records(paths, t_start, t_end):
+    """Engine stats lines (ours only) whose operation ended inside the window."""
+    recs = []
+    for p in paths:
+        p = Path(p)
+        if not p.exists():
+            continue
+        for line in p.read_text().splitlines():
+            try:
+                r = json.loads(line)
+            except json.JSONDecodeError:
+                continue
+            if t_start < r.get("t", 0) <= t_end + 1.0:
+                recs.append(r)
+    return recs
+
+
+# ------------------------------------------------------------------ running --
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, path, gpu=0):
+        self.path = Path(path)
+        self.p = None
+        self.gpu = gpu
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except FileNotFoundError:
+            self.p = None
+
+    def stop(self, t_start=None, t_end=None):
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        sm, smax, reasons = [], [], set()
+        if self.path.exists():
+            for line in self.path.read_text().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def start_scheduler(impl, sock_dir, log_path, tq):
+    paths = impl_paths(impl)
+    env = dict(os.environ, NVSHARE_DEBUG="1")
+    if impl == "ours":
+        env["NVSHARE_SOCK_DIR"] = str(sock_dir)
+    sock = Path(sock_dir) / "scheduler.sock"
+    if sock.exists():
+        sock.unlink()
+    log = open(log_path, "wb")
+    p = subprocess.Popen([str(paths["sched"])], env=env, stdout=log, stderr=subprocess.STDOUT)
+    deadline = time.time() + 10
+    while not sock.exists():
+        if p.poll() is not None or time.time() > deadline:
+            raise RuntimeError(f"{impl} nvshare-scheduler did not start; see {log_path}")
+        time.sleep(0.02)
+    time.sleep(0.1)
+    r = subprocess.run([str(paths["ctl"]), "-T", str(int(tq))], env=env, capture_output=True, text=True)
+    if r.returncode != 0:
+        p.kill()
+        raise RuntimeError(f"nvsharectl -T failed: {r.stderr}")
+    return p
+
+
+def stop_process(p, timeout=10):
+    if p is None or p.poll() is not None:
+        return
+    p.send_signal(signal.SIGTERM)
+    try:
+        p.wait(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        p.wait()
+
+
+def count_handoffs(out_dir, n_clients):
+    clients = {}
+    for i in range(n_clients):
+        f = Path(out_dir) / f"client{i}.jsonl"
+        clients[f"client{i}"] = load_iters(f)[0] if f.exists() else []
+    return len(handoff_boundaries(merged_timeline(clients)))
+
+
+def run_clients(impl, out_dir, n_clients, kind, n, pattern, seconds, tq, extra_env=None, start_stagger=0.0,
+                stop_after_handoffs=0):
+    """Run the co-located clients until `stop_after_handoffs` hand-offs have been
+    observed (or `seconds` elapsed); each client then verifies its results.
+    Returns per-client dicts."""
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    paths = impl_paths(impl)
+    sock_dir = out_dir / "sock" if impl == "ours" else Path("/var/run/nvshare")
+    sock_dir.mkdir(parents=True, exist_ok=True)
+    sched = start_scheduler(impl, sock_dir, out_dir / "scheduler.log", tq)
+    barrier = out_dir / "go"
+    stop_file = out_dir / "stop"
+    for f in (barrier, stop_file):
+        if f.exists():
+            f.unlink()
+    procs = []
+    try:
+        for i in range(n_clients):
+            env = dict(os.environ, LD_PRELOAD=str(paths["lib"]), PYTHONPATH=str(ROOT))
+            if impl == "ours":
+                env["NVSHARE_SOCK_DIR"] = str(sock_dir)
+                env["NVSHARE_STATS_FILE"] = str(out_dir / f"engine{i}.jsonl")
+            env.update({k: str(v) for k, v in (extra_env or {}).items()})
+            cmd = [sys.executable, "-m", "nvshare_b200.workloads", "--kind", kind, "--n", str(n), "--iters", "100000000",
+                   "--seconds", str(seconds), "--pattern", pattern, "--log", str(out_dir / f"client{i}.jsonl"),
+                   "--tag", f"client{i}", "--start-barrier", str(barrier), "--stop-file", str(stop_file)]
+            procs.append(subprocess.Popen(cmd, env=env, cwd=ROOT, stdout=open(out_dir / f"client{i}.out", "w"),
+                                          stderr=open(out_dir / f"client{i}.err", "w")))
+            time.sleep(start_stagger)
+        # release the clients together once each has built its inputs
+        deadline = time.time() + 1800
+        while time.time() < deadline:
+            ready = 0
+            for i in range(n_clients):
+                f = out_dir / f"client{i}.jsonl"
+                if f.exists() and '"setup_done"' in f.read_text():
+                    ready += 1
+            if ready == n_clients or any(p.poll() is not None for p in procs):
+                break
+            time.sleep(0.2)
+        barrier.write_text("go")
+        t_go = time.time()
+        while any(p.poll() is None for p in procs) and time.time() - t_go < seconds + 60:
+            time.sleep(1.0)
+            if stop_after_handoffs and not stop_file.exists() and count_handoffs(out_dir, n_clients) >= stop_after_handoffs:
+                stop_file.write_text("stop")
+        for p in procs:
+            p.wait(timeout=1800)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        stop_process(sched)
+    res = []
+    for i, p in enumerate(procs):
+        iters, meta = load_iters(out_dir / f"client{i}.jsonl") if (out_dir / f"client{i}.jsonl").exists() else ([], {})
+        res.append({"rc": p.returncode, "iters": iters, "meta": meta, "out": (out_dir / f"client{i}.out").read_text()[-2000:],
+                    "err_tail": (out_dir / f"client{i}.err").read_text()[-3000:]})
+    return res

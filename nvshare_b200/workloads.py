@@ -58,6 +58,7 @@ def run(argv=None) -> int:
     ap.add_argument("--log", default="", help="JSON-lines file: one record per iteration + a summary")
     ap.add_argument("--tag", default="client")
     ap.add_argument("--start-barrier", default="", help="path: wait until this file exists before iterating")
+    ap.add_argument("--stop-file", default="", help="path: finish the loop (then verify) once this file exists")
     args = ap.parse_args(argv)
 
     import torch
@@ -115,6 +116,8 @@ def run(argv=None) -> int:
         it += 1
         emit({"event": "iter", "i": it, "t": now})
         if args.seconds > 0 and now - t_loop >= args.seconds:
+            break
+        if args.stop_file and (it & 15) == 0 and os.path.exists(args.stop_file):
             break
     t_end = time.time()
 

@@ -1,0 +1,206 @@
+"""Parity tests proper: the sm_100a kernels and the swap engine on a real B200,
+called through the C-ABI (libnvs_engine.so), checked bit-exact against the CPU
+oracle (oracle/nvshare_oracle.c) on the same seeded inputs, plus
+size-independent round-trip properties at sizes the oracle would take too long
+for.  torch is used only to obtain a CUDA context and raw device / pinned
+buffers."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from nvs_testlib import ORACLE
+
+pytestmark = pytest.mark.gpu
+
+MiB = 1 << 20
+GiB = 1 << 30
+SLAB = 2 * MiB
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")          # makes the primary context current on this thread
+    return torch
+
+
+@pytest.fixture(scope="module")
+def oracle(artefacts):
+    lib = C.CDLL(str(ORACLE / "liboracle.so"))
+    lib.oracle_pattern_mismatches.restype = C.c_uint64
+    lib.oracle_pattern_mismatches.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+    lib.oracle_pattern_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+    lib.oracle_slab_move.argtypes = [C.c_void_p, C.c_uint32]
+    return lib
+
+
+@pytest.fixture()
+def engine(torch_cuda, artefacts):
+    from nvshare_b200 import engine as E
+    e = E.Engine()                          # production defaults: 64 MiB chunks, TMA both ways
+    yield e
+    e.close()
+
+
+def ragged_pieces(rng, size, n):
+    cuts = sorted(set([0, size] + [int(x) & ~15 for x in rng.integers(16, size - 16, n - 1)]))
+    pieces = [(cuts[i], cuts[i + 1] - cuts[i]) for i in range(len(cuts) - 1)]
+    out = []
+    for off, ln in pieces:                  # a descriptor never exceeds one slab
+        while ln > 0:
+            step = min(ln, SLAB)
+            out.append((off, step))
+            off += step
+            ln -= step
+    rng.shuffle(out)
+    return out
+
+
+@pytest.mark.parametrize("variant,grid", [("tma", 1), ("tma", 8), ("tma", 148), ("ldg", 8), ("ldg", 148), ("ce", 0)])
+def test_copy_kernels_match_oracle_device_to_device(torch_cuda, engine, oracle, variant, grid):
+    torch = torch_cuda
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    size = 24 * MiB
+    src_h = torch.randint(0, 256, (size,), dtype=torch.uint8, generator=g)
+    src = src_h.cuda()
+    dst = torch.zeros(size, dtype=torch.uint8, device="cuda")
+    pieces = ragged_pieces(np.random.default_rng(5), size, 40)
+    ms = engine.copy_slabs([(src.data_ptr() + o, dst.data_ptr() + o, n) for o, n in pieces], variant=variant, grid=grid)
+    assert ms > 0
+    # oracle: the same descriptor list applied with memcpy on host copies
+    from nvshare_b200.engine import CopyDesc
+    src_np = src_h.numpy()
+    want = np.zeros(size, dtype=np.uint8)
+    arr = (CopyDesc * len(pieces))()
+    for i, (o, n) in enumerate(pieces):
+        arr[i].src, arr[i].dst, arr[i].bytes = src_np.ctypes.data + o, want.ctypes.data + o, n
+    oracle.oracle_slab_move(arr, len(pieces))
+    torch.cuda.synchronize()
+    assert np.array_equal(dst.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("variant", ["tma", "ldg", "ce"])
+def test_copy_kernels_to_and_from_pinned_host(torch_cuda, engine, oracle, variant):
+    """The swap path itself: HBM -> pinned host -> HBM, each leg checked against the oracle."""
+    torch = torch_cuda
+    size = 64 * MiB
+    words = size // 8
+    dev = torch.empty(size, dtype=torch.uint8, device="cuda")
+    host = torch.zeros(size, dtype=torch.uint8).pin_memory()
+    back = torch.zeros(size, dtype=torch.uint8, device="cuda")
+    engine.pattern_fill(dev.data_ptr(), words, first_index=99, seed=3)
+    slabs = [(i * SLAB, SLAB) for i in range(size // SLAB)]
+    engine.copy_slabs([(dev.data_ptr() + o, host.data_ptr() + o, n) for o, n in slabs], variant=variant, grid=8)
+    assert oracle.oracle_pattern_mismatches(host.data_ptr(), words, 99, 3) == 0      # CPU reads what the GPU wrote
+    engine.copy_slabs([(host.data_ptr() + o, back.data_ptr() + o, n) for o, n in reversed(slabs)], variant=variant,
+                      grid=8)
+    assert engine.pattern_verify(back.data_ptr(), words, first_index=99, seed=3) == 0
+    assert torch.equal(dev, back)
+
+
+def test_pattern_kernels_agree_with_oracle(torch_cuda, engine, oracle):
+    torch = torch_cuda
+    words = (8 * MiB) // 8
+    dev = torch.empty(words, dtype=torch.int64, device="cuda")
+    engine.pattern_fill(dev.data_ptr(), words, first_index=1 << 40, seed=77)
+    host = dev.cpu().numpy()
+    assert oracle.oracle_pattern_mismatches(host.ctypes.data, words, 1 << 40, 77) == 0
+    want = np.empty(words, dtype=np.uint64)
+    oracle.oracle_pattern_fill(want.ctypes.data, words, 1 << 40, 77)
+    assert np.array_equal(host.view(np.uint64), want)
+    dev[12345] ^= 1                                                                   # one flipped bit is seen
+    assert engine.pattern_verify(dev.data_ptr(), words, first_index=1 << 40, seed=77) == 1
+
+
+def test_edge_cases(torch_cuda, engine):
+    torch = torch_cuda
+    buf = torch.zeros(4 * MiB, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(4 * MiB, dtype=torch.uint8, device="cuda")
+    buf[:] = torch.arange(4 * MiB, device="cuda") % 251
+    p, q = buf.data_ptr(), out.data_ptr()
+    assert engine.copy_slabs([], variant="tma") >= 0                                  # empty
+    engine.copy_slabs([(p, q, 16)], variant="tma", grid=4)                            # minimum bulk size
+    engine.copy_slabs([(p + 16, q + 16, 0), (p + 32, q + 32, 48)], variant="tma")     # zero-length descriptor skipped
+    engine.copy_slabs([(p + 1024, q + 1024, 1000)], variant="ldg")                    # 8-byte tail on the LDG variant
+    torch.cuda.synchronize()
+    assert torch.equal(out[:16], buf[:16]) and torch.equal(out[32:80], buf[32:80])
+    assert int(out[16:32].sum()) == 0
+    assert torch.equal(out[1024:2024], buf[1024:2024]) and int(out[2024:2048].sum()) == 0
+    # many tiny descriptors (more descriptors than CTAs x stages)
+    n = 4096
+    descs = [(p + 4096 + i * 256, q + 4096 + i * 256, 256) for i in range(n)]
+    engine.copy_slabs(descs, variant="tma", grid=16)
+    torch.cuda.synchronize()
+    assert torch.equal(out[4096:4096 + n * 256], buf[4096:4096 + n * 256])
+
+
+def test_engine_round_trips_release_hbm(torch_cuda, engine):
+    torch = torch_cuda
+    sizes = [3 * GiB + 6 * MiB, 512 * MiB, 2 * MiB, 70 * MiB]
+    ptrs = [engine.alloc(s) for s in sizes]
+    engine.fetch_all()
+    for k, (p, s) in enumerate(zip(ptrs, sizes)):
+        engine.pattern_fill(p, s // 8, first_index=k << 36, seed=42)
+    total = sum((s + SLAB - 1) // SLAB * SLAB for s in sizes)
+    free_resident, _ = torch.cuda.mem_get_info()
+    for cycle in range(2):
+        rep = engine.evict(0)
+        assert rep["bytes"] == total and rep["slabs"] == total // SLAB
+        free_out, _ = torch.cuda.mem_get_info()
+        assert free_out - free_resident >= total - 64 * MiB                           # the HBM really went back
+        assert engine.stats()["resident_bytes"] == 0
+        rep = engine.fetch_all()
+        assert rep["bytes"] == total
+        for k, (p, s) in enumerate(zip(ptrs, sizes)):
+            assert engine.pattern_verify(p, s // 8, first_index=k << 36, seed=42) == 0
+    # partial eviction, then the application "computes" on everything again
+    rep = engine.evict(1 * GiB)
+    assert 1 * GiB <= rep["bytes"] <= 1 * GiB + 64 * MiB
+    engine.fetch_all()
+    assert engine.pattern_verify(ptrs[0], sizes[0] // 8, first_index=0, seed=42) == 0
+    st = engine.stats()
+    assert st["kernel_launches_total"] > 0
+    for p in ptrs:
+        engine.free(p)
+
+
+@pytest.mark.parametrize("evict_v,fetch_v", [("ldg", "ldg"), ("ce", "ce"), ("tma", "ce")])
+def test_engine_variants(torch_cuda, artefacts, evict_v, fetch_v):
+    from nvshare_b200 import engine as E
+    e = E.Engine(evict_variant=evict_v, fetch_variant=fetch_v)
+    try:
+        p = e.alloc(1 * GiB + 2 * MiB)
+        e.fetch_all()
+        e.pattern_fill(p, (1 * GiB + 2 * MiB) // 8, seed=9)
+        e.evict(0)
+        e.fetch_all()
+        assert e.pattern_verify(p, (1 * GiB + 2 * MiB) // 8, seed=9) == 0
+    finally:
+        e.close()
+
+
+def test_torch_can_use_engine_memory(torch_cuda, engine):
+    """Memory handed out by nvs_alloc behaves like cuMemAlloc memory for CUDA
+    libraries: wrap it with torch via the CUDA array interface and compute."""
+    torch = torch_cuda
+    n = 1 << 24
+    p = engine.alloc(n * 4)
+    engine.fetch_all()
+
+    class Raw:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+    t = torch.as_tensor(Raw(p, n), device="cuda")
+    t.fill_(1.0)
+    torch.cuda.synchronize()
+    engine.evict(0)
+    engine.fetch_all()
+    assert float((t + t).sum().item()) == 2.0 * n                                     # the add test's exact value
+    del t
+    engine.free(p)

@@ -1,0 +1,87 @@
+"""Host logic of the measurement harness (nvshare_b200/harness.py) and of
+bench.py's multi-rank plumbing, on CPU: the hand-off / stall analysis on
+synthetic timelines, and a world_size-2 gloo run of the reduction path."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+from nvshare_b200 import harness
+from nvs_testlib import ROOT
+
+
+def synth(tau=0.02, quantum=1.0, stall=0.5, handoffs=8, slow_first=0.0):
+    """Two clients alternating; every hand-off costs `stall` seconds before the arriving
+    client's first iteration (plus `slow_first` spread over its first iteration)."""
+    t, clients, who = 0.0, {"client0": [], "client1": []}, 0
+    for _ in range(handoffs + 1):
+        name = f"client{who}"
+        t += stall
+        first = True
+        end = t + quantum
+        while t < end:
+            t += tau + (slow_first if first else 0.0)
+            first = False
+            clients[name].append(t)
+        who ^= 1
+    return clients
+
+
+def test_analysis_recovers_stall_and_rate():
+    c = synth(tau=0.02, quantum=1.0, stall=0.5, handoffs=10)
+    a = harness.analyse(c, warmup=3, steps=4)
+    assert a["handoffs"] == 4
+    assert abs(a["stall_per_handoff_s"] - 0.5) < 0.03
+    assert abs(a["tau_s"]["client0"] - 0.02) < 1e-6
+    # 1 s of work per 1.5 s of wall: ~33 iterations/s overall, 50/s when resident
+    assert abs(a["iter_per_s"] - (1.0 / 0.02) / 1.5) < 1.5
+    assert abs(a["iter_per_s_resident"]["client1"] - 50) < 1e-6
+    assert all(abs(g - 0.5) < 0.03 for g in a["first_iter_gap_s"])
+
+
+def test_slow_post_resume_iterations_count_as_stall():
+    # the reference's shape: no clean gap, but the first iteration after a hand-off is slow
+    c = synth(tau=0.02, quantum=1.0, stall=0.0, handoffs=10, slow_first=0.7)
+    a = harness.analyse(c, warmup=2, steps=5)
+    assert abs(a["stall_per_handoff_s"] - 0.7) < 0.03
+
+
+def test_not_enough_handoffs_is_an_error():
+    c = synth(handoffs=3)
+    with pytest.raises(RuntimeError):
+        harness.analyse(c, warmup=3, steps=4)
+
+
+def test_boundaries():
+    tl = harness.merged_timeline({"a": [1, 2, 5], "b": [3, 4, 6]})
+    assert [n for _, n in tl] == ["a", "a", "b", "b", "a", "b"]
+    assert [(a, b) for _, a, b in harness.handoff_boundaries(tl)] == [("a", "b"), ("b", "a"), ("a", "b")]
+
+
+def test_world_size_2_gloo_reduction(tmp_path):
+    """bench.py's N>1 plumbing: barrier + MAX over ranks, rank 0 alone reports (gloo on CPU)."""
+    code = textwrap.dedent("""
+        import os, sys, json, torch, torch.distributed as dist
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        t_region = 3.5 if rank == 0 else 0.0          # only rank 0 does data-path work
+        dist.barrier()
+        t = torch.tensor([t_region], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        if rank == 0:
+            print(json.dumps({"max_s": t.item(), "n_gpus": world}))
+        dist.destroy_process_group()
+    """)
+    script = tmp_path / "w2.py"
+    script.write_text(code)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and '"max_s": 3.5' in lines[0] and '"n_gpus": 2' in lines[0]

@@ -28,6 +28,7 @@
 #include <time.h>
 #include <unistd.h>
 #include <sys/mman.h>
+#include <pthread.h>
 #include <vector>
 #include <algorithm>
 
@@ -705,9 +706,181 @@ static int section_f(void)
 	return 0;
 }
 
+/* --------------------------------------------------------------- G ------ */
+/* Two PROCESSES sharing the GPU, one evicting (HBM->host) and one fetching
+ * (host->HBM) at the same time: does the link run full duplex across contexts,
+ * and does it depend on kernel vs copy engine?  (The engine's early-release
+ * overlap is exactly this situation.) */
+#include <sys/wait.h>
+struct SharedG {
+	volatile int ready;
+	volatile int go;
+	double gbps[2];
+	double secs[2];
+};
+
+static int child_g(int role, int variant, SharedG *sh, int n_procs)
+{
+	if (cuInit(0) != CUDA_SUCCESS || cudaSetDevice(0) != cudaSuccess || cudaFree(0) != cudaSuccess)
+		return 1;
+	CUdevice dev;
+	cuDeviceGet(&dev, 0);
+	cuDeviceGetAttribute(&g_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev);
+	Bufs b;
+	memset(&b, 0, sizeof b);
+	b.bytes = 4 * GiB;
+	b.n_slabs = b.bytes / NVS_SLAB_BYTES;
+	CU(cuMemAlloc(&b.dev_a, b.bytes));
+	CU(cuMemHostAlloc((void **)&b.host_a, b.bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+	CU(cuMemHostAlloc((void **)&b.descs_h, 2 * b.n_slabs * sizeof(nvs_copy_desc), CU_MEMHOSTALLOC_PORTABLE));
+	RT(cudaMalloc(&b.descs_d[0], b.n_slabs * sizeof(nvs_copy_desc)));
+	RT(cudaMalloc(&b.counters, 64));
+	RT(cudaStreamCreateWithFlags(&b.st[0], cudaStreamNonBlocking));
+	RT(cudaFuncSetAttribute(nvs_slab_copy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	memset(b.host_a, 1, b.bytes);
+	RT(cudaMemset((void *)b.dev_a, 2, b.bytes));
+	uint64_t src = role == 0 ? b.dev_a : (uint64_t)b.host_a;
+	uint64_t dst = role == 0 ? (uint64_t)b.host_a : b.dev_a;
+	build_descs(b, 0, src, dst);
+	Geo g = {variant, 8, variant == NVS_COPY_LDG ? 8 : 1, 6, 32768};
+	/* warm-up */
+	if (variant == NVS_COPY_CE) {
+		for (size_t off = 0; off < b.bytes; off += 64 * MiB)
+			CU(cuMemcpyAsync(dst + off, src + off, 64 * MiB, b.st[0]));
+	} else if (launch_copy(b, 0, g, b.st[0]))
+		return 1;
+	RT(cudaStreamSynchronize(b.st[0]));
+	__sync_fetch_and_add(&sh->ready, 1);
+	while (sh->ready < n_procs || !sh->go)
+		usleep(100);
+	const int reps = 6;
+	double t0 = now_s();
+	for (int r = 0; r < reps; ++r) {
+		if (variant == NVS_COPY_CE) {
+			for (size_t off = 0; off < b.bytes; off += 64 * MiB)
+				CU(cuMemcpyAsync(dst + off, src + off, 64 * MiB, b.st[0]));
+		} else if (launch_copy(b, 0, g, b.st[0]))
+			return 1;
+	}
+	RT(cudaStreamSynchronize(b.st[0]));
+	double t = now_s() - t0;
+	sh->gbps[role] = reps * (double)b.bytes / 1e9 / t;
+	sh->secs[role] = t;
+	return 0;
+}
+
+static int section_g(void)
+{
+	SharedG *sh = (SharedG *)mmap(NULL, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+	const int combos[][2] = {{NVS_COPY_TMA, -1}, {-1, NVS_COPY_TMA}, {NVS_COPY_CE, -1}, {-1, NVS_COPY_CE},
+				 {NVS_COPY_TMA, NVS_COPY_TMA}, {NVS_COPY_CE, NVS_COPY_CE},
+				 {NVS_COPY_TMA, NVS_COPY_CE}, {NVS_COPY_CE, NVS_COPY_TMA},
+				 {NVS_COPY_LDG, NVS_COPY_LDG}};
+	for (auto &c : combos) {
+		memset((void *)sh, 0, sizeof *sh);
+		int n_procs = (c[0] >= 0) + (c[1] >= 0);
+		pid_t pids[2] = {0, 0};
+		for (int role = 0; role < 2; ++role) {
+			if (c[role] < 0)
+				continue;
+			pids[role] = fork();
+			if (pids[role] == 0)
+				_exit(child_g(role, c[role], sh, n_procs));
+		}
+		while (sh->ready < n_procs) {
+			int st;
+			pid_t w = waitpid(-1, &st, WNOHANG);
+			if (w > 0) { printf("PROBE {\"section\":\"G\",\"error\":\"child died early\"}\n"); break; }
+			usleep(1000);
+		}
+		sh->go = 1;
+		for (int role = 0; role < 2; ++role)
+			if (pids[role] > 0) {
+				int st;
+				waitpid(pids[role], &st, 0);
+			}
+		printf("PROBE {\"section\":\"G\",\"evict_variant\":\"%s\",\"fetch_variant\":\"%s\",\"evict_GBps\":%.2f,"
+		       "\"fetch_GBps\":%.2f,\"sum_GBps\":%.2f,\"evict_s\":%.2f,\"fetch_s\":%.2f}\n",
+		       c[0] < 0 ? "-" : vname(c[0]), c[1] < 0 ? "-" : vname(c[1]), sh->gbps[0], sh->gbps[1],
+		       sh->gbps[0] + sh->gbps[1], sh->secs[0], sh->secs[1]);
+		fflush(stdout);
+	}
+	return 0;
+}
+
+/* --------------------------------------------------------------- H ------ */
+static long long read_ll(const char *path)
+{
+	FILE *f = fopen(path, "r");
+	long long v = -1;
+	if (f) {
+		if (fscanf(f, "%lld", &v) != 1)
+			v = -1;
+		fclose(f);
+	}
+	return v;
+}
+
+static void *pin_worker(void *arg)
+{
+	CUcontext ctx = (CUcontext)arg;
+	cuCtxSetCurrent(ctx);
+	void *p = NULL;
+	cuMemHostAlloc(&p, 2 * GiB, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP);
+	return p;
+}
+
+static int section_h(void)
+{
+	const char *cur = "/sys/fs/cgroup/memory.current";
+	long long limit = read_ll("/sys/fs/cgroup/memory.max");
+	long long before = read_ll(cur);
+	void *p = NULL;
+	CU(cuMemHostAlloc(&p, 8 * GiB, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+	memset(p, 1, 8 * GiB);
+	long long after = read_ll(cur);
+	printf("PROBE {\"section\":\"H\",\"what\":\"cuMemHostAlloc 8 GiB vs cgroup\",\"cgroup_limit\":%lld,"
+	       "\"current_before\":%lld,\"current_after\":%lld,\"charged_bytes\":%lld}\n", limit, before, after, after - before);
+	CU(cuMemFreeHost(p));
+	/* UVM: host copies of evicted managed pages -- are THEY charged? */
+	CUdeviceptr m = 0;
+	CU(cuMemAllocManaged(&m, 8 * GiB, CU_MEM_ATTACH_GLOBAL));
+	RT(cudaMemset((void *)m, 1, 8 * GiB));
+	RT(cudaDeviceSynchronize());
+	before = read_ll(cur);
+	CU(cuMemPrefetchAsync(m, 8 * GiB, CU_DEVICE_CPU, 0));
+	RT(cudaDeviceSynchronize());
+	after = read_ll(cur);
+	printf("PROBE {\"section\":\"H\",\"what\":\"8 GiB managed memory evicted to host vs cgroup\",\"charged_bytes\":%lld}\n",
+	       after - before);
+	CU(cuMemFree(m));
+	/* does pinning parallelise across threads? */
+	CUcontext ctx;
+	CU(cuCtxGetCurrent(&ctx));
+	for (int nt : {1, 4, 8}) {
+		pthread_t th[8];
+		double t0 = now_s();
+		for (int i = 0; i < nt; ++i)
+			pthread_create(&th[i], NULL, pin_worker, ctx);
+		void *ptrs[8];
+		for (int i = 0; i < nt; ++i)
+			pthread_join(th[i], &ptrs[i]);
+		double t = now_s() - t0;
+		printf("PROBE {\"section\":\"H\",\"what\":\"parallel cuMemHostAlloc\",\"threads\":%d,\"GiB\":%d,\"seconds\":%.2f,"
+		       "\"GBps\":%.2f}\n", nt, 2 * nt, t, 2.0 * nt * GiB / 1e9 / t);
+		fflush(stdout);
+		for (int i = 0; i < nt; ++i)
+			if (ptrs[i])
+				cuMemFreeHost(ptrs[i]);
+	}
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
 	const char *sections = argc > 1 ? argv[1] : "ABCDEF";
+	if (argc > 1 && !strcmp(argv[1], "G")) /* forks before any CUDA initialisation */
+		return section_g();
 	if (argc > 2)
 		g_scale_gib = strtoull(argv[2], NULL, 0);
 	if (cuInit(0) != CUDA_SUCCESS) {
@@ -729,6 +902,7 @@ int main(int argc, char **argv)
 		case 'D': r = section_d(); break;
 		case 'E': r = section_e(); break;
 		case 'F': r = section_f(); break;
+		case 'H': r = section_h(); break;
 		default: break;
 		}
 		printf("PROBE {\"section_done\":\"%c\",\"rc\":%d,\"seconds\":%.1f}\n", *s, r, now_s() - t0);
