@@ -234,6 +234,8 @@ struct nvs_engine {
 	pthread_t pin_thread;
 	int pin_thread_started;
 	pthread_cond_t pin_cv;
+	pthread_cond_t grow_cv; /* an arena finished pinning (or failed) */
+	int growing;            /* a thread is inside cuMemHostAlloc for a new arena */
 	int stopping;
 	uint64_t pin_target; /* bytes of host pool we want to have */
 
@@ -438,8 +440,8 @@ static struct arena *arena_new(uint64_t bytes)
 	return a;
 }
 
-/* Pin one more host arena.  Called WITHOUT e->mu (pinning is slow); ctx must be current. */
-static int host_pool_grow(nvs_engine *e)
+/* The slow part: cuMemHostAlloc of one arena.  e->mu NOT held; ctx must be current. */
+static int host_pool_grow_unlocked(nvs_engine *e)
 {
 	struct arena *a = arena_new(e->cfg.host_arena_bytes);
 	if (!a)
@@ -466,6 +468,23 @@ static int host_pool_grow(nvs_engine *e)
 	return 0;
 }
 
+/* Pin one more host arena.  Called WITH e->mu held; drops it while pinning
+ * (slow, ~3.8 GB/s) with `growing` set so that only one thread pins at a time
+ * and others wait for the result instead of pinning a second arena. */
+static int host_pool_grow(nvs_engine *e)
+{
+	if (e->growing) {
+		pthread_cond_wait(&e->grow_cv, &e->mu);
+		return 0; /* the caller re-checks the pool */
+	}
+	e->growing = 1;
+	pthread_mutex_unlock(&e->mu);
+	int rc = host_pool_grow_unlocked(e);
+	pthread_mutex_lock(&e->mu);
+	e->growing = 0;
+	pthread_cond_broadcast(&e->grow_cv);
+	return rc;
+}
 /* Create one arena of peer HBM mapped into this context.  Called with e->mu held. */
 static int peer_pool_grow(nvs_engine *e, int pi)
 {
@@ -532,10 +551,8 @@ static int backing_assign(nvs_engine *e, struct chunk *c)
 		}
 	}
 	while (pool_take(&e->host_pool, n, &c->backing) != 0) {
-		/* pool empty: pin inline (slow path; the background thread normally keeps ahead) */
-		pthread_mutex_unlock(&e->mu);
+		/* pool empty: wait for the background pinning, or pin inline */
 		int rc = host_pool_grow(e);
-		pthread_mutex_lock(&e->mu);
 		if (rc != 0)
 			return rc;
 	}
@@ -571,9 +588,7 @@ static void *pin_thread_main(void *arg)
 			pthread_cond_wait(&e->pin_cv, &e->mu);
 			continue;
 		}
-		pthread_mutex_unlock(&e->mu);
 		int rc = host_pool_grow(e);
-		pthread_mutex_lock(&e->mu);
 		if (rc != 0) /* out of pinnable memory: stop trying, evict will report it */
 			e->pin_target = e->host_pool.bytes;
 	}
@@ -1390,6 +1405,7 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	pthread_mutex_init(&e->api_mu, NULL);
 	pthread_mutex_init(&e->mu, NULL);
 	pthread_cond_init(&e->pin_cv, NULL);
+	pthread_cond_init(&e->grow_cv, NULL);
 
 	CK(e, e->d.CtxGetCurrent(&e->ctx));
 	if (!e->ctx) {
@@ -1529,5 +1545,6 @@ void nvs_engine_destroy(nvs_engine *e)
 	pthread_mutex_destroy(&e->mu);
 	pthread_mutex_destroy(&e->api_mu);
 	pthread_cond_destroy(&e->pin_cv);
+	pthread_cond_destroy(&e->grow_cv);
 	free(e);
 }
