@@ -51,6 +51,7 @@ extern "C" {
 #define NVS_E_NO_KERNEL  (-5) /* embedded sm_100a image failed to load             */
 #define NVS_E_TIMEOUT    (-6) /* HBM did not become available in time              */
 #define NVS_E_HOST_OOM   (-7) /* backing tier exhausted                            */
+#define NVS_E_SHUTDOWN   (-8) /* the CUDA context is being destroyed (process exit) */
 
 #define NVS_MAX_PEERS 7
 
@@ -65,7 +66,7 @@ typedef struct nvs_engine_config {
 	uint32_t struct_size;        /* sizeof(nvs_engine_config), for ABI growth          */
 	int32_t  device;             /* CUDA ordinal; -1 = device of the current context   */
 	nvs_resolve_fn resolve;      /* NULL = dlopen("libcuda.so.1") + dlsym              */
-	uint64_t chunk_bytes;        /* physical mapping unit, multiple of 2 MiB (64 MiB)  */
+	uint64_t chunk_bytes;        /* physical mapping unit, multiple of 2 MiB (256 MiB) */
 	uint64_t small_alloc_bytes;  /* smaller requests stay plain cuMemAlloc (1 MiB)     */
 	uint64_t batch_bytes;        /* pipeline batch: copy(b+1) overlaps (un)map(b)      */
 	uint64_t host_arena_bytes;   /* pinned-host growth unit (1 GiB)                    */
@@ -82,6 +83,10 @@ typedef struct nvs_engine_config {
 	int32_t  peers[NVS_MAX_PEERS];
 	uint64_t peer_capacity_bytes; /* per peer; 0 = none                                */
 	const char *stats_path;      /* JSON lines, one per evict/fetch; NULL = off        */
+	/* called (rate-limited) while a fetch/alloc waits for HBM other processes hold:
+	 * `bytes` = what is still missing.  libnvshare.so turns it into a REQ_LOCK "p<MiB>". */
+	void (*pressure_cb)(void *user, uint64_t bytes);
+	void *pressure_user;
 } nvs_engine_config;
 
 typedef struct nvs_xfer_report {

@@ -75,11 +75,19 @@ _Static_assert(offsetof(struct nvs_msg, data) == 517, "data offset");
  * `data` hints (ASCII, NUL-terminated, <= 19 chars).  Absent / unparsable
  * hints mean "no information" and select the reference-compatible behaviour.
  *   REQ_LOCK   "n<MiB>"  physical HBM the requester must map before it can run
- *   DROP_LOCK  "w<k>"    k clients are waiting behind the holder (k == 0: the
- *                        holder may keep its slabs resident)
+ *   DROP_LOCK  "w<k>n<MiB>"  k clients wait behind the holder (k == 0: it may keep
+ *                        its slabs resident); the next one must map <MiB>
+ *   REQ_LOCK   "p<MiB>"  (from the client that is being granted / holds the lock)
+ *                        it cannot map <MiB> more: memory pressure
+ *   DROP_LOCK  "e<MiB>"  (to clients that do not hold the lock) evict at least <MiB>
+ *   register reply: data[17] == '2' marks a daemon that speaks these hints; without
+ *   it our client behaves like the conservative default (evict everything on release).
  */
-#define NVS_HINT_NEED_PREFIX    'n'
-#define NVS_HINT_WAITERS_PREFIX 'w'
+#define NVS_HINT_NEED_PREFIX     'n'
+#define NVS_HINT_WAITERS_PREFIX  'w'
+#define NVS_HINT_PRESSURE_PREFIX 'p' /* REQ_LOCK "p<MiB>" from the client that is mapping: it is short of HBM */
+#define NVS_HINT_EVICT_PREFIX    'e' /* DROP_LOCK "e<MiB>" to clients that do NOT hold the lock: release HBM */
+#define NVS_CAP_MARKER           '2' /* register reply data[17]: the daemon understands the hints            */
 
 /* helpers shared by the daemon, the CLI and the client library (not exported from libnvshare.so) */
 #pragma GCC visibility push(hidden)

@@ -64,6 +64,10 @@ static int sock_fd = -1;
 static int scheduler_on, own_lock, need_lock, did_work;
 static int nvml_ok;
 static int early_release = 1;
+static int sched_v2;          /* the daemon speaks the data-field hints (include/nvshare_wire.h)   */
+static int evict_all_policy;  /* NVSHARE_EVICT_POLICY=all: never keep slabs resident without lock */
+static pthread_mutex_t send_mu = PTHREAD_MUTEX_INITIALIZER; /* frames from several threads      */
+#define EVICT_MARGIN_MIB 1024 /* head-room left free beyond what the next client asked for        */
 static uint64_t client_id;
 static CUcontext app_ctx;
 static int app_ctx_known;
@@ -83,8 +87,11 @@ static void send_msg(uint8_t type, const char *hint)
 	m.id = client_id;
 	if (hint)
 		snprintf(m.data, sizeof(m.data), "%s", hint);
-	nvs_must(nvs_write_all(sock_fd, &m, sizeof(m)) == (ssize_t)sizeof(m));
-	nvs_debug("Sent %s", nvs_msg_type_name(type));
+	pthread_mutex_lock(&send_mu);
+	ssize_t w = nvs_write_all(sock_fd, &m, sizeof(m));
+	pthread_mutex_unlock(&send_mu);
+	nvs_must(w == (ssize_t)sizeof(m));
+	nvs_debug("Sent %s %s", nvs_msg_type_name(type), hint ? hint : "");
 }
 
 /* Drain everything the application has submitted (mutex held). */
@@ -109,15 +116,53 @@ static void set_own_lock(int v)
 		dp.lock_state(v);
 }
 
+void nvs_client_pressure(uint64_t mib)
+{
+	char hint[NVS_MSG_DATA_LEN];
+	if (sock_fd < 0)
+		return;
+	snprintf(hint, sizeof(hint), "%c%" PRIu64, NVS_HINT_PRESSURE_PREFIX, mib);
+	send_msg(NVS_REQ_LOCK, hint);
+}
+
+#define EVICT_ALL UINT64_MAX
+
+/*
+ * How much HBM to give up when the lock leaves us.
+ *   - daemon without hints (the reference's), or NVSHARE_EVICT_POLICY=all: everything.
+ *     A client without the lock then holds no swappable HBM -- always safe.
+ *   - nobody is waiting (waiters == 0, or an idle release): nothing.  If someone
+ *     needs the memory later, the daemon forwards its pressure ("e<MiB>").
+ *   - otherwise just enough for the next client's stated need plus head-room.
+ */
+static uint64_t eviction_amount_mib(int have_hint, unsigned waiters, uint64_t need_mib)
+{
+	if (!sched_v2 || evict_all_policy)
+		return EVICT_ALL;
+	if (!have_hint || waiters == 0)
+		return 0;
+	uint64_t want = need_mib + EVICT_MARGIN_MIB;
+	uint64_t free_mib = dp.free_hbm_mib ? dp.free_hbm_mib() : 0;
+	return want > free_mib ? want - free_mib : 0;
+}
+
+static void do_evict(uint64_t mib)
+{
+	if (!dp.evict || mib == 0)
+		return;
+	if (dp.evict(mib == EVICT_ALL ? 0 : mib << 20) != 0)
+		nvs_fatal("eviction failed; cannot hand the GPU over safely");
+}
+
 /* Give the lock back and get our slabs out of the next holder's way (mutex held). */
-static void release_lock_and_evict(void)
+static void release_lock_and_evict(int have_hint, unsigned waiters, uint64_t need_mib)
 {
 	set_own_lock(0);
 	sync_app_context();
+	uint64_t mib = eviction_amount_mib(have_hint, waiters, need_mib);
 	if (early_release)
 		send_msg(NVS_LOCK_RELEASED, NULL);
-	if (dp.evict && dp.evict(0) != 0)
-		nvs_fatal("eviction failed; cannot hand the GPU over safely");
+	do_evict(mib);
 	if (!early_release)
 		send_msg(NVS_LOCK_RELEASED, NULL);
 }
@@ -184,6 +229,7 @@ static void *message_thread(void *arg)
 	memset(&out, 0, sizeof(out));
 	out.type = NVS_REGISTER;
 	out.id = NVS_ID_CLIENT_PREREG;
+	snprintf(out.data, sizeof(out.data), "nvs2"); /* the reference daemon ignores REGISTER.data */
 	fill_identity(&out);
 	nvs_debug("NVSHARE_POD_NAME = %s", out.pod_name);
 	nvs_debug("NVSHARE_POD_NAMESPACE = %s", out.pod_namespace);
@@ -201,7 +247,8 @@ static void *message_thread(void *arg)
 	if (in.type != NVS_SCHED_ON && in.type != NVS_SCHED_OFF)
 		nvs_fatal("Got message with type (%d) instead of initial nvshare-scheduler status", (int)in.type);
 	nvs_debug("Received %s", nvs_msg_type_name(in.type));
-	in.data[NVS_MSG_DATA_LEN - 1] = '\0';
+	sched_v2 = (in.data[17] == NVS_CAP_MARKER);
+	in.data[16] = '\0';
 	unsigned long long id = 0;
 	nvs_must(sscanf(in.data, "%llx", &id) == 1);
 	client_id = id;
@@ -228,22 +275,33 @@ static void *message_thread(void *arg)
 			nvs_must(pthread_cond_broadcast(&lock_cv) == 0);
 			nvs_must(pthread_cond_broadcast(&idle_cv) == 0);
 			break;
-		case NVS_DROP_LOCK:
-			nvs_debug("Received %s", nvs_msg_type_name(in.type));
-			if (own_lock && scheduler_on)
-				release_lock_and_evict();
+		case NVS_DROP_LOCK: {
+			in.data[NVS_MSG_DATA_LEN - 1] = '\0';
+			nvs_debug("Received %s %s", nvs_msg_type_name(in.type), in.data);
+			if (own_lock && scheduler_on) {
+				unsigned waiters = 0;
+				unsigned long long need = 0;
+				int have = sscanf(in.data, "w%un%llu", &waiters, &need) == 2;
+				release_lock_and_evict(have, waiters, need);
+			} else if (!own_lock && in.data[0] == NVS_HINT_EVICT_PREFIX) {
+				/* memory pressure from the client that is mapping: get out of its way */
+				uint64_t mib = strtoull(in.data + 1, NULL, 10);
+				sync_app_context();
+				do_evict(mib ? mib + EVICT_MARGIN_MIB : EVICT_ALL);
+			}
 			break;
+		}
 		case NVS_SCHED_ON:
 			nvs_debug("Received %s", nvs_msg_type_name(in.type));
 			if (!scheduler_on) {
 				nvs_debug("Scheduler status changed to ON");
 				scheduler_on = 1;
 				need_lock = 0;
-				/* we were running ungated: stop, drain, and get out of HBM */
+				/* we were running ungated: stop, drain, and (unless the daemon will
+				 * tell us when somebody needs the memory) get out of HBM */
 				set_own_lock(0);
 				sync_app_context();
-				if (dp.evict && dp.evict(0) != 0)
-					nvs_fatal("eviction failed after SCHED_ON");
+				do_evict(eviction_amount_mib(0, 0, 0));
 			} else {
 				nvs_debug("Scheduler status did not change, doing nothing");
 			}
@@ -325,7 +383,7 @@ static void *idle_thread(void *arg)
 			}
 		}
 		nvs_debug("Releasing the lock early due to inactivity");
-		release_lock_and_evict();
+		release_lock_and_evict(0, 0, 0);
 	}
 	return NULL;
 }
@@ -340,6 +398,8 @@ void nvs_client_start(const struct nvs_client_driver *d, const struct nvs_client
 	const char *er = getenv("NVSHARE_EARLY_RELEASE");
 	if (er && *er)
 		early_release = atoi(er) != 0;
+	const char *pol = getenv("NVSHARE_EVICT_POLICY");
+	evict_all_policy = pol && strcmp(pol, "all") == 0;
 	nvs_must(sem_init(&registered, 0, 0) == 0);
 	nvs_must(pthread_create(&t, NULL, message_thread, NULL) == 0);
 	/* the application does not proceed until the scheduler has told us its status */

@@ -32,9 +32,14 @@ struct nvs_client_datapath {
 	int (*evict)(uint64_t min_bytes);       /* release HBM (0 = everything)              */
 	uint64_t (*nonresident_mib)(void);      /* for the REQ_LOCK "n<MiB>" hint            */
 	void (*lock_state)(int holds_lock);     /* told whenever own_lock changes            */
+	uint64_t (*free_hbm_mib)(void);         /* what the driver reports free right now    */
 };
 
 void nvs_client_start(const struct nvs_client_driver *drv, const struct nvs_client_datapath *dp);
+
+/* Tell the scheduler that this process cannot map `mib` more MiB of HBM (other
+ * clients still hold it).  Safe from any thread; rate-limited by the caller. */
+void nvs_client_pressure(uint64_t mib);
 
 /* Returns only when this process holds the GPU lock (or the scheduler is off). */
 void continue_with_lock(void);

@@ -265,13 +265,25 @@ static const char *cu_name(nvs_engine *e, CUresult r)
 	return "CUDA_ERROR_?";
 }
 
+/* The driver is going away under us (the application is exiting and its context
+ * has been or is being destroyed): not an engine failure. */
+static int is_shutdown_error(CUresult r)
+{
+	return r == 4 /* DEINITIALIZED */ || r == CUDA_ERROR_NOT_INITIALIZED || r == CUDA_ERROR_INVALID_CONTEXT ||
+	       r == 709 /* CONTEXT_IS_DESTROYED */;
+}
+
 #define CK(e, call)                                                                        \
 	do {                                                                               \
 		CUresult r_ = (call);                                                      \
 		if (r_ != CUDA_SUCCESS) {                                                  \
-			nvs_warn("engine: %s returned %s (%d) at %s:%d", #call, cu_name(e, r_), \
-				 (int)r_, __FILE__, __LINE__);                             \
-			rc = (int)r_;                                                      \
+			if (is_shutdown_error(r_)) {                                       \
+				rc = NVS_E_SHUTDOWN;                                       \
+			} else {                                                           \
+				nvs_warn("engine: %s returned %s (%d) at %s:%d", #call,    \
+					 cu_name(e, r_), (int)r_, __FILE__, __LINE__);     \
+				rc = (int)r_;                                              \
+			}                                                                  \
 			goto out;                                                          \
 		}                                                                          \
 	} while (0)
@@ -291,6 +303,7 @@ const char *nvs_strerror(int rc)
 	case NVS_E_NO_KERNEL: return "embedded sm_100a kernel image failed to load";
 	case NVS_E_TIMEOUT: return "timed out waiting for HBM to be released";
 	case NVS_E_HOST_OOM: return "backing tier exhausted";
+	case NVS_E_SHUTDOWN: return "the CUDA context is being torn down (process exit)";
 	case CUDA_ERROR_OUT_OF_MEMORY: return "CUDA_ERROR_OUT_OF_MEMORY";
 	case CUDA_ERROR_NOT_INITIALIZED: return "CUDA_ERROR_NOT_INITIALIZED";
 	default: return rc > 0 ? "CUDA driver error" : "unknown engine error";
@@ -329,14 +342,19 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	memset(cfg, 0, sizeof(*cfg));
 	cfg->struct_size = sizeof(*cfg);
 	cfg->device = -1;
-	cfg->chunk_bytes = env_u64("NVSHARE_CHUNK_MIB", 64) << 20;
+	cfg->chunk_bytes = env_u64("NVSHARE_CHUNK_MIB", 256) << 20;
 	cfg->small_alloc_bytes = env_u64("NVSHARE_SMALL_ALLOC_KIB", 1024) << 10;
 	cfg->batch_bytes = env_u64("NVSHARE_BATCH_MIB", 1024) << 20;
 	cfg->host_arena_bytes = env_u64("NVSHARE_HOST_ARENA_MIB", 1024) << 20;
 	cfg->evict_variant = parse_variant(getenv("NVSHARE_EVICT_VARIANT"),
 					   parse_variant(getenv("NVSHARE_COPY_VARIANT"), NVS_COPY_TMA));
+	/* Fetch runs in the process that is being granted the lock, usually WHILE the
+	 * previous holder's eviction kernel is still running in another process.  The
+	 * GPU time-slices compute work of different processes, so kernel+kernel gets
+	 * 22+22 GB/s, kernel(evict)+copy-engine(fetch) 49+44 GB/s (B200, probe G):
+	 * fetch defaults to the copy engines, eviction to the sm_100a kernel. */
 	cfg->fetch_variant = parse_variant(getenv("NVSHARE_FETCH_VARIANT"),
-					   parse_variant(getenv("NVSHARE_COPY_VARIANT"), NVS_COPY_TMA));
+					   parse_variant(getenv("NVSHARE_COPY_VARIANT"), NVS_COPY_CE));
 	/* B200 probe: 2 CTAs already saturate PCIe Gen5 x16 in one direction
 	 * (52.7 GB/s); 8 leaves head-room when SMs are shared; the peer tier
 	 * (NVLink 5) wants ~74. */
@@ -365,6 +383,9 @@ static int ctx_enter(nvs_engine *e)
 {
 	return e->d.CtxPushCurrent(e->ctx) == CUDA_SUCCESS ? 0 : -1;
 }
+/* entry points return this when the context cannot be entered: at process exit
+ * that is normal, so it is reported as a shutdown, not as a failure */
+#define CTX_GONE NVS_E_SHUTDOWN
 
 static void ctx_leave(nvs_engine *e)
 {
@@ -675,11 +696,13 @@ static int chunk_map(nvs_engine *e, struct chunk *c, double *wait_ms)
 	acc.location = prop.location;
 	acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
 
-	double t0 = now_ms(), warned = 0;
+	double t0 = now_ms(), warned = 0, next_pressure = 200;
 	for (;;) {
 		CUresult r = e->d.MemCreate(&c->handle, c->bytes, &prop, 0);
 		if (r == CUDA_SUCCESS)
 			break;
+		if (is_shutdown_error(r))
+			return NVS_E_SHUTDOWN;
 		if (r != CUDA_ERROR_OUT_OF_MEMORY) {
 			nvs_warn("engine: cuMemCreate failed: %s", cu_name(e, r));
 			return (int)r;
@@ -693,7 +716,20 @@ static int chunk_map(nvs_engine *e, struct chunk *c, double *wait_ms)
 			nvs_debug("engine: waiting for HBM to be released by another client");
 			warned = 1;
 		}
-		usleep(500);
+		if (e->cfg.pressure_cb && waited >= next_pressure) {
+			/* nobody is (any longer) freeing memory for us: say how much we still miss */
+			e->cfg.pressure_cb(e->cfg.pressure_user, e->st.swapped_bytes + e->st.unbacked_bytes);
+			next_pressure = waited + 1000;
+		}
+		/* Wait until the driver reports room for this chunk before trying again: a
+		 * failing cuMemCreate is expensive and serialises with the cuMemRelease
+		 * calls of the process that is evicting (measured: B200 r01 call 2). */
+		for (int spin = 0; spin < 20; ++spin) {
+			size_t free_b = 0, total_b = 0;
+			usleep(1000);
+			if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= c->bytes + (64u << 20))
+				break;
+		}
 	}
 	if (wait_ms)
 		*wait_ms += now_ms() - t0;
@@ -714,9 +750,11 @@ static int chunk_unmap(nvs_engine *e, struct chunk *c)
 	CUresult r = e->d.MemUnmap(c->va, c->bytes);
 	if (r == CUDA_SUCCESS)
 		r = e->d.MemRelease(c->handle);
+	c->handle = 0;
+	if (is_shutdown_error(r))
+		return NVS_E_SHUTDOWN;
 	if (r != CUDA_SUCCESS)
 		nvs_warn("engine: cuMemUnmap/cuMemRelease failed: %s", cu_name(e, r));
-	c->handle = 0;
 	return (int)r;
 }
 
@@ -857,7 +895,7 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
 	struct chunk **victims = NULL;
 	double t_begin = now_ms();
 	if (ctx_enter(e) != 0)
-		return CUDA_ERROR_INVALID_CONTEXT;
+		return CTX_GONE;
 	pthread_mutex_lock(&e->api_mu);
 	pthread_mutex_lock(&e->mu);
 
@@ -972,7 +1010,7 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 	int rc = 0;
 	double t_begin = now_ms();
 	if (ctx_enter(e) != 0)
-		return CUDA_ERROR_INVALID_CONTEXT;
+		return CTX_GONE;
 	pthread_mutex_lock(&e->api_mu);
 	pthread_mutex_lock(&e->mu);
 	e->epoch++;
@@ -1198,7 +1236,7 @@ int nvs_free_sized(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes)
 		return NVS_E_BAD_ARG;
 	int rc = 0;
 	if (ctx_enter(e) != 0)
-		return CUDA_ERROR_INVALID_CONTEXT;
+		return CTX_GONE;
 	pthread_mutex_lock(&e->api_mu);
 	pthread_mutex_lock(&e->mu);
 	struct alloc *a = table_find(e, dptr);
@@ -1269,7 +1307,7 @@ int nvs_copy_slabs(nvs_engine *e, const nvs_copy_desc *descs, uint32_t n, uint32
 	int rc = 0;
 	void *staging = NULL;
 	if (ctx_enter(e) != 0)
-		return CUDA_ERROR_INVALID_CONTEXT;
+		return CTX_GONE;
 	pthread_mutex_lock(&e->api_mu);
 	pthread_mutex_lock(&e->mu);
 	const size_t bytes = (size_t)n * sizeof(nvs_copy_desc);
@@ -1304,7 +1342,7 @@ int nvs_pattern_fill(nvs_engine *e, uint64_t addr, uint64_t n_words, uint64_t fi
 		return NVS_E_BAD_ARG;
 	int rc = 0;
 	if (ctx_enter(e) != 0)
-		return CUDA_ERROR_INVALID_CONTEXT;
+		return CTX_GONE;
 	pthread_mutex_lock(&e->api_mu);
 	pthread_mutex_lock(&e->mu);
 	void *params[] = {&addr, &n_words, &first_index, &seed};
@@ -1324,7 +1362,7 @@ int nvs_pattern_verify(nvs_engine *e, uint64_t addr, uint64_t n_words, uint64_t 
 		return NVS_E_BAD_ARG;
 	int rc = 0;
 	if (ctx_enter(e) != 0)
-		return CUDA_ERROR_INVALID_CONTEXT;
+		return CTX_GONE;
 	pthread_mutex_lock(&e->api_mu);
 	pthread_mutex_lock(&e->mu);
 	CUdeviceptr out = e->scratch;

@@ -331,10 +331,16 @@ static void *engine_resolver(const char *symbol)
 
 static struct nvs_client_driver client_drv;
 
+static void mark_exiting(void)
+{
+	nvs_process_exiting = 1;
+}
+
 static void bootstrap(void)
 {
 	if (getenv(NVS_ENV_DEBUG))
 		nvs_debug_enabled = 1;
+	atexit(mark_exiting);
 	if (getenv("NVSHARE_ENABLE_SINGLE_OVERSUB")) {
 		single_oversub = 1;
 		uvm_mode = 1; /* a single process bigger than HBM needs demand paging */
@@ -403,6 +409,8 @@ static void bootstrap(void)
 
 static int dp_fetch_all(void)
 {
+	if (nvs_process_exiting)
+		return 0;
 	pthread_mutex_lock(&engine_mu);
 	nvs_engine *e = engine;
 	pthread_mutex_unlock(&engine_mu);
@@ -410,6 +418,8 @@ static int dp_fetch_all(void)
 		return 0;
 	nvs_xfer_report rep;
 	int rc = nvs_fetch_all(e, &rep);
+	if (rc == NVS_E_SHUTDOWN || nvs_process_exiting)
+		return 0; /* the application is exiting: nothing left to keep consistent */
 	if (rc != 0)
 		nvs_warn("fetch failed: %s", nvs_strerror(rc));
 	return rc;
@@ -417,6 +427,8 @@ static int dp_fetch_all(void)
 
 static int dp_evict(uint64_t min_bytes)
 {
+	if (nvs_process_exiting)
+		return 0;
 	pthread_mutex_lock(&engine_mu);
 	nvs_engine *e = engine;
 	pthread_mutex_unlock(&engine_mu);
@@ -424,6 +436,8 @@ static int dp_evict(uint64_t min_bytes)
 		return 0;
 	nvs_xfer_report rep;
 	int rc = nvs_evict(e, min_bytes, &rep);
+	if (rc == NVS_E_SHUTDOWN || nvs_process_exiting)
+		return 0;
 	if (rc != 0)
 		nvs_warn("evict failed: %s", nvs_strerror(rc));
 	return rc;
@@ -438,6 +452,20 @@ static uint64_t dp_nonresident_mib(void)
 	if (!e || nvs_get_stats(e, &st) != 0)
 		return 0;
 	return (st.swapped_bytes + st.unbacked_bytes) >> 20;
+}
+
+static uint64_t dp_free_hbm_mib(void)
+{
+	size_t free_b = 0, total_b = 0;
+	if (!real_cuMemGetInfo || real_cuMemGetInfo(&free_b, &total_b) != CUDA_SUCCESS)
+		return 0;
+	return (uint64_t)free_b >> 20;
+}
+
+static void on_engine_pressure(void *user, uint64_t bytes)
+{
+	(void)user;
+	nvs_client_pressure((bytes + (1u << 20) - 1) >> 20);
 }
 
 static void dp_lock_state(int v)
@@ -458,7 +486,8 @@ static void reset_sync_window(void)
 
 static void start_client(void)
 {
-	static const struct nvs_client_datapath dp = {dp_fetch_all, dp_evict, dp_nonresident_mib, dp_lock_state};
+	static const struct nvs_client_datapath dp = {dp_fetch_all, dp_evict, dp_nonresident_mib, dp_lock_state,
+						       dp_free_hbm_mib};
 	nvs_client_on_context_sync = reset_sync_window;
 	nvs_client_start(&client_drv, uvm_mode ? NULL : &dp);
 }
@@ -480,6 +509,7 @@ static nvs_engine *engine_get(void)
 			nvs_engine_config cfg;
 			nvs_engine_default_config(&cfg);
 			cfg.resolve = engine_resolver;
+			cfg.pressure_cb = on_engine_pressure;
 			int rc = nvs_engine_create(&cfg, &engine);
 			if (rc != 0)
 				nvs_fatal("swap engine could not start (%s); set NVSHARE_ENGINE=uvm to run with "

@@ -12,8 +12,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <errno.h>
+#include <unistd.h>
 
 extern int nvs_debug_enabled __attribute__((visibility("hidden")));
+/* set once the host process has entered exit(): library threads must not call exit() again */
+extern volatile int nvs_process_exiting __attribute__((visibility("hidden")));
 
 #define nvs_log_at(level, ...)                               \
 	do {                                                 \
@@ -32,6 +35,8 @@ extern int nvs_debug_enabled __attribute__((visibility("hidden")));
 #define nvs_fatal(...)                                       \
 	do {                                                 \
 		nvs_log_at("FATAL", __VA_ARGS__);            \
+		if (nvs_process_exiting)                     \
+			_exit(1);                            \
 		exit(1);                                     \
 	} while (0)
 #define nvs_fatal_errno(...)                                 \

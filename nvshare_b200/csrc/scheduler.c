@@ -263,7 +263,10 @@ static void on_timer(void)
 	memset(&m, 0, sizeof(m));
 	m.type = NVS_DROP_LOCK;
 	m.id = NVS_ID_DAEMON_TIMER;
-	snprintf(m.data, sizeof(m.data), "%c%u", NVS_HINT_WAITERS_PREFIX, q_len - 1);
+	/* hint for our own clients (reference clients never read `data` here):
+	 * how many clients wait behind the holder and how much HBM the next one must map */
+	snprintf(m.data, sizeof(m.data), "%c%u%c%" PRIu64, NVS_HINT_WAITERS_PREFIX, q_len - 1, NVS_HINT_NEED_PREFIX,
+		 q_head->q_next ? q_head->q_next->need_mib : 0);
 	if (send_frame(q_head, &m) != 0) {
 		drop_client(q_head);
 		try_schedule();
@@ -293,6 +296,7 @@ static void on_message(struct client *c, const struct nvs_msg *in)
 		m.type = sched_on ? NVS_SCHED_ON : NVS_SCHED_OFF;
 		m.id = NVS_ID_DAEMON;
 		snprintf(m.data, sizeof(m.data), "%016" PRIx64, c->id);
+		m.data[17] = NVS_CAP_MARKER; /* after the NUL that ends the id: invisible to reference clients */
 		if (send_frame(c, &m) != 0) {
 			drop_client(c);
 			return;
@@ -344,6 +348,24 @@ static void on_message(struct client *c, const struct nvs_msg *in)
 		}
 		if (!sched_on)
 			return;
+		if (in->data[0] == NVS_HINT_PRESSURE_PREFIX) {
+			/* the sender cannot map its working set: ask everybody else to get out of HBM.
+			 * Reference clients ignore a DROP_LOCK they do not hold the lock for. */
+			struct nvs_msg m;
+			memset(&m, 0, sizeof(m));
+			m.type = NVS_DROP_LOCK;
+			m.id = NVS_ID_DAEMON_TIMER;
+			snprintf(m.data, sizeof(m.data), "%c%" PRIu64, NVS_HINT_EVICT_PREFIX,
+				 (uint64_t)strtoull(in->data + 1, NULL, 10));
+			for (struct client *o = all_head, *nx; o; o = nx) {
+				nx = o->next;
+				if (o == c || o->id == NVS_UNREGISTERED_ID)
+					continue;
+				if (send_frame(o, &m) != 0)
+					drop_client(o);
+			}
+			return;
+		}
 		if (in->data[0] == NVS_HINT_NEED_PREFIX)
 			c->need_mib = strtoull(in->data + 1, NULL, 10);
 		if (c->queued)

@@ -34,6 +34,7 @@ class EngineConfig(C.Structure):
         ("tma_tile_bytes", C.c_uint32), ("ldg_threads", C.c_uint32), ("oom_wait_ms", C.c_uint32),
         ("prepin", C.c_uint32), ("n_peers", C.c_int32), ("peers", C.c_int32 * NVS_MAX_PEERS),
         ("peer_capacity_bytes", C.c_uint64), ("stats_path", C.c_char_p),
+        ("pressure_cb", C.c_void_p), ("pressure_user", C.c_void_p),
     ]
 
 

@@ -62,7 +62,8 @@ def test_version_and_default_config(fake):
     from nvshare_b200 import engine as E
     assert b"sm_100a" in E.load().nvs_engine_version()
     cfg = E.default_config()
-    assert cfg.chunk_bytes == 64 * MiB and cfg.host_arena_bytes == 1024 * MiB
+    assert cfg.chunk_bytes == 256 * MiB and cfg.host_arena_bytes == 1024 * MiB
+    assert cfg.evict_variant == E.COPY_TMA and cfg.fetch_variant == E.COPY_CE     # see engine.c: probe G
     assert cfg.tma_stages == 6 and cfg.tma_tile_bytes == 32768 and cfg.tma_warps == 1
 
 

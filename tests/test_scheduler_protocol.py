@@ -234,12 +234,17 @@ def test_drop_lock_carries_waiter_hint_ours_only(artefacts, tmp_path):
     try:
         d.ctl("-T", "1")
         a, b = MockClient(d.sock_path, "a"), MockClient(d.sock_path, "b")
-        a.register(); b.register()
+        ra = a.register(); b.register()
+        assert ra["raw_data"][17:18] == b"2" and ra["raw_data"][16:17] == b"\0"   # capability marker after the id
         a.send(REQ_LOCK, data=b"n1234"); a.expect(LOCK_OK)
-        b.send(REQ_LOCK)
-        assert a.expect(DROP_LOCK, timeout=3)["data"] == b"w1"
+        b.send(REQ_LOCK, data=b"n777")
+        assert a.expect(DROP_LOCK, timeout=3)["data"] == b"w1n777"      # one waiter, who must map 777 MiB
         a.send(LOCK_RELEASED)
         b.expect(LOCK_OK)
-        assert b.expect(DROP_LOCK, timeout=3)["data"] == b"w0"
+        # pressure from the client being granted is forwarded to everybody else as an eviction request
+        b.send(REQ_LOCK, data=b"p300")
+        assert a.expect(DROP_LOCK, timeout=3)["data"] == b"e300"
+        b.expect_nothing(0.2)
+        assert b.expect(DROP_LOCK, timeout=3)["data"] == b"w0n0"        # nobody waits: the holder may stay resident
     finally:
         d.stop()
