@@ -87,6 +87,11 @@ typedef struct nvs_engine_config {
 	 * `bytes` = what is still missing.  libnvshare.so turns it into a REQ_LOCK "p<MiB>". */
 	void (*pressure_cb)(void *user, uint64_t bytes);
 	void *pressure_user;
+	/* Host backing shared by all clients of one scheduler (a file, normally in
+	 * /dev/shm): host RAM then follows what is actually swapped out instead of
+	 * the sum of per-process pools.  NULL = private cuMemHostAlloc arenas. */
+	const char *shared_pool_path;
+	uint64_t shared_pool_bytes;  /* capacity when this client creates it; 0 = one HBM */
 } nvs_engine_config;
 
 typedef struct nvs_xfer_report {

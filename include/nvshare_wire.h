@@ -97,6 +97,9 @@ const char *nvs_msg_type_name(unsigned type);
 int nvs_socket_path(char *out, size_t outlen);
 /* Directory part of the above, with trailing '/'. */
 int nvs_socket_dir(char *out, size_t outlen);
+/* Path of the pinned-host pool shared by the clients of the scheduler listening on
+ * the socket above: NVSHARE_POOL_PATH, else /dev/shm/nvshare-pool-<fnv1a(socket path)>. */
+int nvs_pool_path(char *out, size_t outlen);
 
 int nvs_listen(const char *path, int backlog);          /* -> nonblocking listening fd or -1 */
 int nvs_accept(int lfd);                                /* -> nonblocking fd, -1 (errno set) */

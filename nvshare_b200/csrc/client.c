@@ -59,6 +59,9 @@ void (*nvs_client_on_context_sync)(void) = NULL;
 static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t lock_cv = PTHREAD_COND_INITIALIZER; /* own_lock became 1          */
 static pthread_cond_t idle_cv = PTHREAD_COND_INITIALIZER; /* activity / lock hand-over  */
+static pthread_cond_t drain_cv = PTHREAD_COND_INITIALIZER; /* inflight dropped to 0     */
+static int inflight; /* application threads between the gate and the return of their driver call */
+static int releasing; /* a release is in progress: REQ_LOCK must not overtake its LOCK_RELEASED     */
 static sem_t registered;
 static int sock_fd = -1;
 static int scheduler_on, own_lock, need_lock, did_work;
@@ -67,7 +70,8 @@ static int early_release = 1;
 static int sched_v2;          /* the daemon speaks the data-field hints (include/nvshare_wire.h)   */
 static int evict_all_policy;  /* NVSHARE_EVICT_POLICY=all: never keep slabs resident without lock */
 static pthread_mutex_t send_mu = PTHREAD_MUTEX_INITIALIZER; /* frames from several threads      */
-#define EVICT_MARGIN_MIB 1024 /* head-room left free beyond what the next client asked for        */
+/* head-room left free beyond what the next client asked for: 1/128 of the HBM, 16 MiB..1 GiB */
+static uint64_t evict_margin_mib(void);
 static uint64_t client_id;
 static CUcontext app_ctx;
 static int app_ctx_known;
@@ -109,6 +113,8 @@ static void sync_app_context(void)
 		nvs_warn("cuCtxSynchronize returned %d", (int)r);
 }
 
+static void close_gate_and_drain(void);
+
 static void set_own_lock(int v)
 {
 	own_lock = v;
@@ -127,6 +133,13 @@ void nvs_client_pressure(uint64_t mib)
 
 #define EVICT_ALL UINT64_MAX
 
+static uint64_t evict_margin_mib(void)
+{
+	uint64_t total = dp.total_hbm_mib ? dp.total_hbm_mib() : 0;
+	uint64_t m = total / 128;
+	return m < 16 ? 16 : m > 1024 ? 1024 : m;
+}
+
 /*
  * How much HBM to give up when the lock leaves us.
  *   - daemon without hints (the reference's), or NVSHARE_EVICT_POLICY=all: everything.
@@ -141,7 +154,7 @@ static uint64_t eviction_amount_mib(int have_hint, unsigned waiters, uint64_t ne
 		return EVICT_ALL;
 	if (!have_hint || waiters == 0)
 		return 0;
-	uint64_t want = need_mib + EVICT_MARGIN_MIB;
+	uint64_t want = need_mib + evict_margin_mib();
 	uint64_t free_mib = dp.free_hbm_mib ? dp.free_hbm_mib() : 0;
 	return want > free_mib ? want - free_mib : 0;
 }
@@ -157,7 +170,8 @@ static void do_evict(uint64_t mib)
 /* Give the lock back and get our slabs out of the next holder's way (mutex held). */
 static void release_lock_and_evict(int have_hint, unsigned waiters, uint64_t need_mib)
 {
-	set_own_lock(0);
+	releasing = 1;
+	close_gate_and_drain();
 	sync_app_context();
 	uint64_t mib = eviction_amount_mib(have_hint, waiters, need_mib);
 	if (early_release)
@@ -165,6 +179,9 @@ static void release_lock_and_evict(int have_hint, unsigned waiters, uint64_t nee
 	do_evict(mib);
 	if (!early_release)
 		send_msg(NVS_LOCK_RELEASED, NULL);
+	releasing = 0;
+	/* threads parked at the gate may now ask for the lock again (behind the waiters) */
+	nvs_must(pthread_cond_broadcast(&lock_cv) == 0);
 }
 
 void continue_with_lock(void)
@@ -180,7 +197,7 @@ void continue_with_lock(void)
 		}
 	}
 	while (!own_lock) {
-		if (!need_lock) { /* one request on behalf of every application thread */
+		if (!need_lock && !releasing) { /* one request on behalf of every application thread */
 			char hint[NVS_MSG_DATA_LEN];
 			need_lock = 1;
 			snprintf(hint, sizeof(hint), "%c%" PRIu64, NVS_HINT_NEED_PREFIX,
@@ -190,8 +207,30 @@ void continue_with_lock(void)
 		nvs_must(pthread_cond_wait(&lock_cv, &mu) == 0);
 	}
 	did_work = 1;
+	inflight++; /* paired with nvs_gate_leave() once the driver call has been issued */
 	nvs_must(pthread_cond_broadcast(&idle_cv) == 0);
 	nvs_must(pthread_mutex_unlock(&mu) == 0);
+}
+
+void nvs_gate_leave(void)
+{
+	nvs_must(pthread_mutex_lock(&mu) == 0);
+	if (--inflight == 0)
+		nvs_must(pthread_cond_broadcast(&drain_cv) == 0);
+	nvs_must(pthread_mutex_unlock(&mu) == 0);
+}
+
+/*
+ * Close the gate and wait until every application thread that had already passed
+ * it has handed its call to the driver.  The reference only clears own_lock
+ * (src/client.c:312): with managed memory a late launch merely faults pages back
+ * in; with VMM memory it would touch slabs that are being unmapped.  Mutex held.
+ */
+static void close_gate_and_drain(void)
+{
+	set_own_lock(0);
+	while (inflight > 0)
+		nvs_must(pthread_cond_wait(&drain_cv, &mu) == 0);
 }
 
 static void fill_identity(struct nvs_msg *m)
@@ -287,7 +326,7 @@ static void *message_thread(void *arg)
 				/* memory pressure from the client that is mapping: get out of its way */
 				uint64_t mib = strtoull(in.data + 1, NULL, 10);
 				sync_app_context();
-				do_evict(mib ? mib + EVICT_MARGIN_MIB : EVICT_ALL);
+				do_evict(mib ? mib + evict_margin_mib() : EVICT_ALL);
 			}
 			break;
 		}
@@ -299,7 +338,7 @@ static void *message_thread(void *arg)
 				need_lock = 0;
 				/* we were running ungated: stop, drain, and (unless the daemon will
 				 * tell us when somebody needs the memory) get out of HBM */
-				set_own_lock(0);
+				close_gate_and_drain();
 				sync_app_context();
 				do_evict(eviction_amount_mib(0, 0, 0));
 			} else {

@@ -33,6 +33,7 @@ struct nvs_client_datapath {
 	uint64_t (*nonresident_mib)(void);      /* for the REQ_LOCK "n<MiB>" hint            */
 	void (*lock_state)(int holds_lock);     /* told whenever own_lock changes            */
 	uint64_t (*free_hbm_mib)(void);         /* what the driver reports free right now    */
+	uint64_t (*total_hbm_mib)(void);
 };
 
 void nvs_client_start(const struct nvs_client_driver *drv, const struct nvs_client_datapath *dp);
@@ -43,6 +44,8 @@ void nvs_client_pressure(uint64_t mib);
 
 /* Returns only when this process holds the GPU lock (or the scheduler is off). */
 void continue_with_lock(void);
+/* Must follow every continue_with_lock() once the gated driver call has returned. */
+void nvs_gate_leave(void);
 
 /* Called by the launch hooks: resets the adaptive sync window (reference
  * src/client.c:62 touches pending_kernel_window directly). */

@@ -42,6 +42,10 @@
 #include <strings.h>
 #include <time.h>
 #include <unistd.h>
+#include <fcntl.h>
+#include <signal.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 
 #include "../../include/nvshare_engine.h"
 #include "cuda_min.h"
@@ -70,6 +74,8 @@ struct drv {
 	CUresult (*MemHostAlloc)(void **, size_t, unsigned);
 	CUresult (*MemFreeHost)(void *);
 	CUresult (*MemHostGetDevicePointer)(CUdeviceptr *, void *, unsigned);
+	CUresult (*MemHostRegister)(void *, size_t, unsigned);
+	CUresult (*MemHostUnregister)(void *);
 	CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long);
 	CUresult (*MemAddressFree)(CUdeviceptr, size_t);
 	CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *,
@@ -115,6 +121,8 @@ static const struct {
 	S(MemHostAlloc, "cuMemHostAlloc"),
 	S(MemFreeHost, "cuMemFreeHost"),
 	S(MemHostGetDevicePointer, "cuMemHostGetDevicePointer_v2"),
+	S(MemHostRegister, "cuMemHostRegister_v2"),
+	S(MemHostUnregister, "cuMemHostUnregister"),
 	S(MemAddressReserve, "cuMemAddressReserve"),
 	S(MemAddressFree, "cuMemAddressFree"),
 	S(MemCreate, "cuMemCreate"),
@@ -179,9 +187,51 @@ struct arena {
 	CUmemGenericAllocationHandle handle; /* peer tier                   */
 	uint64_t bytes;
 	uint32_t n_slabs, used;
-	uint32_t hint;      /* first word worth scanning                   */
+	uint32_t hint;      /* private pool: first slab worth scanning     */
 	uint64_t *bitmap;   /* 1 = slab in use                             */
+	int32_t *owners;    /* shared pool only: pid owning each slab      */
+	int shared;         /* bitmap/owners live in the shared pool header */
+	uint64_t bit_base;  /* index of this arena's slab 0 in `bitmap` / `owners` (shared pool: global) */
+	uint32_t window;    /* shared pool only: index of this 1 GiB window */
 	struct arena *next;
+};
+
+/*
+ * Shared pinned-host pool: ONE backing store for every client of a scheduler
+ * (a file in /dev/shm mapped by all of them), so that host RAM tracks what is
+ * actually swapped out (~0.5 C for two clients at 1.5x) instead of the sum of
+ * per-process pools (~1.0-1.5 C).  On the r01 box pinned memory is charged to a
+ * 200 GiB cgroup (probe H), which the per-process pools of the BASELINE
+ * configuration would exceed.  Layout of the file:
+ *   [0, SHP_HDR_BYTES)   struct shp_hdr: robust process-shared mutex, slab
+ *                        bitmap, owner pid per slab
+ *   [SHP_HDR_BYTES, ..)  data: capacity_slabs x 2 MiB, handed out in contiguous
+ *                        runs that never straddle a 1 GiB registration window
+ * Each process cuMemHostRegister()s a window the first time it needs it.
+ */
+#define SHP_MAGIC 0x6e767368504f4f4cull /* "nvshPOOL" */
+#define SHP_HDR_BYTES (8ull << 20)
+#define SHP_MAX_SLABS (1u << 19) /* 1 TiB */
+
+struct shp_hdr {
+	volatile uint64_t magic;
+	uint32_t version;
+	uint32_t window_slabs;
+	uint64_t capacity_slabs;
+	uint64_t used_slabs;
+	pthread_mutex_t mu;
+	uint64_t bitmap[SHP_MAX_SLABS / 64];
+	int32_t owners[SHP_MAX_SLABS];
+};
+_Static_assert(sizeof(struct shp_hdr) <= SHP_HDR_BYTES, "shared pool header too large");
+
+struct shpool {
+	int fd;
+	struct shp_hdr *hdr;
+	uint8_t *data;       /* host VA of the data region (whole capacity mapped, registered per window) */
+	uint32_t n_windows;
+	uint8_t *registered; /* per window: this process has it pinned */
+	char path[256];
 };
 
 struct pool {
@@ -197,7 +247,7 @@ struct slot {
 	uint32_t n_descs, cap_descs;
 	struct chunk **chunks;
 	uint32_t n_chunks, cap_chunks;
-	CUevent done;
+	CUevent begin, done; /* around this batch's copy: device time of the copy alone */
 	int busy;
 };
 
@@ -224,6 +274,7 @@ struct nvs_engine {
 	struct alloc *buckets[HASH_SIZE];
 	struct alloc *head, *tail;
 	struct pool host_pool;
+	struct shpool *shp; /* non-NULL: host_pool's arenas are windows of the shared pool */
 	struct pool peer_pools[NVS_MAX_PEERS];
 	uint32_t peer_rr;
 	uint64_t epoch;
@@ -367,6 +418,8 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->prepin = (uint32_t)env_u64("NVSHARE_PREPIN", 1);
 	cfg->peer_capacity_bytes = env_u64("NVSHARE_PEER_CAPACITY_MIB", 0) << 20;
 	cfg->stats_path = getenv("NVSHARE_STATS_FILE");
+	cfg->shared_pool_path = getenv("NVSHARE_POOL_PATH"); /* libnvshare.so derives one from the socket path */
+	cfg->shared_pool_bytes = env_u64("NVSHARE_POOL_GIB", 0) << 30;
 	const char *peers = getenv("NVSHARE_PEERS"); /* "1,2,3" */
 	if (peers && *peers) {
 		char buf[128];
@@ -395,23 +448,40 @@ static void ctx_leave(nvs_engine *e)
 
 /* -------------------------------------------------------------- pool ---- */
 
+static inline int bit_get(const struct arena *a, uint32_t i)
+{
+	uint64_t k = a->bit_base + i;
+	return (a->bitmap[k >> 6] >> (k & 63)) & 1;
+}
+
+static inline void bit_put(struct arena *a, uint32_t i, int v, int32_t owner)
+{
+	uint64_t k = a->bit_base + i;
+	if (v)
+		a->bitmap[k >> 6] |= 1ull << (k & 63);
+	else
+		a->bitmap[k >> 6] &= ~(1ull << (k & 63));
+	if (a->owners)
+		a->owners[k] = owner;
+}
+
 static int arena_take(struct arena *a, uint32_t n, uint64_t *addr)
 {
-	if (a->n_slabs - a->used < n)
+	if (!a->shared && a->n_slabs - a->used < n)
 		return -1;
 	/* first fit over the bitmap; runs never straddle arenas */
 	uint32_t run = 0;
-	for (uint32_t i = a->hint * 64; i < a->n_slabs; ++i) {
-		if (a->bitmap[i >> 6] & (1ull << (i & 63))) {
+	for (uint32_t i = a->shared ? 0 : a->hint; i < a->n_slabs; ++i) {
+		if (bit_get(a, i)) {
 			run = 0;
 			continue;
 		}
 		if (++run == n) {
 			uint32_t first = i + 1 - n;
 			for (uint32_t k = first; k <= i; ++k)
-				a->bitmap[k >> 6] |= 1ull << (k & 63);
+				bit_put(a, k, 1, (int32_t)getpid());
 			a->used += n;
-			while (a->hint < (a->n_slabs + 63) / 64 && a->bitmap[a->hint] == ~0ull)
+			while (!a->shared && a->hint < a->n_slabs && bit_get(a, a->hint))
 				a->hint++;
 			*addr = a->dev_base + (uint64_t)first * SLAB;
 			return 0;
@@ -420,30 +490,59 @@ static int arena_take(struct arena *a, uint32_t n, uint64_t *addr)
 	return -1;
 }
 
-static int pool_take(struct pool *p, uint32_t n, uint64_t *addr)
+/* the shared pool's mutex is robust: a client that dies holding it does not wedge the others */
+static void shp_lock(struct shpool *sp)
 {
+	int rc = pthread_mutex_lock(&sp->hdr->mu);
+	if (rc == EOWNERDEAD)
+		pthread_mutex_consistent(&sp->hdr->mu);
+}
+
+static void shp_unlock(struct shpool *sp)
+{
+	pthread_mutex_unlock(&sp->hdr->mu);
+}
+
+static int pool_take(nvs_engine *e, struct pool *p, uint32_t n, uint64_t *addr)
+{
+	struct shpool *sp = (p == &e->host_pool) ? e->shp : NULL;
+	int rc = -1;
+	if (sp)
+		shp_lock(sp);
 	for (struct arena *a = p->arenas; a; a = a->next)
 		if (arena_take(a, n, addr) == 0) {
 			p->used += (uint64_t)n * SLAB;
-			return 0;
+			if (sp)
+				sp->hdr->used_slabs += n;
+			rc = 0;
+			break;
 		}
-	return -1;
+	if (sp)
+		shp_unlock(sp);
+	return rc;
 }
 
-static void pool_give(struct pool *p, uint64_t addr, uint32_t n)
+static void pool_give(nvs_engine *e, struct pool *p, uint64_t addr, uint32_t n)
 {
+	struct shpool *sp = (p == &e->host_pool) ? e->shp : NULL;
+	if (sp)
+		shp_lock(sp);
 	for (struct arena *a = p->arenas; a; a = a->next) {
 		if (addr < a->dev_base || addr >= a->dev_base + a->bytes)
 			continue;
 		uint32_t first = (uint32_t)((addr - a->dev_base) / SLAB);
 		for (uint32_t k = first; k < first + n; ++k)
-			a->bitmap[k >> 6] &= ~(1ull << (k & 63));
+			bit_put(a, k, 0, 0);
 		a->used -= n;
-		if ((first >> 6) < a->hint)
-			a->hint = first >> 6;
+		if (!a->shared && first < a->hint)
+			a->hint = first;
 		p->used -= (uint64_t)n * SLAB;
-		return;
+		if (sp)
+			sp->hdr->used_slabs -= n;
+		break;
 	}
+	if (sp)
+		shp_unlock(sp);
 }
 
 static struct arena *arena_new(uint64_t bytes)
@@ -461,9 +560,86 @@ static struct arena *arena_new(uint64_t bytes)
 	return a;
 }
 
+struct touch_job {
+	volatile const uint8_t *p;
+	size_t bytes;
+};
+
+static void *touch_worker(void *arg)
+{
+	/* READ faults only: the pages may already hold another client's evicted data */
+	struct touch_job *j = arg;
+	uint8_t acc = 0;
+	for (size_t off = 0; off < j->bytes; off += 4096)
+		acc ^= j->p[off];
+	return (void *)(uintptr_t)acc;
+}
+
+/* Pin the next window of the shared pool into this process.  e->mu NOT held. */
+static int shared_pool_grow_unlocked(nvs_engine *e)
+{
+	struct shpool *sp = e->shp;
+	uint32_t w;
+	for (w = 0; w < sp->n_windows && sp->registered[w]; ++w)
+		;
+	if (w == sp->n_windows)
+		return NVS_E_HOST_OOM; /* every window is pinned here already: the pool itself is full */
+	const uint64_t win_bytes = (uint64_t)sp->hdr->window_slabs * SLAB;
+	uint8_t *base = sp->data + (uint64_t)w * win_bytes;
+	/* populate the page cache in parallel (page faults scale across cores; a lone
+	 * cuMemHostRegister would fault the pages in one by one) */
+	enum { NT = 8 };
+	pthread_t th[NT];
+	struct touch_job jobs[NT];
+	int started = 0;
+	for (int i = 0; i < NT; ++i) {
+		jobs[i].p = base + (win_bytes / NT) * (uint64_t)i;
+		jobs[i].bytes = win_bytes / NT;
+		if (pthread_create(&th[i], NULL, touch_worker, &jobs[i]) != 0)
+			break;
+		started++;
+	}
+	for (int i = 0; i < started; ++i)
+		pthread_join(th[i], NULL);
+	CUresult r = e->d.MemHostRegister(base, win_bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP);
+	if (r != CUDA_SUCCESS) {
+		nvs_warn("engine: cuMemHostRegister of shared pool window %u failed: %s", w, cu_name(e, r));
+		return NVS_E_HOST_OOM;
+	}
+	CUdeviceptr dp = 0;
+	if (e->d.MemHostGetDevicePointer(&dp, base, 0) != CUDA_SUCCESS)
+		dp = (CUdeviceptr)(uintptr_t)base;
+	struct arena *a = calloc(1, sizeof(*a));
+	if (!a)
+		return NVS_E_HOST_OOM;
+	a->shared = 1;
+	a->window = w;
+	a->bytes = win_bytes;
+	a->n_slabs = sp->hdr->window_slabs;
+	a->bitmap = sp->hdr->bitmap;
+	a->owners = sp->hdr->owners;
+	a->bit_base = (uint64_t)w * sp->hdr->window_slabs;
+	a->host_base = base;
+	a->dev_base = dp;
+	pthread_mutex_lock(&e->mu);
+	sp->registered[w] = 1;
+	/* keep the list in window order so that first-fit packs the low end of the file */
+	struct arena **pp = &e->host_pool.arenas;
+	while (*pp && (*pp)->window < w)
+		pp = &(*pp)->next;
+	a->next = *pp;
+	*pp = a;
+	e->host_pool.bytes += a->bytes;
+	e->st.host_pool_bytes = e->host_pool.bytes;
+	pthread_mutex_unlock(&e->mu);
+	return 0;
+}
+
 /* The slow part: cuMemHostAlloc of one arena.  e->mu NOT held; ctx must be current. */
 static int host_pool_grow_unlocked(nvs_engine *e)
 {
+	if (e->shp)
+		return shared_pool_grow_unlocked(e);
 	struct arena *a = arena_new(e->cfg.host_arena_bytes);
 	if (!a)
 		return NVS_E_HOST_OOM;
@@ -563,22 +739,39 @@ static int backing_assign(nvs_engine *e, struct chunk *c)
 	for (int t = 0; t < e->cfg.n_peers; ++t) {
 		int pi = (int)((e->peer_rr + (uint32_t)t) % (uint32_t)e->cfg.n_peers);
 		struct pool *p = &e->peer_pools[pi];
-		if (pool_take(p, n, &c->backing) == 0 ||
-		    (peer_pool_grow(e, pi) == 0 && pool_take(p, n, &c->backing) == 0)) {
+		if (pool_take(e, p, n, &c->backing) == 0 ||
+		    (peer_pool_grow(e, pi) == 0 && pool_take(e, p, n, &c->backing) == 0)) {
 			c->tier = (uint8_t)(TIER_PEER0 + pi);
 			e->peer_rr = (uint32_t)pi + 1;
 			e->st.peer_pool_used += c->bytes;
 			return 0;
 		}
 	}
-	while (pool_take(&e->host_pool, n, &c->backing) != 0) {
+	double t0 = now_ms();
+	while (pool_take(e, &e->host_pool, n, &c->backing) != 0) {
 		/* pool empty: wait for the background pinning, or pin inline */
 		int rc = host_pool_grow(e);
-		if (rc != 0)
+		if (rc == 0)
+			continue;
+		if (!e->shp || now_ms() - t0 > e->cfg.oom_wait_ms)
 			return rc;
+		/* the shared pool is full and entirely pinned here: another client is about
+		 * to hand units back (its fetch releases them batch by batch) */
+		pthread_mutex_unlock(&e->mu);
+		usleep(1000);
+		pthread_mutex_lock(&e->mu);
 	}
 	c->tier = TIER_HOST;
 	e->st.host_pool_used = e->host_pool.used;
+	if (e->shp && e->cfg.prepin) {
+		/* keep a few windows pinned ahead of the eviction front (pinning a window of
+		 * the shared pool is ~10x faster than the eviction that fills it is not) */
+		uint64_t want = e->host_pool.used + 8 * e->cfg.host_arena_bytes;
+		if (want > e->pin_target) {
+			e->pin_target = want;
+			pthread_cond_signal(&e->pin_cv);
+		}
+	}
 	return 0;
 }
 
@@ -588,14 +781,128 @@ static void backing_release(nvs_engine *e, struct chunk *c)
 		return;
 	const uint32_t n = (uint32_t)(c->bytes / SLAB);
 	if (c->tier == TIER_HOST) {
-		pool_give(&e->host_pool, c->backing, n);
+		pool_give(e, &e->host_pool, c->backing, n);
 		e->st.host_pool_used = e->host_pool.used;
 	} else if (c->tier >= TIER_PEER0) {
-		pool_give(&e->peer_pools[c->tier - TIER_PEER0], c->backing, n);
+		pool_give(e, &e->peer_pools[c->tier - TIER_PEER0], c->backing, n);
 		e->st.peer_pool_used -= c->bytes;
 	}
 	c->backing = 0;
 	c->tier = TIER_NONE;
+}
+
+/* ------------------------------------------------------ shared pool ---- */
+
+static void shp_close(nvs_engine *e)
+{
+	struct shpool *sp = e->shp;
+	if (!sp)
+		return;
+	for (struct arena *a = e->host_pool.arenas, *nx; a; a = nx) {
+		nx = a->next;
+		e->d.MemHostUnregister(a->host_base);
+		free(a);
+	}
+	e->host_pool.arenas = NULL;
+	if (sp->hdr)
+		munmap(sp->hdr, SHP_HDR_BYTES + sp->hdr->capacity_slabs * SLAB);
+	if (sp->fd >= 0)
+		close(sp->fd);
+	free(sp->registered);
+	free(sp);
+	e->shp = NULL;
+}
+
+/* Open (or create) the pool file.  Returns 0, or -1 to fall back to a private pool. */
+static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
+{
+	struct shpool *sp = calloc(1, sizeof(*sp));
+	if (!sp)
+		return -1;
+	snprintf(sp->path, sizeof(sp->path), "%s", path);
+	const uint32_t window_slabs = (uint32_t)(e->cfg.host_arena_bytes / SLAB);
+	uint64_t cap_slabs = capacity_bytes / SLAB / window_slabs * window_slabs;
+	if (cap_slabs > SHP_MAX_SLABS)
+		cap_slabs = SHP_MAX_SLABS / window_slabs * window_slabs;
+	int creator = 1;
+	sp->fd = open(path, O_RDWR | O_CREAT | O_EXCL | O_CLOEXEC, 0600);
+	if (sp->fd < 0 && errno == EEXIST) {
+		creator = 0;
+		sp->fd = open(path, O_RDWR | O_CLOEXEC);
+	}
+	if (sp->fd < 0)
+		goto fail;
+	if (creator && ftruncate(sp->fd, (off_t)(SHP_HDR_BYTES + cap_slabs * SLAB)) != 0)
+		goto fail;
+	if (!creator) {
+		/* wait for the creator to size and initialise the file */
+		struct stat st;
+		for (int i = 0; i < 5000; ++i) {
+			if (fstat(sp->fd, &st) == 0 && (uint64_t)st.st_size > SHP_HDR_BYTES)
+				break;
+			usleep(1000);
+		}
+		if (fstat(sp->fd, &st) != 0 || (uint64_t)st.st_size <= SHP_HDR_BYTES)
+			goto fail;
+		cap_slabs = ((uint64_t)st.st_size - SHP_HDR_BYTES) / SLAB;
+	}
+	void *m = mmap(NULL, SHP_HDR_BYTES + cap_slabs * SLAB, PROT_READ | PROT_WRITE, MAP_SHARED, sp->fd, 0);
+	if (m == MAP_FAILED)
+		goto fail;
+	sp->hdr = m;
+	sp->data = (uint8_t *)m + SHP_HDR_BYTES;
+	if (creator) {
+		pthread_mutexattr_t at;
+		pthread_mutexattr_init(&at);
+		pthread_mutexattr_setpshared(&at, PTHREAD_PROCESS_SHARED);
+		pthread_mutexattr_setrobust(&at, PTHREAD_MUTEX_ROBUST);
+		pthread_mutex_init(&sp->hdr->mu, &at);
+		pthread_mutexattr_destroy(&at);
+		sp->hdr->version = 1;
+		sp->hdr->window_slabs = window_slabs;
+		sp->hdr->capacity_slabs = cap_slabs;
+		__atomic_store_n(&sp->hdr->magic, SHP_MAGIC, __ATOMIC_RELEASE);
+	} else {
+		for (int i = 0; i < 5000 && __atomic_load_n(&sp->hdr->magic, __ATOMIC_ACQUIRE) != SHP_MAGIC; ++i)
+			usleep(1000);
+		if (sp->hdr->magic != SHP_MAGIC || sp->hdr->version != 1 || sp->hdr->capacity_slabs != cap_slabs ||
+		    sp->hdr->window_slabs == 0 || (uint64_t)sp->hdr->window_slabs * SLAB < e->cfg.chunk_bytes) {
+			nvs_warn("engine: shared pool %s is not usable by this client (geometry/version)", path);
+			munmap(m, SHP_HDR_BYTES + cap_slabs * SLAB);
+			sp->hdr = NULL;
+			goto fail;
+		}
+		/* units of clients that died without returning them */
+		shp_lock(sp);
+		for (uint64_t k = 0; k < cap_slabs; ++k) {
+			int32_t pid = sp->hdr->owners[k];
+			if (pid > 0 && kill(pid, 0) != 0 && errno == ESRCH) {
+				sp->hdr->bitmap[k >> 6] &= ~(1ull << (k & 63));
+				sp->hdr->owners[k] = 0;
+				sp->hdr->used_slabs--;
+			}
+		}
+		shp_unlock(sp);
+	}
+	sp->n_windows = (uint32_t)(cap_slabs / sp->hdr->window_slabs);
+	sp->registered = calloc(sp->n_windows ? sp->n_windows : 1, 1);
+	if (!sp->registered)
+		goto fail;
+	e->cfg.host_arena_bytes = (uint64_t)sp->hdr->window_slabs * SLAB;
+	e->shp = sp;
+	nvs_debug("engine: shared host pool %s: %" PRIu64 " GiB in %u windows (%s)", path, (uint64_t)((cap_slabs * SLAB) >> 30),
+		  sp->n_windows, creator ? "created" : "attached");
+	return 0;
+fail:
+	if (sp->hdr)
+		munmap(sp->hdr, SHP_HDR_BYTES + cap_slabs * SLAB);
+	if (sp->fd >= 0)
+		close(sp->fd);
+	if (creator && sp->fd >= 0)
+		unlink(path);
+	free(sp->registered);
+	free(sp);
+	return -1;
 }
 
 static void *pin_thread_main(void *arg)
@@ -869,6 +1176,11 @@ static int evict_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
 	if (!s->busy)
 		return 0;
 	CK(e, e->d.EventSynchronize(s->done));
+	{
+		float ms = 0;
+		if (e->d.EventElapsedTime(&ms, s->begin, s->done) == CUDA_SUCCESS)
+			rep->copy_ms += ms;
+	}
 	double t0 = now_ms();
 	for (uint32_t i = 0; i < s->n_chunks; ++i) {
 		struct chunk *c = s->chunks[i];
@@ -949,10 +1261,8 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
 				rep.peer_bytes += c->bytes;
 			++i;
 		}
-		if (!started) {
-			CK(e, e->d.EventRecord(e->ev_begin, e->stream));
-			started = 1;
-		}
+		started = 1;
+		CK(e, e->d.EventRecord(s->begin, e->stream));
 		if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, variant,
 				       grid_for(e, 0, peer_traffic))) != 0)
 			goto out;
@@ -963,18 +1273,11 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
 		rep.slabs += batch / SLAB;
 		batch_no++;
 	}
-	if (started)
-		CK(e, e->d.EventRecord(e->ev_end, e->stream));
+	(void)started;
 	for (unsigned k = 0; k < N_SLOTS; ++k) {
 		int r = evict_retire(e, &e->slots[(batch_no + k) % N_SLOTS], &rep);
 		if (r != 0 && rc == 0)
 			rc = r;
-	}
-	if (started && rc == 0) {
-		float ms = 0;
-		CK(e, e->d.EventSynchronize(e->ev_end));
-		CK(e, e->d.EventElapsedTime(&ms, e->ev_begin, e->ev_end));
-		rep.copy_ms = ms;
 	}
 	if (min_bytes == 0)
 		e->resident_mode = 0; /* everything is out: the owner no longer holds the GPU */
@@ -1001,6 +1304,25 @@ out:
 
 /* ------------------------------------------------------------- fetch ---- */
 
+/* A batch has landed in HBM: its backing units go back to the pool at once, so
+ * that the client evicting right now (other process, shared pool) can reuse them. */
+static int fetch_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
+{
+	int rc = 0;
+	if (s->busy) {
+		float ms = 0;
+		CK(e, e->d.EventSynchronize(s->done));
+		if (e->d.EventElapsedTime(&ms, s->begin, s->done) == CUDA_SUCCESS)
+			rep->copy_ms += ms;
+		for (uint32_t i = 0; i < s->n_chunks; ++i)
+			backing_release(e, s->chunks[i]);
+	}
+out:
+	s->busy = 0;
+	slot_reset(s);
+	return rc;
+}
+
 int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 {
 	nvs_xfer_report rep;
@@ -1023,11 +1345,8 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 	for (;;) {
 		/* next batch of non-resident chunks, allocation order */
 		struct slot *s = &e->slots[batch_no % N_SLOTS];
-		if (s->busy) {
-			CK(e, e->d.EventSynchronize(s->done));
-			s->busy = 0;
-		}
-		slot_reset(s);
+		if ((rc = fetch_retire(e, s, &rep)) != 0)
+			goto out;
 		uint64_t batch = 0, copy_bytes = 0;
 		int peer_traffic = 0;
 		double t0 = now_ms();
@@ -1070,10 +1389,8 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 			break;
 		}
 		if (s->n_descs) {
-			if (!started) {
-				CK(e, e->d.EventRecord(e->ev_begin, e->stream));
-				started = 1;
-			}
+			started = 1;
+			CK(e, e->d.EventRecord(s->begin, e->stream));
 			if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, variant,
 					       grid_for(e, 0, peer_traffic))) != 0)
 				goto out;
@@ -1085,13 +1402,10 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 		}
 		batch_no++;
 	}
-	if (started) {
-		float ms = 0;
-		CK(e, e->d.EventRecord(e->ev_end, e->stream));
-		CK(e, e->d.EventSynchronize(e->ev_end));
-		CK(e, e->d.EventElapsedTime(&ms, e->ev_begin, e->ev_end));
-		rep.copy_ms = ms;
-	}
+	(void)started;
+	for (unsigned k = 0; k < N_SLOTS; ++k)
+		if ((rc = fetch_retire(e, &e->slots[k], &rep)) != 0)
+			goto out;
 	e->resident_mode = 1;
 	e->st.n_fetches++;
 	e->st.fetched_bytes_total += rep.bytes;
@@ -1208,9 +1522,13 @@ int nvs_alloc(nvs_engine *e, uint64_t *dptr, uint64_t bytes)
 	e->st.va_bytes += a->va_bytes;
 	table_insert(e, a);
 	*dptr = va;
-	/* keep the pinned pool ahead of what may have to be swapped out */
+	/* keep the pinned pool ahead of what may have to be swapped out (private pool:
+	 * the whole footprint; shared pool: a head start, the rest follows the usage) */
 	if (e->cfg.prepin && e->cfg.n_peers == 0) {
-		e->pin_target += a->va_bytes;
+		if (!e->shp)
+			e->pin_target += a->va_bytes;
+		else if (e->pin_target < 8 * e->cfg.host_arena_bytes)
+			e->pin_target = 8 * e->cfg.host_arena_bytes;
 		pthread_cond_signal(&e->pin_cv);
 	}
 	a = NULL;
@@ -1266,7 +1584,7 @@ int nvs_free_sized(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes)
 		}
 		e->d.MemAddressFree(a->va, a->va_bytes);
 		e->st.va_bytes -= a->va_bytes;
-		if (e->cfg.prepin && e->cfg.n_peers == 0 && e->pin_target >= a->va_bytes)
+		if (e->cfg.prepin && e->cfg.n_peers == 0 && !e->shp && e->pin_target >= a->va_bytes)
 			e->pin_target -= a->va_bytes;
 	}
 	table_remove(e, a);
@@ -1393,6 +1711,8 @@ static void slots_free(nvs_engine *e)
 			e->d.MemFreeHost(s->descs);
 		if (s->done)
 			e->d.EventDestroy(s->done);
+		if (s->begin)
+			e->d.EventDestroy(s->begin);
 		free(s->chunks);
 		memset(s, 0, sizeof(*s));
 	}
@@ -1494,11 +1814,21 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 				rc = CUDA_ERROR_OUT_OF_MEMORY;
 				goto out;
 			}
-			CK(e, e->d.EventCreate(&s->done, CU_EVENT_DISABLE_TIMING));
+			CK(e, e->d.EventCreate(&s->begin, CU_EVENT_DEFAULT));
+			CK(e, e->d.EventCreate(&s->done, CU_EVENT_DEFAULT));
 		}
 	}
 
 	e->host_pool.device = -1;
+	if (e->cfg.shared_pool_path && *e->cfg.shared_pool_path) {
+		size_t free_b = 0, total_b = 0;
+		uint64_t cap = e->cfg.shared_pool_bytes;
+		if (!cap && e->d.MemGetInfo(&free_b, &total_b) == CUDA_SUCCESS)
+			cap = ((uint64_t)total_b + (1ull << 30) - 1) & ~((1ull << 30) - 1); /* one HBM's worth */
+		if (shp_open(e, e->cfg.shared_pool_path, cap) != 0)
+			nvs_warn("engine: cannot use the shared host pool %s (%s); using a private pinned pool",
+				 e->cfg.shared_pool_path, strerror(errno));
+	}
 	for (int i = 0; i < e->cfg.n_peers; ++i) {
 		int can = 0;
 		e->peer_pools[i].device = e->cfg.peers[i];
@@ -1548,6 +1878,8 @@ void nvs_engine_destroy(nvs_engine *e)
 			e->d.StreamSynchronize(e->stream);
 		while (e->head)
 			nvs_free(e, e->head->va);
+		if (e->shp)
+			shp_close(e);
 		for (struct arena *a = e->host_pool.arenas, *nx; a; a = nx) {
 			nx = a->next;
 			e->d.MemFreeHost(a->host_base);

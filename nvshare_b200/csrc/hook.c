@@ -177,6 +177,7 @@ static void after_launch(void);
 		warn_if_error(r, #name);                                             \
 		if (is_launch)                                                       \
 			after_launch();                                              \
+		nvs_gate_leave();                                                    \
 		return r;                                                            \
 	}                                                                            \
 	static CUresult gate_##name##_0 params { return gate_##name##_impl NVS_PREPEND(0, args); } \
@@ -462,6 +463,14 @@ static uint64_t dp_free_hbm_mib(void)
 	return (uint64_t)free_b >> 20;
 }
 
+static uint64_t dp_total_hbm_mib(void)
+{
+	size_t free_b = 0, total_b = 0;
+	if (!real_cuMemGetInfo || real_cuMemGetInfo(&free_b, &total_b) != CUDA_SUCCESS)
+		return 0;
+	return (uint64_t)total_b >> 20;
+}
+
 static void on_engine_pressure(void *user, uint64_t bytes)
 {
 	(void)user;
@@ -487,7 +496,7 @@ static void reset_sync_window(void)
 static void start_client(void)
 {
 	static const struct nvs_client_datapath dp = {dp_fetch_all, dp_evict, dp_nonresident_mib, dp_lock_state,
-						       dp_free_hbm_mib};
+						       dp_free_hbm_mib, dp_total_hbm_mib};
 	nvs_client_on_context_sync = reset_sync_window;
 	nvs_client_start(&client_drv, uvm_mode ? NULL : &dp);
 }
@@ -510,6 +519,11 @@ static nvs_engine *engine_get(void)
 			nvs_engine_default_config(&cfg);
 			cfg.resolve = engine_resolver;
 			cfg.pressure_cb = on_engine_pressure;
+			/* one pinned-host backing store for all clients of this scheduler */
+			static char pool_path[256];
+			const char *pool = getenv("NVSHARE_POOL");
+			if (!(pool && strcmp(pool, "private") == 0) && nvs_pool_path(pool_path, sizeof(pool_path)) == 0)
+				cfg.shared_pool_path = pool_path;
 			int rc = nvs_engine_create(&cfg, &engine);
 			if (rc != 0)
 				nvs_fatal("swap engine could not start (%s); set NVSHARE_ENGINE=uvm to run with "

@@ -57,6 +57,20 @@ int nvs_socket_path(char *out, size_t outlen)
 	return 0;
 }
 
+int nvs_pool_path(char *out, size_t outlen)
+{
+	const char *forced = getenv("NVSHARE_POOL_PATH");
+	if (forced && *forced)
+		return snprintf(out, outlen, "%s", forced) < (int)outlen ? 0 : -1;
+	char sock[108];
+	if (nvs_socket_path(sock, sizeof(sock)) != 0)
+		return -1;
+	uint64_t h = 0xcbf29ce484222325ull; /* FNV-1a over the socket path: one pool per scheduler */
+	for (const char *c = sock; *c; ++c)
+		h = (h ^ (unsigned char)*c) * 0x100000001b3ull;
+	return snprintf(out, outlen, "/dev/shm/nvshare-pool-%016llx", (unsigned long long)h) < (int)outlen ? 0 : -1;
+}
+
 static int fill_addr(struct sockaddr_un *addr, const char *path)
 {
 	memset(addr, 0, sizeof(*addr));

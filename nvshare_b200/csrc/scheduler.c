@@ -449,11 +449,23 @@ static void on_accept(void)
 	}
 }
 
+static char pool_path[256];
+
+static void on_term(int sig)
+{
+	(void)sig;
+	if (pool_path[0])
+		unlink(pool_path); /* the clients' shared pinned-host pool dies with its scheduler */
+	_exit(0);
+}
+
 int main(void)
 {
 	char dir[108], path[108];
 
 	signal(SIGPIPE, SIG_IGN);
+	signal(SIGTERM, on_term);
+	signal(SIGINT, on_term);
 	if (getenv(NVS_ENV_DEBUG)) {
 		nvs_debug_enabled = 1;
 		nvs_info("nvshare-scheduler started in debug mode");
@@ -480,6 +492,12 @@ int main(void)
 	nvs_must(epoll_ctl(ep_fd, EPOLL_CTL_ADD, listen_fd, &ev) == 0);
 	ev.data.ptr = &timer_fd;
 	nvs_must(epoll_ctl(ep_fd, EPOLL_CTL_ADD, timer_fd, &ev) == 0);
+
+	/* a pool file left by a previous instance belongs to clients that are gone */
+	if (nvs_pool_path(pool_path, sizeof(pool_path)) == 0)
+		unlink(pool_path);
+	else
+		pool_path[0] = '\0';
 
 	nvs_info("nvshare-scheduler listening on %s", path);
 

@@ -35,6 +35,7 @@ class EngineConfig(C.Structure):
         ("prepin", C.c_uint32), ("n_peers", C.c_int32), ("peers", C.c_int32 * NVS_MAX_PEERS),
         ("peer_capacity_bytes", C.c_uint64), ("stats_path", C.c_char_p),
         ("pressure_cb", C.c_void_p), ("pressure_user", C.c_void_p),
+        ("shared_pool_path", C.c_char_p), ("shared_pool_bytes", C.c_uint64),
     ]
 
 
@@ -128,7 +129,7 @@ class Engine:
                 for i, d in enumerate(v):
                     cfg.peers[i] = d
                 continue
-            if k == "stats_path" and isinstance(v, str):
+            if k in ("stats_path", "shared_pool_path") and isinstance(v, str):
                 v = v.encode()
             setattr(cfg, k, v)
         self.cfg = cfg

@@ -297,6 +297,8 @@ CUresult cuMemHostAlloc(void **pp, size_t bytes, unsigned flags)
 }
 CUresult cuMemFreeHost(void *p) { return plain_free((CUdeviceptr)(uintptr_t)p); }
 CUresult cuMemHostGetDevicePointer_v2(CUdeviceptr *d, void *p, unsigned f) { (void)f; *d = (CUdeviceptr)(uintptr_t)p; return OK; }
+CUresult cuMemHostRegister_v2(void *p, size_t bytes, unsigned flags) { (void)flags; trace("cuMemHostRegister %zu", bytes); return p ? OK : E_INVALID; }
+CUresult cuMemHostUnregister(void *p) { (void)p; return OK; }
 
 /* -------------------------------------------------------------- VMM ------ */
 

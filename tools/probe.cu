@@ -876,6 +876,108 @@ static int section_h(void)
 	return 0;
 }
 
+/* --------------------------------------------------------------- I ------ */
+/* The shared host pool: a /dev/shm file, pages faulted in by 8 threads (reads),
+ * pinned with cuMemHostRegister.  How fast is provisioning, and is the link
+ * bandwidth to such memory the same as to cuMemHostAlloc memory? */
+#include <fcntl.h>
+static void *touch_ro(void *arg)
+{
+	volatile const uint8_t *p = (volatile const uint8_t *)((void **)arg)[0];
+	size_t n = (size_t)((void **)arg)[1];
+	uint8_t acc = 0;
+	for (size_t off = 0; off < n; off += 4096)
+		acc ^= p[off];
+	return (void *)(uintptr_t)acc;
+}
+
+static int section_i(void)
+{
+	const size_t bytes = 4 * GiB;
+	const char *path = "/dev/shm/nvs_probe_pool";
+	unlink(path);
+	int fd = open(path, O_RDWR | O_CREAT, 0600);
+	if (fd < 0 || ftruncate(fd, bytes) != 0) {
+		printf("PROBE {\"section\":\"I\",\"error\":\"shm file\"}\n");
+		return -1;
+	}
+	uint8_t *p = (uint8_t *)mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	if (p == MAP_FAILED)
+		return -1;
+	double t0 = now_s();
+	pthread_t th[8];
+	void *args[8][2];
+	for (int i = 0; i < 8; ++i) {
+		args[i][0] = p + bytes / 8 * i;
+		args[i][1] = (void *)(bytes / 8);
+		pthread_create(&th[i], NULL, touch_ro, args[i]);
+	}
+	for (int i = 0; i < 8; ++i)
+		pthread_join(th[i], NULL);
+	double t_touch = now_s() - t0;
+	t0 = now_s();
+	CUresult r = cuMemHostRegister(p, bytes, CU_MEMHOSTREGISTER_PORTABLE | CU_MEMHOSTREGISTER_DEVICEMAP);
+	double t_reg = now_s() - t0;
+	CUdeviceptr dp = 0;
+	if (r == CUDA_SUCCESS)
+		cuMemHostGetDevicePointer(&dp, p, 0);
+	printf("PROBE {\"section\":\"I\",\"what\":\"shm pool provisioning\",\"bytes\":%zu,\"touch8_GBps\":%.2f,"
+	       "\"register_rc\":%d,\"register_GBps\":%.2f,\"overall_GBps\":%.2f,\"dev_eq_host\":%d}\n",
+	       bytes, bytes / 1e9 / t_touch, (int)r, bytes / 1e9 / t_reg, bytes / 1e9 / (t_touch + t_reg),
+	       dp == (CUdeviceptr)(uintptr_t)p);
+	fflush(stdout);
+	if (r != CUDA_SUCCESS)
+		return -1;
+	/* second registration of pages that already exist (what the 2nd client does) */
+	uint8_t *q = (uint8_t *)mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	t0 = now_s();
+	r = cuMemHostRegister(q, bytes, CU_MEMHOSTREGISTER_PORTABLE | CU_MEMHOSTREGISTER_DEVICEMAP);
+	printf("PROBE {\"section\":\"I\",\"what\":\"second mapping register\",\"rc\":%d,\"GBps\":%.2f}\n", (int)r,
+	       bytes / 1e9 / (now_s() - t0));
+	if (r == CUDA_SUCCESS)
+		cuMemHostUnregister(q);
+	munmap(q, bytes);
+
+	Bufs b;
+	memset(&b, 0, sizeof b);
+	b.bytes = bytes;
+	b.n_slabs = b.bytes / NVS_SLAB_BYTES;
+	CU(cuMemAlloc(&b.dev_a, b.bytes));
+	CU(cuMemAlloc(&b.dev_b, b.bytes));
+	b.host_a = (uint8_t *)dp;
+	b.host_b = (uint8_t *)dp;
+	CU(cuMemHostAlloc((void **)&b.descs_h, 2 * b.n_slabs * sizeof(nvs_copy_desc), CU_MEMHOSTALLOC_PORTABLE));
+	RT(cudaMalloc(&b.descs_d[0], b.n_slabs * sizeof(nvs_copy_desc)));
+	RT(cudaMalloc(&b.descs_d[1], b.n_slabs * sizeof(nvs_copy_desc)));
+	RT(cudaMalloc(&b.counters, 64));
+	RT(cudaMalloc(&b.mism, 8));
+	for (int i = 0; i < 2; ++i)
+		RT(cudaStreamCreateWithFlags(&b.st[i], cudaStreamNonBlocking));
+	for (int i = 0; i < 4; ++i)
+		RT(cudaEventCreate(&b.ev[i]));
+	RT(cudaFuncSetAttribute(nvs_slab_copy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	if (fill(b, b.dev_a, 1))
+		return -1;
+	Geo t = {NVS_COPY_TMA, 8, 1, 6, 32768};
+	Geo ce = {NVS_COPY_CE, 0, 0, 0, 0};
+	if (run_case(b, "d2h", t, false, true)) return -1;
+	if (run_case(b, "h2d", t, false, true)) return -1;
+	if (run_case(b, "d2h", ce, false, true)) return -1;
+	if (run_case(b, "h2d", ce, false, true)) return -1;
+	/* the CPU sees what the GPU wrote through the registration */
+	unsigned long long bad = 0;
+	for (size_t i = 0; i < bytes / 8; i += 4099)
+		bad += ((uint64_t *)p)[i] != nvs_pattern(i, 1);
+	printf("PROBE {\"section\":\"I\",\"what\":\"cpu view of shm after d2h\",\"sampled_mismatches\":%llu}\n", bad);
+	cuMemHostUnregister(p);
+	munmap(p, bytes);
+	close(fd);
+	unlink(path);
+	cuMemFree(b.dev_a);
+	cuMemFree(b.dev_b);
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
 	const char *sections = argc > 1 ? argv[1] : "ABCDEF";
@@ -903,6 +1005,7 @@ int main(int argc, char **argv)
 		case 'E': r = section_e(); break;
 		case 'F': r = section_f(); break;
 		case 'H': r = section_h(); break;
+		case 'I': r = section_i(); break;
 		default: break;
 		}
 		printf("PROBE {\"section_done\":\"%c\",\"rc\":%d,\"seconds\":%.1f}\n", *s, r, now_s() - t0);
