@@ -92,6 +92,9 @@ typedef struct nvs_engine_config {
 	 * the sum of per-process pools.  NULL = private cuMemHostAlloc arenas. */
 	const char *shared_pool_path;
 	uint64_t shared_pool_bytes;  /* capacity when this client creates it; 0 = one HBM */
+	/* 1 = scan slabs before eviction and do not move same-filled ones (all 64-bit
+	 * words equal): they are re-created on the device at fetch (nvs_slab_splat) */
+	uint32_t elide_constant;
 } nvs_engine_config;
 
 typedef struct nvs_xfer_report {
@@ -105,6 +108,7 @@ typedef struct nvs_xfer_report {
 	double   wait_ms;      /* host time spent waiting for HBM (OOM retries)           */
 	uint64_t host_bytes;   /* of `bytes`, how much went to / came from the host tier  */
 	uint64_t peer_bytes;   /* ... the peer-HBM tier                                   */
+	uint64_t elided_bytes; /* same-filled slabs: swapped without crossing the link    */
 } nvs_xfer_report;
 
 typedef struct nvs_stats {

@@ -53,6 +53,7 @@
 #include "slab_copy_cubin.h" /* generated: nvs_slab_copy_cubin[], nvs_slab_copy_cubin_len */
 
 #define SLAB NVS_SLAB_BYTES
+#define MAX_CHUNK_SLABS 256u /* chunk_bytes <= 512 MiB */
 #define N_SLOTS 3 /* pipeline depth (batches in flight) */
 
 enum { CH_UNBACKED = 0, CH_RESIDENT = 1, CH_SWAPPED = 2 };
@@ -168,6 +169,11 @@ struct chunk {
 	struct alloc *owner;
 	uint8_t state;
 	uint8_t tier;
+	/* same-filled slabs found at eviction: bit i set = slab i is `cvals[i]` repeated,
+	 * was not copied out and is re-created by nvs_slab_splat at fetch */
+	uint32_t n_const;
+	uint64_t cmask[MAX_CHUNK_SLABS / 64];
+	uint64_t *cvals;
 };
 
 struct alloc {
@@ -241,6 +247,7 @@ struct pool {
 	int device;        /* peer ordinal, -1 for the host tier */
 };
 
+struct scan_result;
 struct slot {
 	nvs_copy_desc *descs; /* pinned, device-mapped */
 	uint64_t descs_dev;
@@ -249,6 +256,17 @@ struct slot {
 	uint32_t n_chunks, cap_chunks;
 	CUevent begin, done; /* around this batch's copy: device time of the copy alone */
 	int busy;
+	/* auxiliary descriptor list: scan inputs (evict) or splat list (fetch), and scan results */
+	nvs_copy_desc *aux;
+	uint64_t aux_dev;
+	uint32_t n_aux, cap_aux;
+	struct scan_result *scan_out;
+	uint64_t scan_out_dev;
+};
+
+struct scan_result {
+	uint64_t value;
+	uint64_t is_const;
 };
 
 #define HASH_BITS 12
@@ -261,8 +279,11 @@ struct nvs_engine {
 	int device;
 	int n_sms;
 	CUmodule module;
-	CUfunction fn_tma, fn_ldg, fn_fill, fn_verify;
+	CUfunction fn_tma, fn_ldg, fn_fill, fn_verify, fn_scan, fn_splat;
 	CUstream stream;
+	CUstream scan_stream; /* the scan of batch b+1 runs beside the copy of batch b */
+	CUevent scan_done;
+	uint32_t scan_counter_next;
 	CUevent ev_begin, ev_end;
 	CUdeviceptr counters; /* u32[N_COUNTERS], device memory */
 	uint32_t counter_next;
@@ -292,7 +313,7 @@ struct nvs_engine {
 
 	FILE *stats_file;
 };
-#define N_COUNTERS 1024u
+#define N_COUNTERS 1024u /* per stream; the scan stream uses the second half of the array */
 
 static double now_ms(void)
 {
@@ -417,6 +438,7 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->oom_wait_ms = (uint32_t)env_u64("NVSHARE_OOM_WAIT_MS", 120000);
 	cfg->prepin = (uint32_t)env_u64("NVSHARE_PREPIN", 1);
 	cfg->peer_capacity_bytes = env_u64("NVSHARE_PEER_CAPACITY_MIB", 0) << 20;
+	cfg->elide_constant = (uint32_t)env_u64("NVSHARE_ELIDE", 1);
 	cfg->stats_path = getenv("NVSHARE_STATS_FILE");
 	cfg->shared_pool_path = getenv("NVSHARE_POOL_PATH"); /* libnvshare.so derives one from the socket path */
 	cfg->shared_pool_bytes = env_u64("NVSHARE_POOL_GIB", 0) << 30;
@@ -1113,34 +1135,105 @@ static void slot_reset(struct slot *s)
 {
 	s->n_descs = 0;
 	s->n_chunks = 0;
+	s->n_aux = 0;
 }
 
+static inline int slab_is_const(const struct chunk *c, uint32_t i)
+{
+	return (c->cmask[i >> 6] >> (i & 63)) & 1;
+}
+
+/* Copy descriptors for the slabs of `c` that really have to move (same-filled
+ * slabs are skipped).  Kernel variants get one descriptor per slab; the copy
+ * engines get one per run of adjacent slabs (a chunk's backing is contiguous). */
 static int slot_push_chunk(struct slot *s, struct chunk *c, int to_backing, uint32_t variant)
 {
 	if (s->n_chunks == s->cap_chunks)
 		return -1;
 	s->chunks[s->n_chunks++] = c;
-	if (variant == NVS_COPY_CE) {
-		/* backing of a chunk is contiguous: one copy-engine call per chunk */
+	const uint32_t n = (uint32_t)(c->bytes / SLAB);
+	for (uint32_t i = 0; i < n;) {
+		if (slab_is_const(c, i)) {
+			++i;
+			continue;
+		}
+		uint32_t run = 1;
+		if (variant == NVS_COPY_CE)
+			while (i + run < n && !slab_is_const(c, i + run))
+				++run;
 		if (s->n_descs == s->cap_descs)
 			return -1;
 		nvs_copy_desc *d = &s->descs[s->n_descs++];
-		d->src = to_backing ? c->va : c->backing;
-		d->dst = to_backing ? c->backing : c->va;
-		d->bytes = c->bytes;
-		d->tag = c->va >> NVS_SLAB_SHIFT;
-		return 0;
-	}
-	for (uint64_t off = 0; off < c->bytes; off += SLAB) {
-		if (s->n_descs == s->cap_descs)
-			return -1;
-		nvs_copy_desc *d = &s->descs[s->n_descs++];
+		const uint64_t off = (uint64_t)i * SLAB;
 		d->src = (to_backing ? c->va : c->backing) + off;
 		d->dst = (to_backing ? c->backing : c->va) + off;
-		d->bytes = SLAB;
+		d->bytes = (uint64_t)run * SLAB;
 		d->tag = (c->va + off) >> NVS_SLAB_SHIFT;
+		i += run;
 	}
 	return 0;
+}
+
+static int launch_aux(nvs_engine *e, CUfunction fn, struct slot *s, CUstream stream, int with_out)
+{
+	int rc = 0;
+	if (s->n_aux == 0)
+		return 0;
+	if (e->scan_counter_next == N_COUNTERS) {
+		CK(e, e->d.MemsetD32Async(e->counters + 4ull * N_COUNTERS, 0, N_COUNTERS, stream));
+		e->scan_counter_next = 0;
+	}
+	CUdeviceptr counter = e->counters + 4ull * (N_COUNTERS + e->scan_counter_next++);
+	uint32_t n = s->n_aux;
+	unsigned grid = n < (unsigned)e->n_sms * 8 ? n : (unsigned)e->n_sms * 8;
+	void *p_scan[] = {&s->aux_dev, &n, &counter, &s->scan_out_dev};
+	void *p_splat[] = {&s->aux_dev, &n, &counter};
+	CK(e, e->d.LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 0, stream, with_out ? p_scan : p_splat, NULL));
+	e->st.kernel_launches_total++;
+out:
+	return rc;
+}
+
+/* Find the same-filled slabs of the chunks gathered in `s` (evict side). */
+static int scan_slot(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
+{
+	int rc = 0;
+	s->n_aux = 0;
+	for (uint32_t k = 0; k < s->n_chunks; ++k) {
+		struct chunk *c = s->chunks[k];
+		for (uint64_t off = 0; off < c->bytes; off += SLAB) {
+			if (s->n_aux == s->cap_aux)
+				return NVS_E_BAD_ARG;
+			nvs_copy_desc *d = &s->aux[s->n_aux++];
+			d->src = c->va + off;
+			d->dst = 0;
+			d->bytes = SLAB;
+			d->tag = 0;
+		}
+	}
+	if ((rc = launch_aux(e, e->fn_scan, s, e->scan_stream, 1)) != 0)
+		return rc;
+	CK(e, e->d.EventRecord(e->scan_done, e->scan_stream));
+	CK(e, e->d.EventSynchronize(e->scan_done));
+	uint32_t at = 0;
+	for (uint32_t k = 0; k < s->n_chunks; ++k) {
+		struct chunk *c = s->chunks[k];
+		const uint32_t n = (uint32_t)(c->bytes / SLAB);
+		memset(c->cmask, 0, sizeof(c->cmask));
+		c->n_const = 0;
+		for (uint32_t i = 0; i < n; ++i, ++at) {
+			if (!s->scan_out[at].is_const)
+				continue;
+			if (!c->cvals && !(c->cvals = calloc(MAX_CHUNK_SLABS, sizeof(uint64_t))))
+				return NVS_E_HOST_OOM;
+			c->cvals[i] = s->scan_out[at].value;
+			c->cmask[i >> 6] |= 1ull << (i & 63);
+			c->n_const++;
+		}
+		rep->elided_bytes += (uint64_t)c->n_const * SLAB;
+	}
+out:
+	return rc;
 }
 
 /* ------------------------------------------------------------- evict ---- */
@@ -1155,17 +1248,18 @@ static int cmp_chunk_lru(const void *a, const void *b)
 
 static void report_emit(nvs_engine *e, const char *what, const nvs_xfer_report *r)
 {
-	nvs_debug("engine: %s %" PRIu64 " MiB in %.1f ms (copy %.1f ms = %.1f GB/s, map %.1f ms, wait %.1f ms)",
-		  what, r->bytes >> 20, r->wall_ms, r->copy_ms,
+	nvs_debug("engine: %s %" PRIu64 " MiB (+%" PRIu64 " MiB same-filled, not moved) in %.1f ms (copy %.1f ms = %.1f GB/s, "
+		  "map %.1f ms, wait %.1f ms)", what, r->bytes >> 20, r->elided_bytes >> 20, r->wall_ms, r->copy_ms,
 		  r->copy_ms > 0 ? r->bytes / 1e6 / r->copy_ms : 0.0, r->map_ms, r->wait_ms);
 	if (!e->stats_file)
 		return;
 	fprintf(e->stats_file,
 		"{\"op\":\"%s\",\"t\":%.6f,\"pid\":%d,\"bytes\":%" PRIu64 ",\"slabs\":%" PRIu64
 		",\"chunks\":%" PRIu64 ",\"launches\":%" PRIu64 ",\"wall_ms\":%.3f,\"copy_ms\":%.3f,"
-		"\"map_ms\":%.3f,\"wait_ms\":%.3f,\"host_bytes\":%" PRIu64 ",\"peer_bytes\":%" PRIu64 "}\n",
+		"\"map_ms\":%.3f,\"wait_ms\":%.3f,\"host_bytes\":%" PRIu64 ",\"peer_bytes\":%" PRIu64
+		",\"elided_bytes\":%" PRIu64 "}\n",
 		what, wall_s(), (int)getpid(), r->bytes, r->slabs, r->chunks, r->launches, r->wall_ms, r->copy_ms,
-		r->map_ms, r->wait_ms, r->host_bytes, r->peer_bytes);
+		r->map_ms, r->wait_ms, r->host_bytes, r->peer_bytes, r->elided_bytes);
 	fflush(e->stats_file);
 }
 
@@ -1245,21 +1339,40 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
 		struct slot *s = &e->slots[batch_no % N_SLOTS];
 		if ((rc = evict_retire(e, s, &rep)) != 0)
 			goto out;
-		uint64_t batch = 0;
+		uint64_t batch = 0, copied = 0;
 		int peer_traffic = 0;
-		while (i < n_vict && batch < e->cfg.batch_bytes) {
-			struct chunk *c = victims[i];
-			if ((rc = backing_assign(e, c)) != 0)
-				goto out;
-			if (slot_push_chunk(s, c, 1, variant) != 0)
-				break;
-			batch += c->bytes;
-			peer_traffic |= c->tier >= TIER_PEER0;
-			if (c->tier == TIER_HOST)
-				rep.host_bytes += c->bytes;
-			else
-				rep.peer_bytes += c->bytes;
+		/* 1. which chunks, 2. which of their slabs are same-filled, 3. backing + descriptors */
+		struct chunk **picked = &victims[i];
+		uint32_t n_picked = 0;
+		while (i < n_vict && batch < e->cfg.batch_bytes && n_picked < s->cap_chunks &&
+		       (batch + victims[i]->bytes) / SLAB <= s->cap_descs) {
+			batch += victims[i]->bytes;
+			++n_picked;
 			++i;
+		}
+		if (e->cfg.elide_constant) {
+			for (uint32_t k = 0; k < n_picked; ++k)
+				s->chunks[k] = picked[k];
+			s->n_chunks = n_picked;
+			if ((rc = scan_slot(e, s, &rep)) != 0)
+				goto out;
+			s->n_chunks = 0;
+		}
+		for (uint32_t k = 0; k < n_picked; ++k) {
+			struct chunk *c = picked[k];
+			const uint64_t moving = c->bytes - (uint64_t)c->n_const * SLAB;
+			if (moving && (rc = backing_assign(e, c)) != 0)
+				goto out;
+			if (slot_push_chunk(s, c, 1, variant) != 0) {
+				rc = NVS_E_BAD_ARG;
+				goto out;
+			}
+			copied += moving;
+			peer_traffic |= c->tier >= TIER_PEER0;
+			if (c->tier >= TIER_PEER0)
+				rep.peer_bytes += moving;
+			else
+				rep.host_bytes += moving;
 		}
 		started = 1;
 		CK(e, e->d.EventRecord(s->begin, e->stream));
@@ -1268,9 +1381,9 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
 			goto out;
 		CK(e, e->d.EventRecord(s->done, e->stream));
 		s->busy = 1;
-		rep.launches += variant == NVS_COPY_CE ? s->n_descs : 1;
-		rep.bytes += batch;
-		rep.slabs += batch / SLAB;
+		rep.launches += variant == NVS_COPY_CE ? s->n_descs : (s->n_descs ? 1 : 0);
+		rep.bytes += copied;
+		rep.slabs += copied / SLAB;
 		batch_no++;
 	}
 	(void)started;
@@ -1295,7 +1408,7 @@ out:
 	pthread_mutex_unlock(&e->api_mu);
 	ctx_leave(e);
 	free(victims);
-	if (rc == 0 && rep.bytes)
+	if (rc == 0 && (rep.bytes || rep.elided_bytes))
 		report_emit(e, "evict", &rep);
 	if (rep_out)
 		*rep_out = rep;
@@ -1361,7 +1474,8 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 				++ci;
 				continue;
 			}
-			if (s->n_chunks == s->cap_chunks || s->n_descs + c->bytes / SLAB > s->cap_descs)
+			if (s->n_chunks == s->cap_chunks || s->n_descs + c->bytes / SLAB > s->cap_descs ||
+			    s->n_aux + c->bytes / SLAB > s->cap_aux)
 				break;
 			double w = 0;
 			if ((rc = chunk_map(e, c, &w)) != 0)
@@ -1369,13 +1483,27 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 			rep.wait_ms += w;
 			rep.chunks++;
 			if (c->state == CH_SWAPPED) {
+				const uint64_t moving = c->bytes - (uint64_t)c->n_const * SLAB;
 				slot_push_chunk(s, c, 0, variant);
-				copy_bytes += c->bytes;
+				/* same-filled slabs are re-created on the device instead of copied */
+				for (uint32_t k = 0; c->n_const && k < c->bytes / SLAB; ++k) {
+					if (!slab_is_const(c, k) || s->n_aux == s->cap_aux)
+						continue;
+					nvs_copy_desc *d = &s->aux[s->n_aux++];
+					d->src = c->cvals[k];
+					d->dst = c->va + (uint64_t)k * SLAB;
+					d->bytes = SLAB;
+					d->tag = 0;
+				}
+				rep.elided_bytes += (uint64_t)c->n_const * SLAB;
+				copy_bytes += moving;
 				peer_traffic |= c->tier >= TIER_PEER0;
-				if (c->tier == TIER_HOST)
-					rep.host_bytes += c->bytes;
+				if (c->tier >= TIER_PEER0)
+					rep.peer_bytes += moving;
 				else
-					rep.peer_bytes += c->bytes;
+					rep.host_bytes += moving;
+				memset(c->cmask, 0, sizeof(c->cmask));
+				c->n_const = 0;
 			} /* UNBACKED: map only, nothing to copy */
 			c->epoch = e->epoch;
 			state_account(e, c, CH_RESIDENT);
@@ -1388,15 +1516,17 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 				rc = NVS_E_BAD_ARG;
 			break;
 		}
-		if (s->n_descs) {
+		if (s->n_descs || s->n_aux) {
 			started = 1;
 			CK(e, e->d.EventRecord(s->begin, e->stream));
 			if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, variant,
 					       grid_for(e, 0, peer_traffic))) != 0)
 				goto out;
+			if ((rc = launch_aux(e, e->fn_splat, s, e->stream, 0)) != 0)
+				goto out;
 			CK(e, e->d.EventRecord(s->done, e->stream));
 			s->busy = 1;
-			rep.launches += variant == NVS_COPY_CE ? s->n_descs : 1;
+			rep.launches += (variant == NVS_COPY_CE ? s->n_descs : (s->n_descs ? 1 : 0)) + (s->n_aux ? 1 : 0);
 			rep.bytes += copy_bytes;
 			rep.slabs += copy_bytes / SLAB;
 		}
@@ -1423,7 +1553,7 @@ out:
 	pthread_mutex_unlock(&e->mu);
 	pthread_mutex_unlock(&e->api_mu);
 	ctx_leave(e);
-	if (rc == 0 && (rep.bytes || rep.chunks))
+	if (rc == 0 && (rep.bytes || rep.chunks || rep.elided_bytes))
 		report_emit(e, "fetch", &rep);
 	if (rep_out)
 		*rep_out = rep;
@@ -1577,6 +1707,8 @@ int nvs_free_sized(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes)
 			if (c->state == CH_RESIDENT)
 				chunk_unmap(e, c);
 			backing_release(e, c);
+			free(c->cvals);
+			c->cvals = NULL;
 			uint64_t *ctr = c->state == CH_RESIDENT ? &e->st.resident_bytes
 					: c->state == CH_SWAPPED ? &e->st.swapped_bytes
 								 : &e->st.unbacked_bytes;
@@ -1709,6 +1841,10 @@ static void slots_free(nvs_engine *e)
 		struct slot *s = &e->slots[k];
 		if (s->descs)
 			e->d.MemFreeHost(s->descs);
+		if (s->aux)
+			e->d.MemFreeHost(s->aux);
+		if (s->scan_out)
+			e->d.MemFreeHost(s->scan_out);
 		if (s->done)
 			e->d.EventDestroy(s->done);
 		if (s->begin)
@@ -1738,7 +1874,7 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 		nvs_debug_enabled = 1;
 
 	/* sanity of geometry */
-	if (e->cfg.chunk_bytes < SLAB || (e->cfg.chunk_bytes & (SLAB - 1)) || e->cfg.host_arena_bytes < e->cfg.chunk_bytes ||
+	if (e->cfg.chunk_bytes < SLAB || (e->cfg.chunk_bytes & (SLAB - 1)) || e->cfg.chunk_bytes > MAX_CHUNK_SLABS * SLAB || e->cfg.host_arena_bytes < e->cfg.chunk_bytes ||
 	    (e->cfg.host_arena_bytes & (SLAB - 1)) || e->cfg.tma_warps == 0 || e->cfg.tma_warps > 8 ||
 	    e->cfg.tma_stages < 2 || e->cfg.tma_stages > 8 || (e->cfg.tma_tile_bytes & 15) || e->cfg.tma_tile_bytes == 0 ||
 	    (uint64_t)e->cfg.tma_warps * e->cfg.tma_stages * e->cfg.tma_tile_bytes > 200u * 1024u ||
@@ -1781,18 +1917,22 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	    e->d.ModuleGetFunction(&e->fn_tma, e->module, "nvs_slab_copy_tma") != CUDA_SUCCESS ||
 	    e->d.ModuleGetFunction(&e->fn_ldg, e->module, "nvs_slab_copy_ldg") != CUDA_SUCCESS ||
 	    e->d.ModuleGetFunction(&e->fn_fill, e->module, "nvs_slab_fill") != CUDA_SUCCESS ||
-	    e->d.ModuleGetFunction(&e->fn_verify, e->module, "nvs_slab_verify") != CUDA_SUCCESS) {
+	    e->d.ModuleGetFunction(&e->fn_verify, e->module, "nvs_slab_verify") != CUDA_SUCCESS ||
+	    e->d.ModuleGetFunction(&e->fn_scan, e->module, "nvs_slab_scan") != CUDA_SUCCESS ||
+	    e->d.ModuleGetFunction(&e->fn_splat, e->module, "nvs_slab_splat") != CUDA_SUCCESS) {
 		nvs_warn("engine: the embedded sm_100a image could not be loaded on this device");
 		rc = NVS_E_NO_KERNEL;
 		goto out;
 	}
 	CK(e, e->d.FuncSetAttribute(e->fn_tma, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024));
 	CK(e, e->d.StreamCreate(&e->stream, CU_STREAM_NON_BLOCKING));
+	CK(e, e->d.StreamCreate(&e->scan_stream, CU_STREAM_NON_BLOCKING));
+	CK(e, e->d.EventCreate(&e->scan_done, CU_EVENT_DISABLE_TIMING));
 	CK(e, e->d.EventCreate(&e->ev_begin, CU_EVENT_DEFAULT));
 	CK(e, e->d.EventCreate(&e->ev_end, CU_EVENT_DEFAULT));
-	CK(e, e->d.MemAlloc(&e->counters, 4 * N_COUNTERS));
+	CK(e, e->d.MemAlloc(&e->counters, 4 * 2 * N_COUNTERS));
 	CK(e, e->d.MemAlloc(&e->scratch, 64));
-	CK(e, e->d.MemsetD32Async(e->counters, 0, N_COUNTERS, e->stream));
+	CK(e, e->d.MemsetD32Async(e->counters, 0, 2 * N_COUNTERS, e->stream));
 	CK(e, e->d.StreamSynchronize(e->stream));
 
 	{
@@ -1808,6 +1948,17 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 				dp = (CUdeviceptr)(uintptr_t)s->descs;
 			s->descs_dev = dp;
 			s->cap_descs = cap_descs;
+			CK(e, e->d.MemHostAlloc((void **)&s->aux, (size_t)cap_descs * sizeof(nvs_copy_desc),
+						CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+			if (e->d.MemHostGetDevicePointer(&dp, s->aux, 0) != CUDA_SUCCESS)
+				dp = (CUdeviceptr)(uintptr_t)s->aux;
+			s->aux_dev = dp;
+			s->cap_aux = cap_descs;
+			CK(e, e->d.MemHostAlloc((void **)&s->scan_out, (size_t)cap_descs * sizeof(struct scan_result),
+						CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+			if (e->d.MemHostGetDevicePointer(&dp, s->scan_out, 0) != CUDA_SUCCESS)
+				dp = (CUdeviceptr)(uintptr_t)s->scan_out;
+			s->scan_out_dev = dp;
 			s->chunks = calloc(cap_chunks, sizeof(*s->chunks));
 			s->cap_chunks = cap_chunks;
 			if (!s->chunks) {
@@ -1906,6 +2057,10 @@ void nvs_engine_destroy(nvs_engine *e)
 			e->d.EventDestroy(e->ev_end);
 		if (e->stream)
 			e->d.StreamDestroy(e->stream);
+		if (e->scan_stream)
+			e->d.StreamDestroy(e->scan_stream);
+		if (e->scan_done)
+			e->d.EventDestroy(e->scan_done);
 		if (e->module)
 			e->d.ModuleUnload(e->module);
 		ctx_leave(e);

@@ -238,6 +238,89 @@ nvs_slab_copy_ldg(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uin
 	}
 }
 
+/* ------------------------------------------- same-filled slab elision ----- */
+
+/*
+ * A slab whose 64-bit words are all equal (zero-initialised buffers, ones(),
+ * padding, freshly memset workspaces -- the reference's own test tensors are
+ * torch.ones) does not have to cross the link at all: 8 bytes describe it.
+ * HBM is ~120x faster than PCIe Gen5 x16 on this part, so looking at every
+ * byte before moving it costs ~1 % of the move it may save.  The copy engines
+ * cannot do this; it is what the SMs are for on this path.
+ *
+ *   nvs_slab_scan    one CTA per slab: out[i] = {word 0, all words equal?},
+ *                    leaving the slab at the first 32 KiB tile that differs
+ *   nvs_slab_splat   the inverse: fill dst with the 64-bit value held in src
+ */
+struct nvs_scan_result {
+	unsigned long long value;
+	unsigned long long is_const;
+};
+
+#define NVS_SCAN_UNROLL 8
+
+extern "C" __global__ void __launch_bounds__(256)
+nvs_slab_scan(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uint32_t *counter,
+	      nvs_scan_result *__restrict__ out)
+{
+	__shared__ uint32_t s_idx;
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0)
+			s_idx = atomicAdd(counter, 1u);
+		__syncthreads();
+		const uint32_t idx = s_idx;
+		if (idx >= n_descs)
+			return;
+		const ulonglong2 *__restrict__ p = reinterpret_cast<const ulonglong2 *>(descs[idx].src);
+		const uint64_t n16 = descs[idx].bytes >> 4;
+		const unsigned long long v0 = reinterpret_cast<const unsigned long long *>(descs[idx].src)[0];
+		const uint64_t step = (uint64_t)blockDim.x * NVS_SCAN_UNROLL;
+		int differs = 0;
+		for (uint64_t base = 0; base < n16; base += step) {
+			ulonglong2 v[NVS_SCAN_UNROLL];
+#pragma unroll
+			for (int u = 0; u < NVS_SCAN_UNROLL; ++u) {
+				const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
+				v[u] = i < n16 ? __ldcs(p + i) : make_ulonglong2(v0, v0);
+			}
+			int d = 0;
+#pragma unroll
+			for (int u = 0; u < NVS_SCAN_UNROLL; ++u)
+				d |= (v[u].x != v0) | (v[u].y != v0);
+			if (__syncthreads_or(d)) {
+				differs = 1;
+				break;
+			}
+		}
+		if (threadIdx.x == 0) {
+			out[idx].value = v0;
+			out[idx].is_const = !differs && (descs[idx].bytes & 15ull) == 0;
+		}
+	}
+}
+
+extern "C" __global__ void __launch_bounds__(256)
+nvs_slab_splat(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uint32_t *counter)
+{
+	__shared__ uint32_t s_idx;
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0)
+			s_idx = atomicAdd(counter, 1u);
+		__syncthreads();
+		const uint32_t idx = s_idx;
+		if (idx >= n_descs)
+			return;
+		const unsigned long long v = descs[idx].src; /* the value, not an address */
+		ulonglong2 *__restrict__ q = reinterpret_cast<ulonglong2 *>(descs[idx].dst);
+		const uint64_t n16 = descs[idx].bytes >> 4;
+		const ulonglong2 vv = make_ulonglong2(v, v);
+		for (uint64_t i = threadIdx.x; i < n16; i += blockDim.x)
+			__stcs(q + i, vv);
+	}
+}
+
 /* ------------------------------------------------- pattern helpers ------- */
 
 /* position-dependent 64-bit pattern: distinguishes every word of every slab */

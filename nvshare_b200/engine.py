@@ -35,7 +35,7 @@ class EngineConfig(C.Structure):
         ("prepin", C.c_uint32), ("n_peers", C.c_int32), ("peers", C.c_int32 * NVS_MAX_PEERS),
         ("peer_capacity_bytes", C.c_uint64), ("stats_path", C.c_char_p),
         ("pressure_cb", C.c_void_p), ("pressure_user", C.c_void_p),
-        ("shared_pool_path", C.c_char_p), ("shared_pool_bytes", C.c_uint64),
+        ("shared_pool_path", C.c_char_p), ("shared_pool_bytes", C.c_uint64), ("elide_constant", C.c_uint32),
     ]
 
 
@@ -43,7 +43,7 @@ class XferReport(C.Structure):
     _fields_ = [
         ("bytes", C.c_uint64), ("slabs", C.c_uint64), ("chunks", C.c_uint64), ("launches", C.c_uint64),
         ("wall_ms", C.c_double), ("copy_ms", C.c_double), ("map_ms", C.c_double), ("wait_ms", C.c_double),
-        ("host_bytes", C.c_uint64), ("peer_bytes", C.c_uint64),
+        ("host_bytes", C.c_uint64), ("peer_bytes", C.c_uint64), ("elided_bytes", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -540,6 +540,38 @@ CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, uns
 		*counter = n + gx; /* what the real kernel leaves behind: every CTA over-increments once */
 		return OK;
 	}
+	if (!strcmp(name, "nvs_slab_scan")) {
+		const struct desc *d = *(const struct desc **)params[0];
+		uint32_t n = *(uint32_t *)params[1];
+		uint32_t *counter = *(uint32_t **)params[2];
+		struct { uint64_t value, is_const; } *out = *(void **)params[3];
+		if (*counter != 0)
+			return 999;
+		for (uint32_t i = 0; i < n; ++i) {
+			const uint64_t *p = (const uint64_t *)(uintptr_t)d[i].src;
+			uint64_t words = d[i].bytes / 8, k = 1;
+			while (k < words && p[k] == p[0])
+				++k;
+			out[i].value = p[0];
+			out[i].is_const = (k == words) && (d[i].bytes & 15) == 0;
+		}
+		*counter = n + gx;
+		return OK;
+	}
+	if (!strcmp(name, "nvs_slab_splat")) {
+		const struct desc *d = *(const struct desc **)params[0];
+		uint32_t n = *(uint32_t *)params[1];
+		uint32_t *counter = *(uint32_t **)params[2];
+		if (*counter != 0)
+			return 999;
+		for (uint32_t i = 0; i < n; ++i) {
+			uint64_t *q = (uint64_t *)(uintptr_t)d[i].dst;
+			for (uint64_t k = 0; k < d[i].bytes / 8; ++k)
+				q[k] = d[i].src;
+		}
+		*counter = n + gx;
+		return OK;
+	}
 	if (!strcmp(name, "nvs_slab_fill")) {
 		uint64_t *p = *(uint64_t **)params[0];
 		uint64_t n = *(uint64_t *)params[1], first = *(uint64_t *)params[2], seed = *(uint64_t *)params[3];

@@ -4,7 +4,7 @@
  * for libcuda) and runnable on a real GPU as well.  It knows nothing about
  * nvshare: the library under test is injected with LD_PRELOAD.
  *
- * usage: driver_app <MiB per buffer> <seconds> <seed> [n_buffers]
+ * usage: driver_app <MiB per buffer> <seconds> <seed> [n_buffers] [idle seconds before verifying]
  * Prints "RESULT PASS|FAIL iters=<n> mismatches=<m>".
  */
 #include <stdint.h>
@@ -45,6 +45,7 @@ int main(int argc, char **argv)
 	double seconds = argc > 2 ? atof(argv[2]) : 2.0;
 	uint64_t seed = argc > 3 ? strtoull(argv[3], NULL, 0) : 1;
 	int nbuf = argc > 4 ? atoi(argv[4]) : 2;
+	double idle = argc > 5 ? atof(argv[5]) : 0.0;
 	size_t bytes = mib << 20, words = bytes / 8;
 	if (nbuf < 2 || nbuf > 64)
 		return 2;
@@ -80,6 +81,11 @@ int main(int argc, char **argv)
 		usleep(2000);
 	}
 	CK(cuCtxSynchronize());
+	if (idle > 0) { /* an interactive application between two bursts: holds memory, submits nothing */
+		printf("idle start\n");
+		fflush(stdout);
+		usleep((useconds_t)(idle * 1e6));
+	}
 	CK(cuMemcpyDtoH_v2(back, buf[iters % (unsigned)nbuf], bytes));
 	unsigned long bad = 0;
 	for (size_t i = 0; i < words; ++i)

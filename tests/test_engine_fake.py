@@ -49,7 +49,9 @@ def oracle(artefacts):
 @pytest.fixture()
 def engine(fake):
     from nvshare_b200 import engine as E
-    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, batch_bytes=24 * MiB, oom_wait_ms=300)
+    # elision off: most tests below move freshly mapped (all-zero) memory on purpose
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, batch_bytes=24 * MiB, oom_wait_ms=300,
+                 elide_constant=0)
     yield e
     e.close()
 
@@ -244,7 +246,7 @@ def test_evicted_memory_is_unmapped(artefacts):
 def test_peer_tier_is_preferred_and_striped(fake):
     from nvshare_b200 import engine as E
     e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=32 * MiB, peers=[1, 2], peer_capacity_bytes=32 * MiB,
-                 prepin=0)
+                 prepin=0, elide_constant=0)
     try:
         p = e.alloc(80 * MiB)
         e.fetch_all()
@@ -257,6 +259,46 @@ def test_peer_tier_is_preferred_and_striped(fake):
         rep = e.fetch_all()
         assert rep["peer_bytes"] == 64 * MiB and rep["host_bytes"] == 16 * MiB
         assert e.pattern_verify(p, 80 * MiB // 8, seed=5) == 0
+        e.free(p)
+    finally:
+        e.close()
+
+
+def test_same_filled_slabs_are_not_moved(fake, oracle):
+    """Slabs whose 64-bit words are all equal are described, not copied: zero
+    pages, ones() tensors (the reference's own test data), memset workspaces."""
+    from nvshare_b200 import engine as E
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, batch_bytes=24 * MiB)
+    try:
+        assert e.cfg.elide_constant == 1
+        p = e.alloc(40 * MiB)                                # 20 slabs in 5 chunks
+        e.fetch_all()
+        ones = np.float32(1.0).view(np.uint32)
+        v = view(p, 40 * MiB).view(np.uint32)
+        v[:] = ones                                          # everything same-filled ...
+        v[(6 * MiB) // 4 + 17] = 0                           # ... except one word in slab 3
+        e.pattern_fill(p + 16 * MiB, (4 * MiB) // 8, seed=11)  # ... and slabs 8, 9 (position-dependent)
+        rep = e.evict(0)
+        assert rep["bytes"] == 3 * SLAB and rep["elided_bytes"] == 17 * SLAB
+        st = e.stats()
+        assert st["swapped_bytes"] == 40 * MiB
+        assert st["host_pool_used"] == 2 * 8 * MiB           # only the 2 chunks with a real slab keep backing
+        rep = e.fetch_all()
+        assert rep["bytes"] == 3 * SLAB and rep["elided_bytes"] == 17 * SLAB
+        got = view(p, 40 * MiB).view(np.uint32)
+        want = np.full(40 * MiB // 4, ones, dtype=np.uint32)
+        want[(6 * MiB) // 4 + 17] = 0
+        tmp = np.empty(4 * MiB // 8, dtype=np.uint64)
+        oracle.oracle_pattern_fill(tmp.ctypes.data, tmp.size, 0, 11)
+        want[(16 * MiB) // 4:(20 * MiB) // 4] = tmp.view(np.uint32)
+        assert np.array_equal(got, want)
+        # a second cycle after the application changed a formerly same-filled slab
+        view(p, 16)[:] = 9
+        rep = e.evict(0)
+        assert rep["bytes"] == 4 * SLAB and rep["elided_bytes"] == 16 * SLAB
+        e.fetch_all()
+        want.view(np.uint8)[:16] = 9
+        assert np.array_equal(view(p, 40 * MiB).view(np.uint32), want)
         e.free(p)
     finally:
         e.close()
@@ -276,7 +318,7 @@ def test_stats_file(fake, tmp_path):
     import json
     from nvshare_b200 import engine as E
     path = tmp_path / "stats.jsonl"
-    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, stats_path=str(path))
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, stats_path=str(path), elide_constant=0)
     p = e.alloc(16 * MiB); e.fetch_all(); e.evict(0); e.fetch_all(); e.free(p); e.close()
     recs = [json.loads(l) for l in path.read_text().splitlines()]
     assert [r["op"] for r in recs] == ["fetch", "evict", "fetch"]
