@@ -63,14 +63,15 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--tq", type=int, default=6, help="scheduler time quantum in seconds (reference default: 30)")
+    ap.add_argument("--tq", type=int, default=10, help="scheduler time quantum in seconds (reference default: 30)")
     ap.add_argument("--oversub", type=float, default=1.5, help="aggregate client footprint / HBM")
     ap.add_argument("--clients", type=int, default=2)
     ap.add_argument("--kind", choices=["add", "matmul"], default="add")
     ap.add_argument("--pattern", choices=["ones", "pos"], default="pos")
-    ap.add_argument("--hbm-fraction", type=float, default=1.0,
-                    help="share of the GPU's HBM the experiment may use; the rest is held by a ballast process "
-                         "(1.0 = the configuration BASELINE.json names)")
+    ap.add_argument("--hbm-fraction", type=float, default=0.0,
+                    help="share of the GPU's HBM the experiment may use; the rest is held by a ballast process. "
+                         "1.0 = the configuration BASELINE.json names; 0 (default) = 1.0 if the host memory this "
+                         "arm needs fits the box's limit, else the largest fraction that does")
     ap.add_argument("--keep", default="", help="directory to keep logs in")
     return ap.parse_args()
 
@@ -131,6 +132,55 @@ def cpu_baseline(sample_gib=4):
             "sample": f"{sample_gib} GiB of 2 MiB slab descriptors, host->host memcpy (oracle_slab_move), best pass in 10 s"}
 
 
+def host_memory_budget():
+    """Bytes of host RAM this job may still take: the cgroup limit (pinned and UVM
+    host pages are charged to it: profiles/r01_probe_h_pinned_accounting.txt) or MemAvailable."""
+    avail = None
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                avail = int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        cur = int(open("/sys/fs/cgroup/memory.current").read())
+        if lim != "max":
+            room = int(lim) - cur
+            avail = room if avail is None else min(avail, room)
+    except (OSError, ValueError):
+        pass
+    return avail
+
+
+def host_memory_needed(impl, clients, footprint, hbm_avail):
+    """What each arm keeps in host RAM (measured, r01 call 3): the reference's UVM ends up
+    holding every client's pages on the host; our shared pool holds what is swapped out plus
+    the pinned windows ahead of it (peak 163 GB for 95.7 GB swapped at full scale)."""
+    if impl == "reference":
+        return clients * footprint * 1.03 + (8 << 30)
+    return max(clients * footprint - hbm_avail, 0) * 1.75 + (12 << 30)
+
+
+def pick_fraction(args, total_b):
+    if args.hbm_fraction > 0:
+        return args.hbm_fraction, None
+    budget = host_memory_budget()
+    frac = 1.0
+    while frac > 0.1:
+        hbm_avail = total_b * frac
+        fp = args.oversub * hbm_avail / args.clients
+        if budget is None or host_memory_needed(args.impl, args.clients, fp, hbm_avail) <= budget - (20 << 30):
+            break
+        frac = round(frac - 0.05, 2)
+    note = None
+    if frac < 0.999:
+        note = (f"host RAM budget {budget / 1e9:.0f} GB cannot hold what the {args.impl} arm needs at full scale "
+                f"({host_memory_needed(args.impl, args.clients, args.oversub * total_b / args.clients, total_b) / 1e9:.0f} GB); "
+                f"scaled to {frac:.2f} of the HBM, the rest is held by a ballast process")
+    return frac, note
+
+
 def main():
     args = parse_args()
     rank, world, local = dist_env()
@@ -176,6 +226,7 @@ def run_rank0(args, torch, world):
     cpu = cpu_baseline() if (args.impl == "ours" and world == 1) or args.impl == "reference" else None
 
     # -- geometry: clients x footprint = oversub x HBM the experiment may use
+    args.hbm_fraction, scale_note = pick_fraction(args, total_b)
     hbm_avail = int(total_b * args.hbm_fraction)
     footprint = args.oversub * hbm_avail / args.clients
     blocks = 4 if args.kind == "add" else 3             # live n^2 fp32 blocks
@@ -251,7 +302,7 @@ def run_rank0(args, torch, world):
                         f"footprint {footprint / 1e9:.1f} GB/client = {args.clients * footprint / hbm_avail:.2f}x of "
                         f"{hbm_avail / 1e9:.1f} GB HBM",
             "clients": args.clients, "oversubscription": args.clients * footprint / hbm_avail,
-            "tq_s": args.tq, "hbm_bytes": total_b, "hbm_fraction_used": args.hbm_fraction,
+            "tq_s": args.tq, "hbm_bytes": total_b, "hbm_fraction_used": args.hbm_fraction, "scale_note": scale_note,
             "backing_tier": "peer-HBM over NVLink (GPUs 1..%d) + pinned host" % (world - 1) if world > 1 and args.impl == "ours" else "pinned host DRAM over PCIe Gen5 x16",
             "l2_policy": "inputs (>= tens of GB per hand-off) exceed the 126 MB L2",
             "algorithmic_bytes_per_handoff_per_direction": algo_bytes_dir,

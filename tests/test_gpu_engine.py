@@ -184,6 +184,41 @@ def test_engine_variants(torch_cuda, artefacts, evict_v, fetch_v):
         e.close()
 
 
+def test_same_filled_slabs_are_elided_and_recreated(torch_cuda, engine, oracle):
+    """nvs_slab_scan / nvs_slab_splat on the GPU against the oracle's per-slab test."""
+    torch = torch_cuda
+    size = 1 * GiB + 4 * MiB
+    n = size // 4
+    p = engine.alloc(size)
+    engine.fetch_all()
+
+    class Raw:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+    t = torch.as_tensor(Raw(p, n), device="cuda")
+    t.fill_(1.0)                                             # the reference workload's data: torch.ones
+    g = torch.Generator(device="cpu").manual_seed(3)
+    noisy_slabs = sorted(set(torch.randint(0, size // SLAB, (37,), generator=g).tolist()))
+    for sidx in noisy_slabs:                                 # one differing word somewhere in 37 slabs
+        t[sidx * (SLAB // 4) + (sidx * 7919) % (SLAB // 4)] = 3.0
+    torch.cuda.synchronize()
+    host = t.cpu().numpy()
+    oracle.oracle_slab_is_const.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    val = C.c_uint64()
+    want_const = sum(oracle.oracle_slab_is_const(host.ctypes.data + i * SLAB, SLAB, C.byref(val))
+                     for i in range(size // SLAB))
+    assert want_const == size // SLAB - len(noisy_slabs)
+    rep = engine.evict(0)
+    assert rep["elided_bytes"] == want_const * SLAB and rep["bytes"] == len(noisy_slabs) * SLAB
+    rep = engine.fetch_all()
+    assert rep["elided_bytes"] == want_const * SLAB and rep["bytes"] == len(noisy_slabs) * SLAB
+    torch.cuda.synchronize()
+    assert np.array_equal(t.cpu().numpy(), host)             # bit-exact, splatted and copied slabs alike
+    del t
+    engine.free(p)
+
+
 def test_torch_can_use_engine_memory(torch_cuda, engine):
     """Memory handed out by nvs_alloc behaves like cuMemAlloc memory for CUDA
     libraries: wrap it with torch via the CUDA array interface and compute."""

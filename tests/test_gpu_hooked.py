@@ -49,13 +49,24 @@ def stats(tmp_path, i):
 
 def test_add_two_clients_exact(artefacts, tmp_path):
     """BASELINE config #2 at small scale: fp32 add, position-dependent inputs, bit-exact."""
-    log, res = run_pair(tmp_path, "add", 12000, 8, "pos", tq=2)
+    # evict-all policy: both working sets would fit side by side at this size, so force the swap
+    log, res = run_pair(tmp_path, "add", 12000, 8, "pos", tq=2, extra_env={"NVSHARE_EVICT_POLICY": "all"})
     for rc, out, err in res:
         assert rc == 0 and out.startswith("PASS"), out + err[-3000:]
     assert log.count("Sent DROP_LOCK") >= 2
     for i in (1, 2):
         ops = [r["op"] for r in stats(tmp_path, i)]
         assert "evict" in ops and "fetch" in ops            # the engine really swapped under the hook
+
+
+def test_no_swap_when_everything_fits(artefacts, tmp_path):
+    """Default (need-based) policy: two small clients fit in HBM together, so hand-offs move nothing."""
+    log, res = run_pair(tmp_path, "add", 8000, 5, "ones", tq=1)
+    for rc, out, err in res:
+        assert rc == 0 and out.startswith("PASS"), out + err[-3000:]
+    assert log.count("Sent DROP_LOCK") >= 3
+    for i in (1, 2):
+        assert [r for r in stats(tmp_path, i) if r["op"] == "evict"] == []
 
 
 def test_matmul_two_clients_within_tolerance(artefacts, tmp_path):

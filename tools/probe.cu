@@ -876,6 +876,196 @@ static int section_h(void)
 	return 0;
 }
 
+/* --------------------------------------------------------------- J ------ */
+/* Why do cuMemUnmap + cuMemRelease cost ~8 ms per 256 MiB chunk inside a real
+ * hand-off (r01 call 3) when section B measured 0.14 ms?  Time them separately:
+ * idle, beside our own copy kernel, beside another process's copy-engine traffic,
+ * and with one cuMemUnmap spanning several chunks. */
+struct JState {
+	CUdeviceptr va;
+	size_t chunk, n;
+	std::vector<CUmemGenericAllocationHandle> h;
+	CUmemAllocationProp prop;
+	CUmemAccessDesc acc;
+};
+
+static int j_map_all(JState &j)
+{
+	for (size_t i = 0; i < j.n; ++i) {
+		CU(cuMemCreate(&j.h[i], j.chunk, &j.prop, 0));
+		CU(cuMemMap(j.va + i * j.chunk, j.chunk, 0, j.h[i], 0));
+		CU(cuMemSetAccess(j.va + i * j.chunk, j.chunk, &j.acc, 1));
+	}
+	nvs_slab_fill<<<g_sms * 8, 256>>>((uint64_t *)j.va, j.n * j.chunk / 8, 0, 5);
+	RT(cudaDeviceSynchronize());
+	return 0;
+}
+
+static int j_unmap_all(JState &j, const char *label, size_t span)
+{
+	double t_unmap = 0, t_rel = 0, worst = 0;
+	for (size_t i = 0; i < j.n; i += span) {
+		double t0 = now_s();
+		CU(cuMemUnmap(j.va + i * j.chunk, j.chunk * span));
+		double t1 = now_s();
+		for (size_t k = 0; k < span; ++k)
+			CU(cuMemRelease(j.h[i + k]));
+		double t2 = now_s();
+		t_unmap += t1 - t0;
+		t_rel += t2 - t1;
+		if (t2 - t0 > worst)
+			worst = t2 - t0;
+	}
+	printf("PROBE {\"section\":\"J\",\"case\":\"%s\",\"chunk_mib\":%zu,\"chunks\":%zu,\"span\":%zu,"
+	       "\"unmap_ms_per_chunk\":%.3f,\"release_ms_per_chunk\":%.3f,\"worst_ms\":%.2f,\"GBps\":%.1f}\n",
+	       label, j.chunk / MiB, j.n, span, t_unmap * 1e3 / j.n, t_rel * 1e3 / j.n, worst * 1e3,
+	       j.n * j.chunk / 1e9 / (t_unmap + t_rel));
+	fflush(stdout);
+	return 0;
+}
+
+static int section_j(SharedG *sh)
+{
+	JState j;
+	j.chunk = 256 * MiB;
+	j.n = 64; /* 16 GiB */
+	j.h.resize(j.n);
+	memset(&j.prop, 0, sizeof j.prop);
+	j.prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+	j.prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	j.prop.location.id = g_dev;
+	memset(&j.acc, 0, sizeof j.acc);
+	j.acc.location = j.prop.location;
+	j.acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	CU(cuMemAddressReserve(&j.va, j.n * j.chunk, 0, 0, 0));
+
+	/* side traffic of our own: TMA D2H of a separate 2 GiB buffer, in a loop */
+	Bufs b;
+	memset(&b, 0, sizeof b);
+	b.bytes = 2 * GiB;
+	b.n_slabs = b.bytes / NVS_SLAB_BYTES;
+	CU(cuMemAlloc(&b.dev_a, b.bytes));
+	CU(cuMemHostAlloc((void **)&b.host_a, b.bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+	CU(cuMemHostAlloc((void **)&b.descs_h, 2 * b.n_slabs * sizeof(nvs_copy_desc), CU_MEMHOSTALLOC_PORTABLE));
+	RT(cudaMalloc(&b.descs_d[0], b.n_slabs * sizeof(nvs_copy_desc)));
+	RT(cudaMalloc(&b.counters, 64));
+	RT(cudaStreamCreateWithFlags(&b.st[0], cudaStreamNonBlocking));
+	RT(cudaFuncSetAttribute(nvs_slab_copy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	build_descs(b, 0, b.dev_a, (uint64_t)b.host_a);
+	Geo g = {NVS_COPY_TMA, 8, 1, 6, 32768};
+
+	if (j_map_all(j)) return -1;
+	if (j_unmap_all(j, "idle", 1)) return -1;
+
+	if (j_map_all(j)) return -1;
+	for (int r = 0; r < 24; ++r) /* ~1 s of queued copies */
+		if (launch_copy(b, 0, g, b.st[0])) return -1;
+	if (j_unmap_all(j, "beside own TMA copy kernel", 1)) return -1;
+	RT(cudaDeviceSynchronize());
+
+	if (j_map_all(j)) return -1;
+	if (j_unmap_all(j, "idle, one unmap per 4 chunks", 4)) return -1;
+
+	if (j_map_all(j)) return -1;
+	for (int r = 0; r < 24; ++r)
+		if (launch_copy(b, 0, g, b.st[0])) return -1;
+	if (j_unmap_all(j, "beside own TMA copy kernel, one unmap per 4 chunks", 4)) return -1;
+	RT(cudaDeviceSynchronize());
+
+	/* cuMemGetInfo latency */
+	{
+		size_t f, t;
+		double t0 = now_s();
+		for (int i = 0; i < 2000; ++i)
+			cuMemGetInfo(&f, &t);
+		printf("PROBE {\"section\":\"J\",\"case\":\"cuMemGetInfo\",\"us_per_call\":%.2f}\n", (now_s() - t0) * 1e6 / 2000);
+	}
+	if (sh) {
+		/* another process doing what a fetching client does */
+		if (j_map_all(j)) return -1;
+		sh->go = 1;
+		usleep(300000);
+		if (j_unmap_all(j, "beside another process (CE H2D + map churn)", 1)) return -1;
+		if (j_map_all(j)) return -1;
+		if (j_unmap_all(j, "beside another process, one unmap per 4 chunks", 4)) return -1;
+		if (j_map_all(j)) return -1;
+		for (int r = 0; r < 24; ++r)
+			if (launch_copy(b, 0, g, b.st[0])) return -1;
+		if (j_unmap_all(j, "beside another process AND own TMA kernel", 1)) return -1;
+		RT(cudaDeviceSynchronize());
+		sh->ready = 99; /* tell the child to stop */
+	}
+	return 0;
+}
+
+/* the "fetching client": copy-engine H2D in 256 MiB calls, plus create/map/release churn and cuMemGetInfo polling */
+static int child_j(SharedG *sh)
+{
+	if (cuInit(0) != CUDA_SUCCESS || cudaSetDevice(0) != cudaSuccess || cudaFree(0) != cudaSuccess)
+		return 1;
+	const size_t bytes = 4 * GiB, chunk = 256 * MiB;
+	CUdeviceptr dev;
+	uint8_t *host;
+	CU(cuMemAlloc(&dev, bytes));
+	CU(cuMemHostAlloc((void **)&host, bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+	memset(host, 1, bytes);
+	cudaStream_t st;
+	RT(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	CUmemAllocationProp prop;
+	memset(&prop, 0, sizeof prop);
+	prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+	prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	prop.location.id = 0;
+	CUmemAccessDesc acc;
+	memset(&acc, 0, sizeof acc);
+	acc.location = prop.location;
+	acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	CUdeviceptr va;
+	CU(cuMemAddressReserve(&va, 8 * chunk, 0, 0, 0));
+	while (!sh->go)
+		usleep(100);
+	unsigned long loops = 0;
+	while (sh->ready != 99) {
+		for (size_t off = 0; off < bytes; off += chunk)
+			CU(cuMemcpyAsync(dev + off, (CUdeviceptr)host + off, chunk, st));
+		for (int k = 0; k < 8; ++k) {
+			CUmemGenericAllocationHandle h;
+			size_t f, t;
+			cuMemGetInfo(&f, &t);
+			if (cuMemCreate(&h, chunk, &prop, 0) != CUDA_SUCCESS)
+				continue;
+			cuMemMap(va + k * chunk, chunk, 0, h, 0);
+			cuMemSetAccess(va + k * chunk, chunk, &acc, 1);
+			cuMemUnmap(va + k * chunk, chunk);
+			cuMemRelease(h);
+		}
+		RT(cudaStreamSynchronize(st));
+		++loops;
+	}
+	printf("PROBE {\"section\":\"J\",\"child_loops\":%lu}\n", loops);
+	return 0;
+}
+
+static int section_j_two_process(void)
+{
+	SharedG *sh = (SharedG *)mmap(NULL, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+	memset((void *)sh, 0, sizeof *sh);
+	pid_t c = fork();
+	if (c == 0)
+		_exit(child_j(sh));
+	if (cuInit(0) != CUDA_SUCCESS || cudaSetDevice(0) != cudaSuccess || cudaFree(0) != cudaSuccess)
+		return 1;
+	CUdevice dev0;
+	cuDeviceGet(&dev0, 0);
+	cuDeviceGetAttribute(&g_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev0);
+	int rc = section_j(sh);
+	sh->go = 1;
+	sh->ready = 99;
+	int st;
+	waitpid(c, &st, 0);
+	return rc;
+}
+
 /* --------------------------------------------------------------- I ------ */
 /* The shared host pool: a /dev/shm file, pages faulted in by 8 threads (reads),
  * pinned with cuMemHostRegister.  How fast is provisioning, and is the link
@@ -905,14 +1095,15 @@ static int section_i(void)
 	if (p == MAP_FAILED)
 		return -1;
 	double t0 = now_s();
-	pthread_t th[8];
-	void *args[8][2];
-	for (int i = 0; i < 8; ++i) {
-		args[i][0] = p + bytes / 8 * i;
-		args[i][1] = (void *)(bytes / 8);
+	enum { NTT = 32 };
+	pthread_t th[NTT];
+	void *args[NTT][2];
+	for (int i = 0; i < NTT; ++i) {
+		args[i][0] = p + bytes / NTT * i;
+		args[i][1] = (void *)(bytes / NTT);
 		pthread_create(&th[i], NULL, touch_ro, args[i]);
 	}
-	for (int i = 0; i < 8; ++i)
+	for (int i = 0; i < NTT; ++i)
 		pthread_join(th[i], NULL);
 	double t_touch = now_s() - t0;
 	t0 = now_s();
@@ -983,6 +1174,8 @@ int main(int argc, char **argv)
 	const char *sections = argc > 1 ? argv[1] : "ABCDEF";
 	if (argc > 1 && !strcmp(argv[1], "G")) /* forks before any CUDA initialisation */
 		return section_g();
+	if (argc > 1 && !strcmp(argv[1], "J"))
+		return section_j_two_process();
 	if (argc > 2)
 		g_scale_gib = strtoull(argv[2], NULL, 0);
 	if (cuInit(0) != CUDA_SUCCESS) {
@@ -992,6 +1185,11 @@ int main(int argc, char **argv)
 	if (cudaSetDevice(g_dev) != cudaSuccess || cudaFree(0) != cudaSuccess) {
 		printf("PROBE {\"error\":\"cudaSetDevice\"}\n");
 		return 1;
+	}
+	{
+		CUdevice dev0;
+		cuDeviceGet(&dev0, g_dev);
+		cuDeviceGetAttribute(&g_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev0);
 	}
 	int rc = 0;
 	for (const char *s = sections; *s; ++s) {
