@@ -104,6 +104,33 @@ def measure_link_peak(torch, nbytes=2 * GiB):
     return out
 
 
+def measure_hbm_roofline(torch, nbytes=4 * GiB):
+    """The same sm_100a kernel used device-to-device, all 148 SMs: shows the kernel itself
+    runs at the HBM copy peak, i.e. the link -- not the kernel -- bounds the swap path."""
+    from nvshare_b200 import engine as E
+    src = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    src.random_(0, 255)
+    descs = [(src.data_ptr() + o, dst.data_ptr() + o, 2 * MiB) for o in range(0, nbytes, 2 * MiB)]
+    with E.Engine(prepin=0) as e:
+        n_sms = torch.cuda.get_device_properties(0).multi_processor_count
+        e.copy_slabs(descs, variant="tma", grid=n_sms)
+        ms = min(e.copy_slabs(descs, variant="tma", grid=n_sms) for _ in range(3))
+    ok = bool(torch.equal(src, dst))
+    del src, dst
+    torch.cuda.empty_cache()
+    peak, source = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        peak = float(json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"])
+        source = "MEASURED_PEAKS.json hbm_gbs (burst)"
+    except Exception:
+        pass
+    traffic_gbps = 2 * nbytes / 1e6 / ms            # every payload byte is read once and written once
+    return {"bound": "hbm", "kernel": "nvs_slab_copy_tma (device-to-device, %d CTAs)" % n_sms,
+            "achieved": traffic_gbps, "peak": peak, "unit": "GB/s", "frac": traffic_gbps / peak,
+            "peak_source": source, "payload_GBps": nbytes / 1e6 / ms, "verified": ok}
+
+
 def cpu_baseline(sample_gib=4):
     """oracle_slab_move (memcpy restatement of page migration) on one core."""
     lib_path = ROOT / "oracle" / "_ref" / "liboracle.so"
@@ -223,6 +250,7 @@ def run_rank0(args, torch, world):
     free_b, total_b = torch.cuda.mem_get_info()
     ncpu = os.cpu_count()
     peak = measure_link_peak(torch)
+    hbm_roof = measure_hbm_roofline(torch) if args.impl == "ours" else None
     cpu = cpu_baseline() if (args.impl == "ours" and world == 1) or args.impl == "reference" else None
 
     # -- geometry: clients x footprint = oversub x HBM the experiment may use
@@ -315,8 +343,8 @@ def run_rank0(args, torch, world):
 
     if args.impl == "ours":
         recs = harness.engine_records([out_dir / f"engine{i}.jsonl" for i in range(args.clients)], a["t_start"], a["t_end"])
-        ev = [r for r in recs if r["op"] == "evict" and r["bytes"]]
-        fe = [r for r in recs if r["op"] == "fetch" and r["bytes"]]
+        ev = [r for r in recs if r["op"] == "evict" and (r["bytes"] or r.get("elided_bytes"))]
+        fe = [r for r in recs if r["op"] == "fetch" and (r["bytes"] or r.get("elided_bytes"))]
         bytes_moved = sum(r["bytes"] for r in ev + fe)
         dev_ms = sum(r["copy_ms"] for r in ev + fe)
         launches = sum(r["launches"] for r in ev + fe)
@@ -325,6 +353,7 @@ def run_rank0(args, torch, world):
         line["value"] = bytes_moved / 1e6 / dev_ms if dev_ms else None
         line["gpu_launches"] = launches
         line["device"] = {"evict_GBps": ev_gbps, "fetch_GBps": fe_gbps, "bytes_moved": bytes_moved,
+                          "bytes_elided_same_filled": sum(r.get("elided_bytes", 0) for r in recs),
                           "evicts": len(ev), "fetches": len(fe),
                           "map_ms_mean": statistics_mean([r["map_ms"] for r in ev + fe]),
                           "wait_ms_mean": statistics_mean([r["wait_ms"] for r in fe]),
@@ -340,6 +369,7 @@ def run_rank0(args, torch, world):
                                            "cuMemcpyAsync pinned<->HBM measured in this run (nominal PCIe Gen5 x16: 63.0 GB/s)",
                             "kernel": "nvs_slab_copy_tma",
                             "algorithmic_bytes_per_launch": bytes_moved / launches if launches else None}
+        line["roofline_hbm"] = hbm_roof
         line["e2e"] = {"value": e2e_gbps, "unit": "GB/s", "iter_per_s": a["iter_per_s"],
                        "h2d_bytes_per_step": sum(r["bytes"] for r in fe) / max(args.steps, 1),
                        "d2h_bytes_per_step": sum(r["bytes"] for r in ev) / max(args.steps, 1),

@@ -125,8 +125,12 @@ def run(argv=None) -> int:
     bad = 0
     if args.kind == "add":
         if args.pattern == "ones":
-            bad = int((z != 2.0).sum().item())
-            bad += int((x != 1.0).sum().item()) + int((y != 1.0).sum().item())
+            # block-wise: a whole-tensor comparison would need n^2 extra bytes (and more for the
+            # reduction), which the per-process cap rightly refuses at 0.75 x HBM
+            for r0 in range(0, n, block_rows):
+                r = min(block_rows, n - r0)
+                bad += int((z[r0:r0 + r] != 2.0).sum().item())
+                bad += int((x[r0:r0 + r] != 1.0).sum().item()) + int((y[r0:r0 + r] != 1.0).sum().item())
         else:
             for r0 in range(0, n, block_rows):
                 r = min(block_rows, n - r0)
@@ -138,7 +142,9 @@ def run(argv=None) -> int:
     else:
         if args.pattern == "ones":
             # tolerance from north_star: 1e-5 relative (exact for n < 2**24)
-            bad = int(((z - float(n)).abs() > 1e-5 * n).sum().item())
+            for r0 in range(0, n, block_rows):
+                r = min(block_rows, n - r0)
+                bad += int(((z[r0:r0 + r] - float(n)).abs() > 1e-5 * n).sum().item())
         else:
             # integer-valued inputs < 2**11 would be needed for exactness; for matmul
             # the pos pattern only checks that the INPUTS survived the hand-offs.

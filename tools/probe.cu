@@ -1066,6 +1066,139 @@ static int section_j_two_process(void)
 	return rc;
 }
 
+/* --------------------------------------------------------------- K ------ */
+/* The hand-off with HBM FULL: process A owns ~all free HBM in 256 MiB chunks and
+ * gives it back chunk by chunk (unmap + release); process B grabs whatever
+ * becomes free (create + map + setaccess), exactly like evict vs fetch but with
+ * no data movement.  r01 call 4 saw ~7.5 ms per chunk in the real hand-off
+ * against 0.4 ms in section J (where HBM was never short).  Variants:
+ *   mode 0  B polls cuMemGetInfo every 1 ms and maps as soon as one chunk fits
+ *   mode 1  B maps only when >= 8 GiB are free (A runs ahead, calls interleave less)
+ *   mode 2  B does not run at all (A alone, memory full at start)            */
+struct SharedK {
+	volatile int ready, go, done_a;
+	volatile long b_chunks;
+	double b_map_ms;
+};
+
+static int child_k(SharedK *sh, int mode, size_t chunk, size_t want_chunks)
+{
+	if (cuInit(0) != CUDA_SUCCESS || cudaSetDevice(0) != cudaSuccess || cudaFree(0) != cudaSuccess)
+		return 1;
+	CUmemAllocationProp prop;
+	memset(&prop, 0, sizeof prop);
+	prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+	prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	prop.location.id = 0;
+	CUmemAccessDesc acc;
+	memset(&acc, 0, sizeof acc);
+	acc.location = prop.location;
+	acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	CUdeviceptr va;
+	CU(cuMemAddressReserve(&va, want_chunks * chunk, 0, 0, 0));
+	std::vector<CUmemGenericAllocationHandle> h(want_chunks);
+	__sync_fetch_and_add(&sh->ready, 1);
+	while (!sh->go)
+		usleep(100);
+	size_t got = 0;
+	double t_map = 0;
+	const size_t need_free = mode == 1 ? 8 * GiB : chunk + 64 * MiB;
+	while (got < want_chunks && !(sh->done_a && got >= want_chunks)) {
+		size_t f = 0, t = 0;
+		cuMemGetInfo(&f, &t);
+		if (f < need_free && !(sh->done_a)) {
+			usleep(1000);
+			continue;
+		}
+		size_t burst = mode == 1 ? (f - 64 * MiB) / chunk : 1;
+		for (size_t k = 0; k < burst && got < want_chunks; ++k) {
+			double t0 = now_s();
+			if (cuMemCreate(&h[got], chunk, &prop, 0) != CUDA_SUCCESS)
+				break;
+			cuMemMap(va + got * chunk, chunk, 0, h[got], 0);
+			cuMemSetAccess(va + got * chunk, chunk, &acc, 1);
+			t_map += now_s() - t0;
+			++got;
+			sh->b_chunks = (long)got;
+		}
+		if (sh->done_a && f < chunk + 64 * MiB)
+			break;
+	}
+	sh->b_map_ms = t_map * 1e3;
+	return 0;
+}
+
+static int section_k(void)
+{
+	const size_t chunk = 256 * MiB;
+	for (int mode = 0; mode < 3; ++mode) {
+		SharedK *sh = (SharedK *)mmap(NULL, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+		memset((void *)sh, 0, sizeof *sh);
+		const size_t n_give = 200; /* 50 GiB change hands */
+		pid_t c = 0;
+		if (mode != 2) {
+			c = fork();
+			if (c == 0)
+				_exit(child_k(sh, mode, chunk, n_give));
+		}
+		pid_t a = fork();
+		if (a == 0) {
+			/* process A */
+			if (cuInit(0) != CUDA_SUCCESS || cudaSetDevice(0) != cudaSuccess || cudaFree(0) != cudaSuccess)
+				_exit(1);
+			CUdevice dev0;
+			cuDeviceGet(&dev0, 0);
+			cuDeviceGetAttribute(&g_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev0);
+			JState j;
+			size_t f = 0, t = 0;
+			cuMemGetInfo(&f, &t);
+			j.chunk = chunk;
+			j.n = (f - 1 * GiB) / chunk; /* take everything but ~1 GiB: HBM is now full */
+			j.h.resize(j.n);
+			memset(&j.prop, 0, sizeof j.prop);
+			j.prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+			j.prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+			j.prop.location.id = 0;
+			memset(&j.acc, 0, sizeof j.acc);
+			j.acc.location = j.prop.location;
+			j.acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+			if (cuMemAddressReserve(&j.va, j.n * j.chunk, 0, 0, 0) != CUDA_SUCCESS || j_map_all(j))
+				_exit(2);
+			while (mode != 2 && sh->ready < 1)
+				usleep(100);
+			sh->go = 1;
+			usleep(50000);
+			double t_unmap = 0, t_rel = 0, t0all = now_s();
+			for (size_t i = 0; i < n_give; ++i) {
+				double t0 = now_s();
+				cuMemUnmap(j.va + i * j.chunk, j.chunk);
+				double t1 = now_s();
+				cuMemRelease(j.h[i]);
+				t_unmap += t1 - t0;
+				t_rel += now_s() - t1;
+			}
+			double wall = now_s() - t0all;
+			sh->done_a = 1;
+			printf("PROBE {\"section\":\"K\",\"mode\":%d,\"hbm_chunks_held\":%zu,\"given\":%zu,\"unmap_ms_per_chunk\":%.3f,"
+			       "\"release_ms_per_chunk\":%.3f,\"wall_s\":%.3f,\"GBps\":%.1f}\n", mode, j.n, n_give,
+			       t_unmap * 1e3 / n_give, t_rel * 1e3 / n_give, wall, n_give * chunk / 1e9 / wall);
+			fflush(stdout);
+			usleep(300000);
+			_exit(0);
+		}
+		int st;
+		waitpid(a, &st, 0);
+		sh->done_a = 1;
+		sh->go = 1;
+		if (c > 0)
+			waitpid(c, &st, 0);
+		printf("PROBE {\"section\":\"K\",\"mode\":%d,\"b_chunks\":%ld,\"b_map_ms_per_chunk\":%.3f}\n", mode, sh->b_chunks,
+		       sh->b_chunks ? sh->b_map_ms / sh->b_chunks : 0.0);
+		fflush(stdout);
+	}
+	return 0;
+}
+
 /* --------------------------------------------------------------- I ------ */
 /* The shared host pool: a /dev/shm file, pages faulted in by 8 threads (reads),
  * pinned with cuMemHostRegister.  How fast is provisioning, and is the link
@@ -1176,6 +1309,8 @@ int main(int argc, char **argv)
 		return section_g();
 	if (argc > 1 && !strcmp(argv[1], "J"))
 		return section_j_two_process();
+	if (argc > 1 && !strcmp(argv[1], "K"))
+		return section_k();
 	if (argc > 2)
 		g_scale_gib = strtoull(argv[2], NULL, 0);
 	if (cuInit(0) != CUDA_SUCCESS) {
