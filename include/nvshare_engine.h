@@ -95,6 +95,9 @@ typedef struct nvs_engine_config {
 	/* 1 = scan slabs before eviction and do not move same-filled ones (all 64-bit
 	 * words equal): they are re-created on the device at fetch (nvs_slab_splat) */
 	uint32_t elide_constant;
+	/* fetch maps HBM in bursts of this many bytes once that much is free, instead of
+	 * chunk by chunk as it trickles in from the evicting process (8 GiB; probe K) */
+	uint64_t burst_bytes;
 } nvs_engine_config;
 
 typedef struct nvs_xfer_report {

@@ -417,6 +417,7 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->chunk_bytes = env_u64("NVSHARE_CHUNK_MIB", 256) << 20;
 	cfg->small_alloc_bytes = env_u64("NVSHARE_SMALL_ALLOC_KIB", 1024) << 10;
 	cfg->batch_bytes = env_u64("NVSHARE_BATCH_MIB", 1024) << 20;
+	cfg->burst_bytes = env_u64("NVSHARE_BURST_MIB", 8192) << 20;
 	cfg->host_arena_bytes = env_u64("NVSHARE_HOST_ARENA_MIB", 1024) << 20;
 	cfg->evict_variant = parse_variant(getenv("NVSHARE_EVICT_VARIANT"),
 					   parse_variant(getenv("NVSHARE_COPY_VARIANT"), NVS_COPY_TMA));
@@ -1417,6 +1418,46 @@ out:
 
 /* ------------------------------------------------------------- fetch ---- */
 
+/*
+ * Burst gating.  While another process is still handing its HBM back, do NOT map
+ * each chunk the moment it fits: with HBM full, one process releasing and another
+ * creating chunk by chunk slow every VMM call from ~0.3 ms to ~5 ms (B200, probe K:
+ * 41 GB/s of "hand-over bandwidth", less than the PCIe copy it is supposed to feed).
+ * Waiting until a burst (8 GiB, or all that is still missing) is free and then
+ * mapping it back to back restores ~0.2 ms per call (511 GB/s in the same probe)
+ * for ~0.17 s of added latency per hand-off.
+ */
+static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report *rep)
+{
+	/* head-room kept below the releasing client's own margin (1/128 of the HBM, client.c) */
+	const uint64_t slack = e->cfg.chunk_bytes < (64ull << 20) ? e->cfg.chunk_bytes : (64ull << 20);
+	uint64_t want = remaining < e->cfg.burst_bytes ? remaining : e->cfg.burst_bytes;
+	size_t free_b = 0, total_b = 0;
+	if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= e->cfg.batch_bytes + e->cfg.chunk_bytes + slack ||
+	    free_b >= remaining + slack)
+		return 0; /* room for at least this batch: carry on with the current burst */
+	double t0 = now_ms(), next_pressure = 200;
+	for (;;) {
+		if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= want + slack)
+			break;
+		double waited = now_ms() - t0;
+		if (waited > e->cfg.oom_wait_ms) {
+			nvs_warn("engine: HBM still exhausted after %.0f ms", waited);
+			rep->wait_ms += waited;
+			return NVS_E_TIMEOUT;
+		}
+		if (e->cfg.pressure_cb && waited >= next_pressure) {
+			e->cfg.pressure_cb(e->cfg.pressure_user, remaining);
+			next_pressure = waited + 1000;
+		}
+		pthread_mutex_unlock(&e->mu);
+		usleep(2000);
+		pthread_mutex_lock(&e->mu);
+	}
+	rep->wait_ms += now_ms() - t0;
+	return 0;
+}
+
 /* A batch has landed in HBM: its backing units go back to the pool at once, so
  * that the client evicting right now (other process, shared pool) can reuse them. */
 static int fetch_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
@@ -1455,10 +1496,13 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 	unsigned batch_no = 0;
 	struct alloc *a = e->head;
 	uint32_t ci = 0;
+	uint64_t remaining = e->st.swapped_bytes + e->st.unbacked_bytes;
 	for (;;) {
 		/* next batch of non-resident chunks, allocation order */
 		struct slot *s = &e->slots[batch_no % N_SLOTS];
 		if ((rc = fetch_retire(e, s, &rep)) != 0)
+			goto out;
+		if (remaining && (rc = wait_for_hbm_burst(e, remaining, &rep)) != 0)
 			goto out;
 		uint64_t batch = 0, copy_bytes = 0;
 		int peer_traffic = 0;
@@ -1508,6 +1552,7 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 			c->epoch = e->epoch;
 			state_account(e, c, CH_RESIDENT);
 			batch += c->bytes;
+			remaining = remaining > c->bytes ? remaining - c->bytes : 0;
 			++ci;
 		}
 		rep.map_ms += now_ms() - t0;

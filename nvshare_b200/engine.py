@@ -36,6 +36,7 @@ class EngineConfig(C.Structure):
         ("peer_capacity_bytes", C.c_uint64), ("stats_path", C.c_char_p),
         ("pressure_cb", C.c_void_p), ("pressure_user", C.c_void_p),
         ("shared_pool_path", C.c_char_p), ("shared_pool_bytes", C.c_uint64), ("elide_constant", C.c_uint32),
+        ("burst_bytes", C.c_uint64),
     ]
 
 
