@@ -46,6 +46,7 @@
 #include <signal.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 
 #include "../../include/nvshare_engine.h"
 #include "cuda_min.h"
@@ -848,6 +849,22 @@ static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
 	if (cap_slabs > SHP_MAX_SLABS)
 		cap_slabs = SHP_MAX_SLABS / window_slabs * window_slabs;
 	int creator = 1;
+	{
+		/* a tmpfs smaller than the pool (docker's default /dev/shm is 64 MiB) would turn
+		 * page faults into SIGBUS: only use the shared pool where it really fits */
+		char dir[256];
+		snprintf(dir, sizeof(dir), "%s", path);
+		char *slash = strrchr(dir, '/');
+		if (slash)
+			*slash = '\0';
+		struct statvfs vfs;
+		if (access(path, F_OK) != 0 && statvfs(slash ? dir : ".", &vfs) == 0 &&
+		    (uint64_t)vfs.f_bavail * vfs.f_frsize < cap_slabs * SLAB + SHP_HDR_BYTES) {
+			errno = ENOSPC;
+			free(sp);
+			return -1;
+		}
+	}
 	sp->fd = open(path, O_RDWR | O_CREAT | O_EXCL | O_CLOEXEC, 0600);
 	if (sp->fd < 0 && errno == EEXIST) {
 		creator = 0;
