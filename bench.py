@@ -280,7 +280,8 @@ def run_rank0(args, torch, world):
     extra = {}
     if world > 1 and args.impl == "ours":
         extra["NVSHARE_PEERS"] = ",".join(str(i) for i in range(1, world))
-        extra["NVSHARE_PEER_CAPACITY_MIB"] = int(0.9 * total_b * (world - 1) / args.clients) >> 20
+        # per peer; empty peer arenas are returned at once, so the clients share the peers' HBM over time
+        extra["NVSHARE_PEER_CAPACITY_MIB"] = int(0.92 * total_b) >> 20
     sampler = harness.ClockSampler(out_dir / "clocks.csv")
     sampler.start()
     t0 = time.time()

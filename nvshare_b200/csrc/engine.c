@@ -808,8 +808,26 @@ static void backing_release(nvs_engine *e, struct chunk *c)
 		pool_give(e, &e->host_pool, c->backing, n);
 		e->st.host_pool_used = e->host_pool.used;
 	} else if (c->tier >= TIER_PEER0) {
-		pool_give(e, &e->peer_pools[c->tier - TIER_PEER0], c->backing, n);
+		struct pool *p = &e->peer_pools[c->tier - TIER_PEER0];
+		pool_give(e, p, c->backing, n);
 		e->st.peer_pool_used -= c->bytes;
+		/* peer HBM is per-process (no shared pool yet): hand empty arenas back to the peer
+		 * GPU at once, so that the client evicting right now finds room there */
+		for (struct arena **pp = &p->arenas; *pp;) {
+			struct arena *a = *pp;
+			if (a->used != 0) {
+				pp = &a->next;
+				continue;
+			}
+			*pp = a->next;
+			e->d.MemUnmap(a->dev_base, a->bytes);
+			e->d.MemAddressFree(a->dev_base, a->bytes);
+			e->d.MemRelease(a->handle);
+			p->bytes -= a->bytes;
+			e->st.peer_pool_bytes -= a->bytes;
+			free(a->bitmap);
+			free(a);
+		}
 	}
 	c->backing = 0;
 	c->tier = TIER_NONE;

@@ -681,6 +681,7 @@ static int section_f(void)
 		RT(cudaStreamCreateWithFlags(&b.st[i], cudaStreamNonBlocking));
 	for (int i = 0; i < 4; ++i)
 		RT(cudaEventCreate(&b.ev[i]));
+	RT(cudaFuncSetAttribute(nvs_slab_copy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	if (fill(b, b.dev_a, 1))
 		return -1;
 	const int grids[] = {8, 16, 32, 74, 148};
