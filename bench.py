@@ -219,8 +219,13 @@ def main():
     use_dist = world > 1 and args.impl != "reference"
     if use_dist:
         import torch.distributed as dist
+        import datetime
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world,
+                                timeout=datetime.timedelta(minutes=60))
+        # create the communicator now, while GPU 0 is still empty; the data-path work then runs on rank 0
+        # alone (the path shards by slab over the peers' HBM, not by rank) and everybody meets again below
+        dist.barrier()
 
     result = None
     t_region = 0.0

@@ -327,6 +327,14 @@ static void *message_thread(void *arg)
 				uint64_t mib = strtoull(in.data + 1, NULL, 10);
 				sync_app_context();
 				do_evict(mib ? mib + evict_margin_mib() : EVICT_ALL);
+				if (need_lock) {
+					/* our queued request still advertises the old need: refresh it, or the
+					 * holder will free too little for us and we will have to press it again */
+					char hint[NVS_MSG_DATA_LEN];
+					snprintf(hint, sizeof(hint), "%c%" PRIu64, NVS_HINT_NEED_PREFIX,
+						 dp.nonresident_mib ? dp.nonresident_mib() : 0);
+					send_msg(NVS_REQ_LOCK, hint);
+				}
 			}
 			break;
 		}

@@ -368,10 +368,12 @@ static void on_message(struct client *c, const struct nvs_msg *in)
 		}
 		if (in->data[0] == NVS_HINT_NEED_PREFIX)
 			c->need_mib = strtoull(in->data + 1, NULL, 10);
-		if (c->queued)
-			nvs_warn("Client %s has already requested the lock", ids);
-		else
+		if (c->queued) {
+			if (in->data[0] != NVS_HINT_NEED_PREFIX) /* a refreshed need hint is not a mistake */
+				nvs_warn("Client %s has already requested the lock", ids);
+		} else {
 			q_push(c);
+		}
 		if (!lock_held)
 			try_schedule();
 		return;
