@@ -131,6 +131,20 @@ def measure_hbm_roofline(torch, nbytes=4 * GiB):
             "peak_source": source, "payload_GBps": nbytes / 1e6 / ms, "verified": ok}
 
 
+def ncu_traffic_ratio():
+    """DRAM bytes (read + write) per payload byte of the eviction kernel, from the committed
+    `ncu --set full` capture (profiles/r01_ncu_full_tma_selected.csv, first launch: 1 GiB HBM -> host)."""
+    import csv
+    try:
+        rows = list(csv.reader(open(ROOT / "profiles" / "r01_ncu_full_tma_selected.csv")))
+        hdr, first = rows[0], rows[2]
+        rd = float(first[hdr.index("dram__bytes_read.sum")])
+        wr = float(first[hdr.index("dram__bytes_write.sum")])
+        return (rd + wr) * 1e9 / float(1 << 30)
+    except Exception:
+        return None
+
+
 def cpu_baseline(sample_gib=4):
     """oracle_slab_move (memcpy restatement of page migration) on one core."""
     lib_path = ROOT / "oracle" / "_ref" / "liboracle.so"
@@ -370,7 +384,11 @@ def run_rank0(args, torch, world):
         link = "nvlink" if world > 1 else "pcie"
         pk = 770.0 if world > 1 else (peak["d2h"] + peak["h2d"]) / 2
         line["roofline"] = {"bound": link, "achieved": achieved, "peak": pk, "unit": "GB/s",
-                            "frac": achieved / pk if achieved else None, "traffic": None,
+                            "frac": achieved / pk if achieved else None,
+                            "traffic": (bytes_moved / launches * ncu_traffic_ratio()) if launches and ncu_traffic_ratio() else None,
+                            "traffic_source": "DRAM read+write per launch = algorithmic bytes per launch x the ratio measured by "
+                                              "ncu --set full (profiles/r01_ncu_summary.md: 1.0796 GB of DRAM traffic for a "
+                                              "1.0737 GB launch)",
                             "peak_source": "770 GB/s measured peer copy (B200_PROFILING.md)" if world > 1 else
                                            "cuMemcpyAsync pinned<->HBM measured in this run (nominal PCIe Gen5 x16: 63.0 GB/s)",
                             "kernel": "nvs_slab_copy_tma",
