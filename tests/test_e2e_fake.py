@@ -100,6 +100,30 @@ def test_reference_library_under_our_daemon(artefacts, default_sock_lock, tmp_pa
     assert log.count("Sent DROP_LOCK") >= 2
 
 
+def test_multithreaded_clients_oversubscribed(artefacts, sock_dir, tmp_path):
+    """Four application threads per client issue copies and launches concurrently while
+    the lock changes hands every second: nothing may touch a slab that is being unmapped
+    (the fake driver would segfault) and every thread's data must survive."""
+    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
+    try:
+        d.ctl("-T", "1")
+        procs = []
+        for i in (1, 2):
+            env = fake_env(total_mib=200, ledger=tmp_path / "ledger",
+                           extra={"NVSHARE_HOST_ARENA_MIB": 64, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_BATCH_MIB": 32,
+                                  "NVSHARE_DEBUG": 1, "NVSHARE_SOCK_DIR": sock_dir, "NVSHARE_POOL_GIB": 1})
+            env["LD_PRELOAD"] = preload("ours")
+            # 4 threads x 2 buffers x 16 MiB = 128 MiB per client on a 200 MiB "GPU"
+            procs.append(subprocess.Popen([str(ORACLE / "mt_app"), "16", "5", str(i), "4"], env=env,
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=120) for p in procs]
+    finally:
+        d.stop()
+    for p, (out, err) in zip(procs, outs):
+        assert p.returncode == 0 and re.search(r"RESULT PASS iters=\d+ mismatches=0", out), out + err[-2500:]
+    assert d.read_log().count("Sent DROP_LOCK") >= 3
+
+
 def test_client_exits_when_scheduler_is_absent(artefacts, sock_dir, tmp_path):
     env = fake_env(extra={"NVSHARE_SOCK_DIR": sock_dir})
     env["LD_PRELOAD"] = preload("ours")
