@@ -100,6 +100,33 @@ def test_reference_library_under_our_daemon(artefacts, default_sock_lock, tmp_pa
     assert log.count("Sent DROP_LOCK") >= 2
 
 
+def test_anti_thrash_off_and_on_again(artefacts, sock_dir, tmp_path):
+    """nvsharectl -S off lets every client run at once (they must all fit: 2 x 120 MiB on
+    400 MiB); -S on closes the gates again.  Data survive both transitions."""
+    import time
+    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
+    try:
+        d.ctl("-T", "1")
+        procs = []
+        for i in (1, 2):
+            env = fake_env(total_mib=400, ledger=tmp_path / "ledger",
+                           extra={"NVSHARE_HOST_ARENA_MIB": 64, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_DEBUG": 1,
+                                  "NVSHARE_SOCK_DIR": sock_dir, "NVSHARE_POOL_GIB": 1})
+            env["LD_PRELOAD"] = preload("ours")
+            procs.append(subprocess.Popen([str(ORACLE / "driver_app"), "40", "6", str(i), "3"], env=env,
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        time.sleep(2.0)
+        d.ctl("-S", "off")
+        time.sleep(2.0)
+        d.ctl("-S", "on")
+        outs = [p.communicate(timeout=120) for p in procs]
+    finally:
+        d.stop()
+    for p, (out, err) in zip(procs, outs):
+        assert p.returncode == 0 and re.search(r"RESULT PASS iters=\d+ mismatches=0", out), out + err[-2500:]
+        assert "Scheduler status changed to OFF" in err and "Scheduler status changed to ON" in err
+
+
 def test_multithreaded_clients_oversubscribed(artefacts, sock_dir, tmp_path):
     """Four application threads per client issue copies and launches concurrently while
     the lock changes hands every second: nothing may touch a slab that is being unmapped
