@@ -232,7 +232,9 @@ def run_clients(impl, out_dir, n_clients, kind, n, pattern, seconds, tq, extra_e
     procs = []
     try:
         for i in range(n_clients):
-            env = dict(os.environ, LD_PRELOAD=str(paths["lib"]), PYTHONPATH=str(ROOT))
+            # keep whatever is already preloaded (e.g. a profiler's injection library) behind ours
+            preload = str(paths["lib"]) + (":" + os.environ["LD_PRELOAD"] if os.environ.get("LD_PRELOAD") else "")
+            env = dict(os.environ, LD_PRELOAD=preload, PYTHONPATH=str(ROOT))
             if impl == "ours":
                 env["NVSHARE_SOCK_DIR"] = str(sock_dir)
                 env["NVSHARE_STATS_FILE"] = str(out_dir / f"engine{i}.jsonl")
