@@ -8,21 +8,25 @@
  *
  *   allocation  cuMemAddressReserve for the application's pointer (stable for
  *               the allocation's life) + cuMemCreate/cuMemMap/cuMemSetAccess
- *               per CHUNK (default 64 MiB = 32 slabs).  Measured on B200
- *               (profiles/r01_probe_b200.txt): mapping 8 GiB costs 221 ms in
- *               2 MiB units but 6.7 ms in 64 MiB units; unmap+release 716 ms vs
- *               12 ms.  Copy and accounting granularity stays one SLAB (2 MiB).
+ *               per CHUNK (default 256 MiB = 128 slabs).  VMM calls cost per call,
+ *               not per byte (profiles/r01_probe_b200.txt section B: mapping
+ *               8 GiB = 221 ms in 2 MiB units, 6.7 ms in 64 MiB, 2.0 ms in
+ *               256 MiB).  Copy and accounting granularity stays one SLAB (2 MiB).
  *   backing     tier 1: HBM of peer GPUs (cuMemCreate on the peer, mapped into
- *               this context; striped per chunk; no NCCL).  tier 0: pinned host
- *               DRAM arenas (cuMemHostAlloc PORTABLE|DEVICEMAP, 1 GiB units,
- *               bitmap sub-allocation, grown in the background because pinning
- *               runs at only ~3.8 GB/s on this box).
- *   evict       resident chunks, least recently fetched first -> descriptors
- *               -> nvs_slab_copy_tma on a side stream, batch b+1 copying
- *               while batch b is unmapped and its HBM released.
- *   fetch       the mirror image: map batch b+1 while batch b copies.  HBM may
- *               still be held by the client that is evicting in another
- *               process: cuMemCreate is retried until it is released.
+ *               this context; striped per chunk; arenas returned as soon as they
+ *               are empty; no NCCL).  tier 0: pinned host DRAM -- by default ONE
+ *               pool per scheduler shared by all its clients (a /dev/shm file,
+ *               1 GiB windows registered per process), else private
+ *               cuMemHostAlloc arenas.  Backing is released as soon as a batch
+ *               has been fetched back.
+ *   evict       resident chunks, least recently fetched first -> nvs_slab_scan
+ *               (same-filled slabs are described, not moved) -> descriptors ->
+ *               nvs_slab_copy_tma on a side stream, batch b+1 copying while
+ *               batch b is unmapped and its HBM released.
+ *   fetch       the mirror image with the copy engines (the evicting process is
+ *               running its kernel at the same time; probe G): wait until a BURST
+ *               of HBM is free (probe K), map it back to back, copy, splat the
+ *               same-filled slabs.
  *
  * Chunk states:  UNBACKED (virtual only; contents undefined like fresh
  * cuMemAlloc memory, nothing to copy) -> RESIDENT <-> SWAPPED.

@@ -22,7 +22,7 @@
  *
  * What is different by design:
  *   - cuMemAlloc does NOT become cuMemAllocManaged.  It goes to the swap engine
- *     (engine.c): a VMM reservation whose 64 MiB chunks are mapped, copied out
+ *     (engine.c): a VMM reservation whose 256 MiB chunks are mapped, copied out
  *     and unmapped explicitly around lock hand-offs.  The reference's path is
  *     still there as a mode (NVSHARE_ENGINE=uvm, and always when
  *     NVSHARE_ENABLE_SINGLE_OVERSUB is set, since a single process larger than
