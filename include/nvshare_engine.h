@@ -96,7 +96,7 @@ typedef struct nvs_engine_config {
 	 * words equal): they are re-created on the device at fetch (nvs_slab_splat) */
 	uint32_t elide_constant;
 	/* fetch maps HBM in bursts of this many bytes once that much is free, instead of
-	 * chunk by chunk as it trickles in from the evicting process (2 GiB; probe K, call 11) */
+	 * chunk by chunk as it trickles in from the evicting process (8 GiB; probe K, calls 11-12) */
 	uint64_t burst_bytes;
 } nvs_engine_config;
 

@@ -422,7 +422,7 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->chunk_bytes = env_u64("NVSHARE_CHUNK_MIB", 256) << 20;
 	cfg->small_alloc_bytes = env_u64("NVSHARE_SMALL_ALLOC_KIB", 1024) << 10;
 	cfg->batch_bytes = env_u64("NVSHARE_BATCH_MIB", 1024) << 20;
-	cfg->burst_bytes = env_u64("NVSHARE_BURST_MIB", 2048) << 20;
+	cfg->burst_bytes = env_u64("NVSHARE_BURST_MIB", 8192) << 20;
 	cfg->host_arena_bytes = env_u64("NVSHARE_HOST_ARENA_MIB", 1024) << 20;
 	cfg->evict_variant = parse_variant(getenv("NVSHARE_EVICT_VARIANT"),
 					   parse_variant(getenv("NVSHARE_COPY_VARIANT"), NVS_COPY_TMA));
@@ -1464,9 +1464,11 @@ out:
  * 41 GB/s of "hand-over bandwidth", less than the PCIe copy it is supposed to feed).
  * Waiting until a burst is free and then mapping it back to back restores ~0.2 ms
  * per call (511 GB/s in the same probe with 8 GiB bursts).  The burst also delays
- * the start of the fetch by burst / eviction rate, so it is kept small: 2 GiB
- * (8 chunks) measured best on the BASELINE configuration (stall 2.59 s vs 2.93-3.02 s
- * with 8 GiB and 3.40 s with 16 GiB: profiles/r01_call11_burst_sweep_summary.txt).
+ * the start of the fetch by burst / eviction rate (0.17 s for 8 GiB over PCIe).
+ * 8 GiB is the measured compromise on the BASELINE configuration: 16 GiB costs
+ * latency (stall 3.40 s vs 2.93-3.02 s), 2 GiB brings the contention back (three
+ * runs: 2.59, 3.16, 4.21 s, eviction down to 35 GB/s; all-ones data 1.10 s vs
+ * 0.30 s) -- profiles/r01_call11_burst_sweep_summary.txt, r01_call12_*.
  */
 static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report *rep)
 {
