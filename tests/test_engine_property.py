@@ -1,0 +1,109 @@
+"""Property test of the swap engine's host logic (fake driver): arbitrary
+interleavings of alloc / write / evict(partial or all) / fetch / free never lose
+or mix up a byte, and the accounting identities always hold.  The model is a
+plain dict of numpy arrays; contents are checked by direct reads (the fake
+driver's "HBM" is host-addressable while mapped)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from nvs_testlib import FAKE_DIR
+
+MiB = 1 << 20
+SLAB = 2 * MiB
+
+
+@pytest.fixture(scope="module")
+def fake(artefacts):
+    lib = C.CDLL(str(FAKE_DIR / "libcuda.so.1"), mode=C.RTLD_GLOBAL)
+    lib.fake_cuda_phys_used.restype = C.c_uint64
+    assert lib.cuInit(0) == 0
+    ctx = C.c_void_p()
+    assert lib.cuDevicePrimaryCtxRetain(C.byref(ctx), 0) == 0
+    assert lib.cuCtxSetCurrent(ctx) == 0
+    return lib
+
+
+def view(ptr, nbytes):
+    return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr))
+
+
+ops = st.lists(
+    st.one_of(
+        st.tuples(st.just("alloc"), st.integers(1, 9), st.booleans()),          # size in slabs (+ ragged bytes), constant fill?
+        st.tuples(st.just("write"), st.integers(0, 7), st.integers(0, 255)),    # which allocation, seed
+        st.tuples(st.just("const"), st.integers(0, 7), st.integers(0, 255)),    # make one slab same-filled
+        st.tuples(st.just("evict"), st.integers(0, 12), st.just(0)),            # 0 = all, else MiB
+        st.tuples(st.just("fetch"), st.just(0), st.just(0)),
+        st.tuples(st.just("free"), st.integers(0, 7), st.just(0)),
+    ),
+    min_size=4, max_size=28)
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(script=ops, elide=st.booleans(), chunk_slabs=st.sampled_from([1, 2, 4]))
+def test_any_interleaving_preserves_contents(fake, script, elide, chunk_slabs):
+    from nvshare_b200 import engine as E
+    base = fake.fake_cuda_phys_used()
+    e = E.Engine(chunk_bytes=chunk_slabs * SLAB, host_arena_bytes=16 * MiB, batch_bytes=8 * MiB, oom_wait_ms=200,
+                 elide_constant=int(elide), prepin=0)
+    model = {}          # ptr -> expected bytes
+    order = []
+    resident = True     # what the owner believes: we fetch before touching memory
+    try:
+        e.fetch_all()
+        for op, a, b in script:
+            if op == "alloc":
+                size = a * SLAB - (123 if b and a > 1 else 0)
+                p = e.alloc(size)
+                if not resident:
+                    e.fetch_all(); resident = True
+                else:
+                    e.fetch_all()                       # a fresh allocation is UNBACKED until mapped
+                data = np.full(size, 7 if b else 0, dtype=np.uint8)
+                view(p, size)[:] = data
+                model[p] = data
+                order.append(p)
+            elif op in ("write", "const") and order:
+                p = order[a % len(order)]
+                if not resident:
+                    e.fetch_all(); resident = True
+                n = len(model[p])
+                if op == "write":
+                    rng = np.random.default_rng(b)
+                    model[p][:] = rng.integers(0, 256, n, dtype=np.uint8)
+                else:
+                    s0 = (b % max(1, n // SLAB)) * SLAB
+                    model[p][s0:min(n, s0 + SLAB)] = b
+                view(p, n)[:] = model[p]
+            elif op == "evict":
+                rep = e.evict(a * MiB)
+                st_ = e.stats()
+                if a == 0:
+                    assert st_["resident_bytes"] == 0
+                resident = False
+            elif op == "fetch":
+                e.fetch_all(); resident = True
+            elif op == "free" and order:
+                p = order.pop(a % len(order))
+                e.free(p)
+                del model[p]
+            st_ = e.stats()
+            va = sum((len(d) + SLAB - 1) // SLAB * SLAB for d in model.values())
+            assert st_["va_bytes"] == va
+            assert st_["resident_bytes"] + st_["swapped_bytes"] + st_["unbacked_bytes"] == va
+            assert st_["n_allocs"] == len(model)
+        e.fetch_all()
+        for p, want in model.items():
+            assert np.array_equal(view(p, len(want)), want)
+        for p in list(model):
+            e.free(p)
+        st_ = e.stats()
+        assert st_["host_pool_used"] == 0 and st_["va_bytes"] == 0
+    finally:
+        e.close()
+    assert fake.fake_cuda_phys_used() == base          # every physical byte went back to the "driver"
