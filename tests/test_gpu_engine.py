@@ -219,6 +219,22 @@ def test_same_filled_slabs_are_elided_and_recreated(torch_cuda, engine, oracle):
     engine.free(p)
 
 
+@pytest.mark.parametrize("warps,stages,tile_kib", [(1, 2, 16), (1, 6, 32), (4, 3, 16), (8, 3, 8), (2, 4, 24), (1, 3, 64)])
+def test_tma_ring_geometries_are_all_exact(torch_cuda, artefacts, warps, stages, tile_kib):
+    """Every ring geometry the engine accepts (warps x stages x tile <= 200 KiB of shared memory) moves bytes
+    identically; tiles that do not divide a slab (24 KiB) exercise the ragged last tile of each descriptor."""
+    torch = torch_cuda
+    from nvshare_b200 import engine as E
+    size = 96 * MiB
+    src = torch.empty(size, dtype=torch.uint8, device="cuda")
+    dst = torch.zeros(size, dtype=torch.uint8, device="cuda")
+    with E.Engine(tma_warps=warps, tma_stages=stages, tma_tile_bytes=tile_kib << 10, prepin=0) as e:
+        e.pattern_fill(src.data_ptr(), size // 8, first_index=5, seed=warps * 100 + stages)
+        e.copy_slabs([(src.data_ptr() + o, dst.data_ptr() + o, SLAB) for o in range(0, size, SLAB)], variant="tma", grid=37)
+        assert e.pattern_verify(dst.data_ptr(), size // 8, first_index=5, seed=warps * 100 + stages) == 0
+    assert torch.equal(src, dst)
+
+
 def test_torch_can_use_engine_memory(torch_cuda, engine):
     """Memory handed out by nvs_alloc behaves like cuMemAlloc memory for CUDA
     libraries: wrap it with torch via the CUDA array interface and compute."""
