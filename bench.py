@@ -200,7 +200,13 @@ def host_memory_needed(impl, clients, footprint, hbm_avail):
     the pinned windows ahead of it (peak 163 GB for 95.7 GB swapped at full scale)."""
     if impl == "reference":
         return clients * footprint * 1.03 + (8 << 30)
-    return max(clients * footprint - hbm_avail, 0) * 1.75 + (12 << 30)
+    swapped = max(clients * footprint - hbm_avail, 0)
+    try:   # the scheduler-wide pool lives in /dev/shm; without room there every client pins its own arenas
+        vfs = os.statvfs("/dev/shm")
+        shared_ok = vfs.f_bavail * vfs.f_frsize >= hbm_avail
+    except OSError:
+        shared_ok = False
+    return (swapped * 1.75 if shared_ok else swapped * clients * 1.15) + (12 << 30)
 
 
 def pick_fraction(args, total_b):

@@ -1093,12 +1093,14 @@ static int chunk_map(nvs_engine *e, struct chunk *c, double *wait_ms)
 		/* Wait until the driver reports room for this chunk before trying again: a
 		 * failing cuMemCreate is expensive and serialises with the cuMemRelease
 		 * calls of the process that is evicting (measured: B200 r01 call 2). */
+		pthread_mutex_unlock(&e->mu); /* api_mu still serialises the entry points; let stats / pinning run */
 		for (int spin = 0; spin < 20; ++spin) {
 			size_t free_b = 0, total_b = 0;
 			usleep(1000);
 			if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= c->bytes + (64u << 20))
 				break;
 		}
+		pthread_mutex_lock(&e->mu);
 	}
 	if (wait_ms)
 		*wait_ms += now_ms() - t0;
