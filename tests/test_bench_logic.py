@@ -9,10 +9,22 @@ import types
 from nvs_testlib import ROOT
 
 
-def load_bench():
+def load_bench(shm_bytes=1 << 40):
+    """bench.py as a module, with /dev/shm reporting `shm_bytes` of free space."""
     spec = importlib.util.spec_from_file_location("bench_module", ROOT / "bench.py")
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
+    real_os = m.os
+
+    class FakeOS:
+        def __getattr__(self, name):
+            return getattr(real_os, name)
+
+        @staticmethod
+        def statvfs(path):
+            return types.SimpleNamespace(f_bavail=shm_bytes // 4096, f_frsize=4096)
+
+    m.os = FakeOS()
     return m
 
 
@@ -50,6 +62,16 @@ def test_host_memory_model():
     assert b.host_memory_needed("reference", 2, f, HBM) > 2 * f
     assert b.host_memory_needed("ours", 2, f, HBM) < 1.0 * HBM
     assert b.host_memory_needed("ours", 2, 0.4 * HBM, HBM) < 20e9          # fits: nothing to swap
+
+
+def test_small_dev_shm_means_private_pools(monkeypatch):
+    # docker's default 64 MiB /dev/shm: every client pins its own arenas, which no longer fits at full scale
+    b = load_bench(shm_bytes=64 << 20)
+    f = 0.75 * HBM
+    assert b.host_memory_needed("ours", 2, f, HBM) > 2 * (2 * f - HBM)
+    monkeypatch.setattr(b, "host_memory_budget", lambda: 213_000_000_000)
+    frac, note = b.pick_fraction(args(impl="ours"), HBM)
+    assert frac < 1.0 and note
 
 
 def test_baseline_geometry():
