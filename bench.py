@@ -282,7 +282,8 @@ def run_rank0(args, torch, world):
     args.hbm_fraction, scale_note = pick_fraction(args, total_b)
     hbm_avail = int(total_b * args.hbm_fraction)
     footprint = args.oversub * hbm_avail / args.clients
-    blocks = 4 if args.kind == "add" else 3             # live n^2 fp32 blocks
+    # live n^2 fp32 blocks: x, y, the result and -- while `z = op(x, y)` rebinds -- the previous result
+    blocks = 4
     n = int(math.floor(math.sqrt(footprint / (4 * blocks))))
     footprint = blocks * 4 * n * n
     algo_bytes_dir = max(args.clients * footprint - hbm_avail, 0.0)   # must come in (and go out) per hand-off

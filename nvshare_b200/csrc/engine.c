@@ -758,6 +758,8 @@ fail:
 	return NVS_E_HOST_OOM;
 }
 
+static uint64_t shp_reap_dead(struct shpool *sp);
+
 /* Find backing for a chunk: peers first (striped), then pinned host.  e->mu held. */
 static int backing_assign(nvs_engine *e, struct chunk *c)
 {
@@ -775,7 +777,7 @@ static int backing_assign(nvs_engine *e, struct chunk *c)
 			return 0;
 		}
 	}
-	double t0 = now_ms();
+	double t0 = now_ms(), next_reap = 0;
 	while (pool_take(e, &e->host_pool, n, &c->backing) != 0) {
 		/* pool empty: wait for the background pinning, or pin inline */
 		int rc = host_pool_grow(e);
@@ -784,7 +786,12 @@ static int backing_assign(nvs_engine *e, struct chunk *c)
 		if (!e->shp || now_ms() - t0 > e->cfg.oom_wait_ms)
 			return rc;
 		/* the shared pool is full and entirely pinned here: another client is about
-		 * to hand units back (its fetch releases them batch by batch) */
+		 * to hand units back (its fetch releases them batch by batch) -- unless it died */
+		if (now_ms() >= next_reap) {
+			next_reap = now_ms() + 500;
+			if (shp_reap_dead(e->shp))
+				continue;
+		}
 		pthread_mutex_unlock(&e->mu);
 		usleep(1000);
 		pthread_mutex_lock(&e->mu);
@@ -857,6 +864,33 @@ static void shp_close(nvs_engine *e)
 	free(sp->registered);
 	free(sp);
 	e->shp = NULL;
+}
+
+/* Take back the units of clients that died without returning them (a killed
+ * process cannot; one that exits normally does not bother).  Returns how many. */
+static uint64_t shp_reap_dead(struct shpool *sp)
+{
+	uint64_t reaped = 0;
+	int32_t last_pid = 0;
+	int last_dead = 0;
+	shp_lock(sp);
+	for (uint64_t k = 0; k < sp->hdr->capacity_slabs; ++k) {
+		int32_t pid = sp->hdr->owners[k];
+		if (pid <= 0)
+			continue;
+		if (pid != last_pid) {
+			last_pid = pid;
+			last_dead = kill(pid, 0) != 0 && errno == ESRCH;
+		}
+		if (!last_dead)
+			continue;
+		sp->hdr->bitmap[k >> 6] &= ~(1ull << (k & 63));
+		sp->hdr->owners[k] = 0;
+		sp->hdr->used_slabs--;
+		reaped++;
+	}
+	shp_unlock(sp);
+	return reaped;
 }
 
 /* Open (or create) the pool file.  Returns 0, or -1 to fall back to a private pool. */
@@ -934,17 +968,7 @@ static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
 			sp->hdr = NULL;
 			goto fail;
 		}
-		/* units of clients that died without returning them */
-		shp_lock(sp);
-		for (uint64_t k = 0; k < cap_slabs; ++k) {
-			int32_t pid = sp->hdr->owners[k];
-			if (pid > 0 && kill(pid, 0) != 0 && errno == ESRCH) {
-				sp->hdr->bitmap[k >> 6] &= ~(1ull << (k & 63));
-				sp->hdr->owners[k] = 0;
-				sp->hdr->used_slabs--;
-			}
-		}
-		shp_unlock(sp);
+		shp_reap_dead(sp);
 	}
 	sp->n_windows = (uint32_t)(cap_slabs / sp->hdr->window_slabs);
 	sp->registered = calloc(sp->n_windows ? sp->n_windows : 1, 1);
@@ -1537,7 +1561,7 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 	e->epoch++;
 
 	const uint32_t variant = e->cfg.fetch_variant;
-	int started = 0;
+	int started = 0, deferred = 0;
 	unsigned batch_no = 0;
 	struct alloc *a = e->head;
 	uint32_t ci = 0;
@@ -1567,8 +1591,8 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 			    s->n_aux + c->bytes / SLAB > s->cap_aux)
 				break;
 			double w = 0;
-			if ((rc = chunk_map(e, c, &w)) != 0)
-				goto out;
+			if ((deferred = chunk_map(e, c, &w)) != 0)
+				break; /* what this batch has mapped so far still gets its data before we give up */
 			rep.wait_ms += w;
 			rep.chunks++;
 			if (c->state == CH_SWAPPED) {
@@ -1602,7 +1626,7 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 		}
 		rep.map_ms += now_ms() - t0;
 		if (batch == 0) {
-			if (a) /* a chunk that cannot fit an empty slot: geometry bug */
+			if (a && !deferred) /* a chunk that cannot fit an empty slot: geometry bug */
 				rc = NVS_E_BAD_ARG;
 			break;
 		}
@@ -1621,17 +1645,28 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 			rep.slabs += copy_bytes / SLAB;
 		}
 		batch_no++;
+		if (deferred)
+			break;
 	}
 	(void)started;
 	for (unsigned k = 0; k < N_SLOTS; ++k)
 		if ((rc = fetch_retire(e, &e->slots[k], &rep)) != 0)
 			goto out;
+	if (deferred) {
+		/* every chunk marked resident holds its data; the rest is still swapped out */
+		rc = deferred;
+		goto out;
+	}
 	e->resident_mode = 1;
 	e->st.n_fetches++;
 	e->st.fetched_bytes_total += rep.bytes;
 out:
-	if (rc != 0)
-		e->d.StreamSynchronize(e->stream);
+	if (rc != 0 && e->d.StreamSynchronize(e->stream) == CUDA_SUCCESS) {
+		/* batches already launched have landed: their backing is no longer needed */
+		for (unsigned k = 0; k < N_SLOTS; ++k)
+			for (uint32_t i = 0; e->slots[k].busy && i < e->slots[k].n_chunks; ++i)
+				backing_release(e, e->slots[k].chunks[i]);
+	}
 	for (unsigned k = 0; k < N_SLOTS; ++k) {
 		e->slots[k].busy = 0;
 		slot_reset(&e->slots[k]);
@@ -2117,8 +2152,14 @@ void nvs_engine_destroy(nvs_engine *e)
 	if (have_ctx) {
 		if (e->stream)
 			e->d.StreamSynchronize(e->stream);
-		while (e->head)
-			nvs_free(e, e->head->va);
+		while (e->head) {
+			struct alloc *a = e->head;
+			if (nvs_free(e, a->va) != 0) { /* the driver refused: drop our record of it anyway */
+				table_remove(e, a);
+				free(a->chunks);
+				free(a);
+			}
+		}
 		if (e->shp)
 			shp_close(e);
 		for (struct arena *a = e->host_pool.arenas, *nx; a; a = nx) {

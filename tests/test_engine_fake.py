@@ -223,6 +223,44 @@ def test_fetch_times_out_when_hbm_never_frees(fake, tmp_path):
     assert "RC -6" in r.stdout, r.stdout + r.stderr         # NVS_E_TIMEOUT
 
 
+def test_timed_out_fetch_leaves_a_consistent_table(fake, tmp_path):
+    """A fetch that gives up half-way must not mark a chunk resident before its
+    data is back: after the HBM hog goes away a second fetch restores everything."""
+    ledger = tmp_path / "ledger"
+    code = textwrap.dedent(f"""
+        import ctypes as C, sys
+        sys.path.insert(0, {str(ROOT)!r})
+        fake = C.CDLL({str(FAKE_DIR / 'libcuda.so.1')!r}, mode=C.RTLD_GLOBAL)
+        fake.cuInit(0); ctx = C.c_void_p(); fake.cuDevicePrimaryCtxRetain(C.byref(ctx), 0); fake.cuCtxSetCurrent(ctx)
+        from nvshare_b200 import engine as E
+        MiB = 1 << 20
+        e = E.Engine(chunk_bytes=8 * MiB, batch_bytes=32 * MiB, burst_bytes=8 * MiB, host_arena_bytes=64 * MiB,
+                     oom_wait_ms=300, elide_constant=0, shared_pool_path=None)
+        p = e.alloc(24 * MiB); e.fetch_all()
+        e.pattern_fill(p, 24 * MiB // 8, first_index=3, seed=99)
+        e.evict(0)
+        hog = C.c_uint64()
+        assert fake.cuMemAlloc_v2(C.byref(hog), C.c_size_t(20 * MiB)) == 0
+        try:
+            e.fetch_all(); print("UNEXPECTED")
+        except E.EngineError as ex:
+            print("RC", ex.rc)
+        st = e.stats()
+        print("RESIDENT", st["resident_bytes"] // MiB, "SWAPPED", st["swapped_bytes"] // MiB)
+        assert fake.cuMemFree_v2(hog) == 0
+        e.fetch_all()
+        print("BAD", e.pattern_verify(p, 24 * MiB // 8, first_index=3, seed=99))
+        st = e.stats()
+        print("POOL_USED", st["host_pool_used"])
+    """)
+    env = dict(__import__("os").environ, FAKE_CUDA_TOTAL_MIB="40", FAKE_CUDA_LEDGER=str(ledger))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=60)
+    out = r.stdout
+    assert "RC -6" in out and "UNEXPECTED" not in out, out + r.stderr
+    assert "SWAPPED 0" not in out, out                      # something was still out when it gave up
+    assert "BAD 0" in out and "POOL_USED 0" in out, out + r.stderr
+
+
 def test_evicted_memory_is_unmapped(artefacts):
     """An access to an evicted slab must fault (fake driver: SIGSEGV), i.e. the
     physical memory really went away."""

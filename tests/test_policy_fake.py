@@ -196,3 +196,39 @@ def test_units_of_a_dead_client_are_reclaimed(artefacts, tmp_path):
     r = subprocess.run([sys.executable, "-c", code, "live"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "USED 48" in r.stdout, r.stdout + r.stderr
     assert used() == 0                                                 # reclaimed at attach, then used and returned
+
+
+def test_units_of_a_client_that_dies_later_are_reclaimed_on_exhaustion(artefacts, tmp_path):
+    """The survivor is already attached when the other client dies holding most of
+    the pool: its next eviction finds the pool full, reaps the dead owner's units
+    and carries on instead of timing out."""
+    pool = tmp_path / "pool"
+    code = textwrap.dedent(f"""
+        import ctypes as C, os, sys, time
+        sys.path.insert(0, {str(ROOT)!r})
+        fake = C.CDLL({str(FAKE_DIR / 'libcuda.so.1')!r}, mode=C.RTLD_GLOBAL)
+        fake.cuInit(0); ctx = C.c_void_p(); fake.cuDevicePrimaryCtxRetain(C.byref(ctx), 0); fake.cuCtxSetCurrent(ctx)
+        from nvshare_b200 import engine as E
+        MiB = 1 << 20
+        e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, shared_pool_path={str(pool)!r},
+                     shared_pool_bytes=64 * MiB, oom_wait_ms=5000, elide_constant=0, prepin=0)
+        role, flag = sys.argv[1], sys.argv[2]
+        p = e.alloc(48 * MiB); e.fetch_all(); e.pattern_fill(p, 48 * MiB // 8, seed=5)
+        if role == "victim":
+            e.evict(0); open(flag, "w").close(); os._exit(0)      # dies holding 48 of the 64 MiB
+        while not os.path.exists(flag):
+            time.sleep(0.01)
+        time.sleep(0.2)
+        e.evict(0)
+        e.fetch_all(); print("BAD", e.pattern_verify(p, 48 * MiB // 8, seed=5), flush=True)
+        e.free(p); e.close()
+    """)
+    flag = tmp_path / "victim_done"
+    survivor = subprocess.Popen([sys.executable, "-c", code, "survivor", str(flag)], stdout=subprocess.PIPE,
+                                stderr=subprocess.PIPE, text=True)
+    time.sleep(1.0)                                                    # the survivor has attached (or created) by now
+    v = subprocess.run([sys.executable, "-c", code, "victim", str(flag)], capture_output=True, text=True, timeout=60)
+    assert v.returncode == 0, v.stderr
+    out, err = survivor.communicate(timeout=60)
+    assert survivor.returncode == 0 and "BAD 0" in out, out + err
+    assert struct.unpack("<QIIQQ", pool.open("rb").read(32))[4] == 0
