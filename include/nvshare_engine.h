@@ -25,6 +25,11 @@
  *                    pages in; here it runs after cuda_sync_context() on
  *                    DROP_LOCK (src/client.c:308-317) and on early release
  *                    (src/client.c:472-476)
+ *   nvs_host_io      src/hook.c:856-967 cuMemcpyHtoD/DtoH hook bodies, for the
+ *                    case the reference cannot have: the device range is not on
+ *                    the GPU at all (swapped out / never materialised), so the
+ *                    copy is host memory -> pinned host backing and needs
+ *                    neither the GPU nor its lock
  *   nvs_get_stats    no counterpart (the reference has no counters)
  *   nvs_copy_slabs / nvs_pattern_fill / nvs_pattern_verify
  *                    no counterpart: raw access to the sm_100a kernels for the
@@ -32,8 +37,10 @@
  *
  * Return values: 0 on success, otherwise a CUresult value from the driver
  * (2 = CUDA_ERROR_OUT_OF_MEMORY, 3 = CUDA_ERROR_NOT_INITIALIZED, ...) or one
- * of the negative NVS_E_* codes below.  Nothing in here falls back to a CPU
- * path: if the driver or the kernel image cannot be loaded, creation fails.
+ * of the negative NVS_E_* codes below.  No device copy ever falls back to the
+ * CPU: if the driver or the kernel image cannot be loaded, creation fails, and
+ * bytes that are in HBM only move by the sm_100a kernels / copy engines.
+ * (nvs_host_io is not such a fallback: both ends of its copies are host RAM.)
  */
 #ifndef NVSHARE_ENGINE_H
 #define NVSHARE_ENGINE_H
@@ -52,6 +59,7 @@ extern "C" {
 #define NVS_E_TIMEOUT    (-6) /* HBM did not become available in time              */
 #define NVS_E_HOST_OOM   (-7) /* backing tier exhausted                            */
 #define NVS_E_SHUTDOWN   (-8) /* the CUDA context is being destroyed (process exit) */
+#define NVS_E_NOT_SWAPPED (-9) /* nvs_host_io: the range is not (entirely) off the GPU */
 
 #define NVS_MAX_PEERS 7
 
@@ -129,6 +137,7 @@ typedef struct nvs_stats {
 	uint64_t n_evicts, n_fetches;
 	uint64_t evicted_bytes_total, fetched_bytes_total;
 	uint64_t kernel_launches_total; /* nvs_slab_copy_* launches since creation       */
+	uint64_t host_io_bytes_total;   /* nvs_host_io: bytes served from / into the backing copy */
 } nvs_stats;
 
 /* Fill *cfg with defaults, then apply NVSHARE_* environment overrides
@@ -153,6 +162,22 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep);
 /* Evict at least `min_bytes` (0 = everything) of resident chunks, least
  * recently fetched first, and release their physical HBM. */
 int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep);
+
+/*
+ * Serve a host<->device copy WITHOUT the GPU, from / into the pinned-host backing
+ * copy of memory that is currently swapped out (or was never materialised).  The
+ * reference has no counterpart: there every cuMemcpy* waits for the GPU lock
+ * (src/hook.c:843-971) even when the data it wants is sitting in host RAM, and a
+ * client that is loading its inputs keeps the GPU from the others meanwhile.
+ *   to_device != 0: host -> [dptr, dptr+bytes)   (cuMemcpyHtoD*)
+ *   to_device == 0: [dptr, dptr+bytes) -> host   (cuMemcpyDtoH*)
+ * Returns 0 when the whole range was served.  NVS_E_NOT_OURS: the range is not
+ * inside one engine allocation.  NVS_E_NOT_SWAPPED: some of it is resident in
+ * HBM, backed by a peer GPU, or (reads) was never written: use the GPU path.
+ * A failed call may have written part of a host->device range; the caller then
+ * repeats the whole copy on the GPU path, which makes that harmless.
+ */
+int nvs_host_io(nvs_engine *e, uint64_t dptr, void *host, uint64_t bytes, int to_device);
 
 int nvs_get_stats(nvs_engine *e, nvs_stats *out);
 

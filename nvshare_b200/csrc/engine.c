@@ -381,6 +381,7 @@ const char *nvs_strerror(int rc)
 	case NVS_E_TIMEOUT: return "timed out waiting for HBM to be released";
 	case NVS_E_HOST_OOM: return "backing tier exhausted";
 	case NVS_E_SHUTDOWN: return "the CUDA context is being torn down (process exit)";
+	case NVS_E_NOT_SWAPPED: return "the range is (partly) resident on a GPU: use the device path";
 	case CUDA_ERROR_OUT_OF_MEMORY: return "CUDA_ERROR_OUT_OF_MEMORY";
 	case CUDA_ERROR_NOT_INITIALIZED: return "CUDA_ERROR_NOT_INITIALIZED";
 	default: return rc > 0 ? "CUDA driver error" : "unknown engine error";
@@ -1851,6 +1852,131 @@ out:
 	pthread_mutex_unlock(&e->mu);
 	pthread_mutex_unlock(&e->api_mu);
 	ctx_leave(e);
+	return rc;
+}
+
+/* ------------------------------------------- lock-free host<->backing ---- */
+
+static struct alloc *table_find_range(nvs_engine *e, uint64_t addr, uint64_t bytes)
+{
+	for (struct alloc *a = e->head; a; a = a->next)
+		if (addr >= a->va && addr - a->va < a->va_bytes)
+			return bytes <= a->va_bytes - (addr - a->va) ? a : NULL;
+	return NULL;
+}
+
+/* host address of a host-tier chunk's backing copy; e->mu held */
+static uint8_t *backing_host_ptr(nvs_engine *e, const struct chunk *c)
+{
+	for (struct arena *ar = e->host_pool.arenas; ar; ar = ar->next)
+		if (c->backing >= ar->dev_base && c->backing < ar->dev_base + ar->bytes)
+			return (uint8_t *)ar->host_base + (c->backing - ar->dev_base);
+	return NULL;
+}
+
+static void fill_words(uint8_t *dst, uint64_t slab_off, uint64_t n, uint64_t value)
+{
+	/* the slab is `value` repeated from its first byte on: byte k is byte (k & 7) of value */
+	const uint8_t *v = (const uint8_t *)&value;
+	uint64_t k = 0;
+	for (; k < n && ((slab_off + k) & 7); ++k)
+		dst[k] = v[(slab_off + k) & 7];
+	for (; k + 8 <= n; k += 8)
+		memcpy(dst + k, &value, 8);
+	for (; k < n; ++k)
+		dst[k] = v[(slab_off + k) & 7];
+}
+
+int nvs_host_io(nvs_engine *e, uint64_t dptr, void *host, uint64_t bytes, int to_device)
+{
+	if (!e || !host || bytes == 0)
+		return NVS_E_BAD_ARG;
+	int rc = 0;
+	/* api_mu keeps evict / fetch / free away for the whole call; mu is only taken
+	 * where the pools are consulted, never across a memcpy */
+	pthread_mutex_lock(&e->api_mu);
+	pthread_mutex_lock(&e->mu);
+	struct alloc *a = table_find_range(e, dptr, bytes);
+	if (!a || a->passthrough) {
+		rc = NVS_E_NOT_OURS;
+		goto out;
+	}
+	const uint64_t off0 = dptr - a->va;
+	const uint32_t first = (uint32_t)(off0 / e->cfg.chunk_bytes);
+	const uint32_t last = (uint32_t)((off0 + bytes - 1) / e->cfg.chunk_bytes);
+	for (uint32_t ci = first; ci <= last; ++ci) {
+		const struct chunk *c = &a->chunks[ci];
+		if (c->state == CH_RESIDENT || (c->backing && c->tier != TIER_HOST) ||
+		    (c->state == CH_UNBACKED && (!to_device || e->cfg.n_peers > 0)) ||
+		    (!c->backing && e->cfg.n_peers > 0)) {
+			rc = NVS_E_NOT_SWAPPED;
+			goto out;
+		}
+	}
+	uint8_t *h = host;
+	for (uint32_t ci = first; ci <= last; ++ci) {
+		struct chunk *c = &a->chunks[ci];
+		const uint64_t c_off = (uint64_t)ci * e->cfg.chunk_bytes;
+		const uint64_t lo = off0 > c_off ? off0 - c_off : 0;
+		const uint64_t hi = off0 + bytes - c_off < c->bytes ? off0 + bytes - c_off : c->bytes;
+		if (to_device && !c->backing) {
+			/* never materialised, or every slab same-filled: it needs a backing copy now */
+			int need_ctx = ctx_enter(e) == 0; /* pinning a new arena needs the context */
+			rc = backing_assign(e, c);
+			if (need_ctx)
+				ctx_leave(e);
+			if (rc != 0)
+				goto out;
+			if (c->state == CH_UNBACKED) {
+				/* Untouched slabs become "same-filled with 0": the pool's pages may hold
+				 * another client's old data, which must neither be copied nor leak. */
+				const uint32_t n_slabs = (uint32_t)(c->bytes / SLAB);
+				if (!c->cvals && !(c->cvals = calloc(MAX_CHUNK_SLABS, sizeof(uint64_t)))) {
+					backing_release(e, c);
+					rc = NVS_E_HOST_OOM;
+					goto out;
+				}
+				memset(c->cvals, 0, MAX_CHUNK_SLABS * sizeof(uint64_t));
+				for (uint32_t k = 0; k < n_slabs; ++k)
+					c->cmask[k >> 6] |= 1ull << (k & 63);
+				c->n_const = n_slabs;
+				state_account(e, c, CH_SWAPPED);
+			}
+		}
+		uint8_t *b = c->backing ? backing_host_ptr(e, c) : NULL;
+		if (c->backing && !b) {
+			rc = NVS_E_NOT_SWAPPED;
+			goto out;
+		}
+		pthread_mutex_unlock(&e->mu);
+		for (uint64_t at = lo; at < hi;) {
+			const uint32_t si = (uint32_t)(at / SLAB);
+			const uint64_t s_end = ((uint64_t)si + 1) * SLAB < hi ? ((uint64_t)si + 1) * SLAB : hi;
+			const uint64_t n = s_end - at;
+			if (slab_is_const(c, si)) {
+				if (to_device) {
+					/* the slab stops being same-filled: write it out in full first */
+					fill_words(b + (uint64_t)si * SLAB, 0, SLAB, c->cvals[si]);
+					c->cmask[si >> 6] &= ~(1ull << (si & 63));
+					c->n_const--;
+					memcpy(b + at, h, n);
+				} else {
+					fill_words(h, at - (uint64_t)si * SLAB, n, c->cvals[si]);
+				}
+			} else if (to_device) {
+				memcpy(b + at, h, n);
+			} else {
+				memcpy(h, b + at, n);
+			}
+			h += n;
+			at = s_end;
+		}
+		pthread_mutex_lock(&e->mu);
+	}
+	e->st.host_io_bytes_total += bytes;
+out:
+	pthread_mutex_unlock(&e->mu);
+	pthread_mutex_unlock(&e->api_mu);
 	return rc;
 }
 

@@ -163,7 +163,14 @@ static void *gate_real[G_COUNT][2];
 
 static void after_launch(void);
 
-#define GATED(name, is_launch, params, args)                                         \
+static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_device);
+#define NO_BYPASS 0
+
+/* `bypass`: an expression that is non-zero when the call has been served without
+ * the GPU (nvs_host_io) and must therefore neither wait for the lock nor reach
+ * the driver. */
+#define GATED(name, is_launch, params, args) GATED_(name, is_launch, params, args, NO_BYPASS)
+#define GATED_(name, is_launch, params, args, bypass)                                \
 	static CUresult gate_##name##_impl(int flavour_, NVS_UNPAREN params)                \
 	{                                                                            \
 		typedef CUresult (*fn_t) params;                                     \
@@ -172,6 +179,8 @@ static void after_launch(void);
 			real = (fn_t)gate_real[G_##name][0];                         \
 		if (!real)                                                           \
 			return CUDA_ERROR_NOT_INITIALIZED;                           \
+		if (bypass)                                                          \
+			return CUDA_SUCCESS;                                         \
 		continue_with_lock();                                                \
 		CUresult r = real args;                                              \
 		warn_if_error(r, #name);                                             \
@@ -199,10 +208,13 @@ GATED(cuLaunchCooperativeKernel, 1,
 GATED(cuGraphLaunch, 1, (CUgraphExec g, CUstream s), (g, s))
 GATED(cuMemcpy, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n), (dst, src, n))
 GATED(cuMemcpyAsync, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
-GATED(cuMemcpyHtoD, 0, (CUdeviceptr dst, const void *src, size_t n), (dst, src, n))
-GATED(cuMemcpyHtoDAsync, 0, (CUdeviceptr dst, const void *src, size_t n, CUstream s), (dst, src, n, s))
-GATED(cuMemcpyDtoH, 0, (void *dst, CUdeviceptr src, size_t n), (dst, src, n))
-GATED(cuMemcpyDtoHAsync, 0, (void *dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
+/* host<->device copies whose device side is swapped out are host<->host copies: no GPU, no lock */
+GATED_(cuMemcpyHtoD, 0, (CUdeviceptr dst, const void *src, size_t n), (dst, src, n), host_io_bypass(dst, src, n, 1))
+GATED_(cuMemcpyHtoDAsync, 0, (CUdeviceptr dst, const void *src, size_t n, CUstream s), (dst, src, n, s),
+       host_io_bypass(dst, src, n, 1))
+GATED_(cuMemcpyDtoH, 0, (void *dst, CUdeviceptr src, size_t n), (dst, src, n), host_io_bypass(src, dst, n, 0))
+GATED_(cuMemcpyDtoHAsync, 0, (void *dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s),
+       host_io_bypass(src, dst, n, 0))
 GATED(cuMemcpyDtoD, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n), (dst, src, n))
 GATED(cuMemcpyDtoDAsync, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
 GATED(cuMemcpyPeer, 0, (CUdeviceptr dst, CUcontext dc, CUdeviceptr src, CUcontext sc, size_t n), (dst, dc, src, sc, n))
@@ -534,6 +546,35 @@ static nvs_engine *engine_get(void)
 	nvs_engine *e = engine;
 	pthread_mutex_unlock(&engine_mu);
 	return e;
+}
+
+/*
+ * SURVEY 8f rank 3.  A client that does not hold the GPU lock has nothing on the
+ * GPU that could race with this: its context was drained before its memory was
+ * swapped out, and everything it submits is parked at the gate.  So a copy
+ * between host memory and a swapped-out (or never materialised) device range is
+ * served by the engine from / into the pinned-host backing copy, and a client
+ * loading its inputs no longer takes the GPU away from the one computing.
+ * The engine re-checks the state of the range under its own lock: if LOCK_OK got
+ * there first the range is resident and the call goes down the gated path.
+ * NVSHARE_LOCKFREE_COPY=0 turns it off.
+ */
+static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_device)
+{
+	static int enabled = -1;
+	if (enabled < 0) {
+		const char *v = getenv("NVSHARE_LOCKFREE_COPY");
+		enabled = !(v && *v && atoi(v) == 0);
+	}
+	if (!enabled || n == 0 || !host || __atomic_load_n(&holds_lock, __ATOMIC_RELAXED))
+		return 0;
+	nvs_engine *e = __atomic_load_n(&engine, __ATOMIC_ACQUIRE);
+	if (!e)
+		return 0;
+	int rc = nvs_host_io(e, (uint64_t)dev, (void *)(uintptr_t)host, (uint64_t)n, to_device);
+	if (rc == 0)
+		nvs_debug("%s of %zu bytes served from the backing copy, no lock needed", to_device ? "HtoD" : "DtoH", n);
+	return rc == 0;
 }
 
 /* ------------------------------------------------- launch window -------- */

@@ -55,7 +55,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_allocs", "requested_bytes", "va_bytes", "resident_bytes", "swapped_bytes", "unbacked_bytes",
         "passthrough_bytes", "host_pool_bytes", "host_pool_used", "peer_pool_bytes", "peer_pool_used",
-        "n_evicts", "n_fetches", "evicted_bytes_total", "fetched_bytes_total", "kernel_launches_total")]
+        "n_evicts", "n_fetches", "evicted_bytes_total", "fetched_bytes_total", "kernel_launches_total",
+        "host_io_bytes_total")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -95,6 +96,7 @@ def load():
     lib.nvs_fetch_all.argtypes = [C.c_void_p, P(XferReport)]
     lib.nvs_evict.argtypes = [C.c_void_p, C.c_uint64, P(XferReport)]
     lib.nvs_get_stats.argtypes = [C.c_void_p, P(Stats)]
+    lib.nvs_host_io.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
     lib.nvs_copy_slabs.argtypes = [C.c_void_p, P(CopyDesc), C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_float)]
     lib.nvs_pattern_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
     lib.nvs_pattern_verify.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, P(C.c_uint64)]
@@ -173,6 +175,14 @@ class Engine:
         st = Stats()
         _check(load().nvs_get_stats(self._h, C.byref(st)), "nvs_get_stats")
         return st.as_dict()
+
+    def host_io(self, dptr: int, host_ptr: int, nbytes: int, to_device: bool) -> int:
+        """nvs_host_io: 0 = served from / into the backing copy, NVS_E_NOT_OURS / NVS_E_NOT_SWAPPED =
+        the caller must use the device path; anything else raises."""
+        rc = load().nvs_host_io(self._h, dptr, host_ptr, nbytes, 1 if to_device else 0)
+        if rc not in (0, -2, -9):
+            _check(rc, "nvs_host_io")
+        return rc
 
     def copy_slabs(self, descs, variant="tma", grid=0) -> float:
         """descs: iterable of (src, dst, nbytes). Returns CUDA-event milliseconds."""

@@ -158,3 +158,51 @@ def test_client_exits_when_scheduler_is_absent(artefacts, sock_dir, tmp_path):
                        timeout=30)
     assert r.returncode == 1                                 # reference: exit(1) in the host app (client.c:250)
     assert "[NVSHARE][FATAL]" in r.stderr
+
+
+def _loader_beside_a_holder(sock_dir, tmp_path, lockfree):
+    """Client A computes and holds the lock for a long quantum; client B only
+    allocates, uploads and reads back (tests/apps/load_app.c)."""
+    import time
+    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
+    try:
+        d.ctl("-T", "30")
+        def env_for():
+            env = fake_env(total_mib=200, ledger=tmp_path / "ledger",
+                           extra={"NVSHARE_HOST_ARENA_MIB": 64, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_BATCH_MIB": 32,
+                                  "NVSHARE_DEBUG": 1, "NVSHARE_LOCKFREE_COPY": int(lockfree)})
+            env["LD_PRELOAD"] = preload("ours")
+            env["NVSHARE_SOCK_DIR"] = str(sock_dir)
+            return env
+        a = subprocess.Popen([str(ORACLE / "driver_app"), "40", "4.0", "1", "3"], env=env_for(),
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        time.sleep(1.0)                                   # A holds the lock and 120 of the 200 MiB by now
+        t0 = time.time()
+        b = subprocess.run([str(ORACLE / "load_app"), "40", "3", "9"], env=env_for(), capture_output=True, text=True,
+                           timeout=60)
+        took = time.time() - t0
+        out_a, err_a = a.communicate(timeout=60)
+        assert a.returncode == 0 and "RESULT PASS" in out_a, out_a + err_a[-1500:]
+        return b, took
+    finally:
+        d.stop()
+
+
+def test_loading_client_does_not_need_the_lock(artefacts, sock_dir, tmp_path):
+    """uploads to (and reads from) memory that is not on the GPU
+    are served from the pinned-host backing copy; the loading client never asks
+    for the lock, so it neither waits for the holder nor takes the GPU from it."""
+    b, took = _loader_beside_a_holder(sock_dir, tmp_path, lockfree=True)
+    assert b.returncode == 0 and re.search(r"RESULT PASS seconds=\S+ mismatches=0", b.stdout), b.stdout + b.stderr[-1500:]
+    assert "Sent REQ_LOCK" not in b.stderr                 # not once
+    assert b.stderr.count("served from the backing copy") >= 12
+    assert took < 2.5                                      # A still had >2.5 s of compute and a 30 s quantum left
+
+
+def test_loading_client_waits_when_the_bypass_is_off(artefacts, sock_dir, tmp_path):
+    """The reference's behaviour (src/hook.c:843-971), kept behind NVSHARE_LOCKFREE_COPY=0:
+    the first copy waits for the lock, i.e. until A goes idle and releases it."""
+    b, took = _loader_beside_a_holder(sock_dir, tmp_path, lockfree=False)
+    assert b.returncode == 0 and "RESULT PASS" in b.stdout, b.stdout + b.stderr[-1500:]
+    assert "Sent REQ_LOCK" in b.stderr and "served from the backing copy" not in b.stderr
+    assert took > 2.5

@@ -361,3 +361,76 @@ def test_stats_file(fake, tmp_path):
     recs = [json.loads(l) for l in path.read_text().splitlines()]
     assert [r["op"] for r in recs] == ["fetch", "evict", "fetch"]
     assert recs[1]["bytes"] == 16 * MiB and recs[1]["slabs"] == 8 and recs[1]["launches"] >= 1
+
+
+# ---- nvs_host_io: copies between host memory and a range that is not on the GPU
+
+def test_host_io_return_codes(fake):
+    from nvshare_b200 import engine as E
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, oom_wait_ms=300, prepin=0)
+    try:
+        buf = np.arange(4096, dtype=np.uint8)
+        p = e.alloc(20 * MiB)
+        assert e.host_io(p, buf.ctypes.data, 4096, False) == -9          # never written: nothing to read back
+        e.fetch_all()
+        assert e.host_io(p, buf.ctypes.data, 4096, True) == -9           # resident: the device path must be used
+        assert e.host_io(p + 20 * MiB + 2 * MiB - 8, buf.ctypes.data, 16, True) == -2   # runs off the allocation's end
+        assert e.host_io(0x1000, buf.ctypes.data, 16, True) == -2        # not ours
+        small = e.alloc(4096)                                            # passthrough allocation: plain device memory
+        assert e.host_io(small, buf.ctypes.data, 16, True) == -2
+        e.evict(0)
+        assert e.host_io(p, buf.ctypes.data, 4096, True) == 0
+        assert e.stats()["host_io_bytes_total"] == 4096
+    finally:
+        e.close()
+
+
+def test_host_io_load_before_first_residency_reads_zero_elsewhere(fake):
+    """Uploading into a fresh allocation without the GPU: the bytes written arrive,
+    everything else in the chunk reads 0 (never another client's stale pool pages)."""
+    from nvshare_b200 import engine as E
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, oom_wait_ms=300, prepin=0)
+    try:
+        # dirty the pool first: whatever backs the next allocation has non-zero bytes in it
+        q = e.alloc(24 * MiB); e.fetch_all(); view(q, 24 * MiB)[:] = 0xAB; e.evict(0); e.fetch_all(); e.free(q)
+        e.evict(0)
+        p = e.alloc(24 * MiB)
+        src = np.random.default_rng(1).integers(1, 256, 9 * MiB + 13, dtype=np.uint8)
+        lo = 3 * MiB + 5                                                  # spans chunks 0 and 1, ragged at both ends
+        assert e.host_io(p + lo, src.ctypes.data, len(src), True) == 0
+        st = e.stats()
+        assert st["swapped_bytes"] == 16 * MiB and st["unbacked_bytes"] == 8 * MiB and st["resident_bytes"] == 0
+        back = np.empty(len(src) + 64, dtype=np.uint8)
+        assert e.host_io(p + lo - 32, back.ctypes.data, len(back), False) == 0     # readable again without the GPU
+        assert not back[:32].any() and np.array_equal(back[32:32 + len(src)], src) and not back[32 + len(src):].any()
+        rep = e.fetch_all()
+        got = view(p, 24 * MiB)
+        assert np.array_equal(got[lo:lo + len(src)], src)
+        assert not got[:lo].any() and not got[lo + len(src):].any()
+        assert rep["bytes"] == 12 * MiB                                   # only the six slabs that were touched moved
+    finally:
+        e.close()
+
+
+def test_host_io_on_same_filled_slabs(fake):
+    from nvshare_b200 import engine as E
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, oom_wait_ms=300, prepin=0, elide_constant=1)
+    try:
+        p = e.alloc(16 * MiB); e.fetch_all()
+        words = np.ctypeslib.as_array((C.c_uint64 * (16 * MiB // 8)).from_address(p))
+        words[:] = 0x0102030405060708                                     # every slab same-filled ...
+        view(p, 16 * MiB)[5 * MiB] ^= 0xFF                                # ... but slab 2
+        rep = e.evict(0)
+        assert rep["bytes"] == 2 * MiB and rep["elided_bytes"] == 14 * MiB
+        expect = np.frombuffer(np.full(16 * MiB // 8, 0x0102030405060708, dtype=np.uint64).tobytes(), dtype=np.uint8).copy()
+        expect[5 * MiB] ^= 0xFF
+        back = np.empty(6 * MiB + 3, dtype=np.uint8)
+        assert e.host_io(p + 1 * MiB + 1, back.ctypes.data, len(back), False) == 0   # unaligned read across const + real slabs
+        assert np.array_equal(back, expect[1 * MiB + 1:1 * MiB + 1 + len(back)])
+        patch = np.arange(100, dtype=np.uint8)
+        assert e.host_io(p + 9 * MiB + 3, patch.ctypes.data, 100, True) == 0         # into a same-filled slab of chunk 1
+        expect[9 * MiB + 3:9 * MiB + 103] = patch
+        e.fetch_all()
+        assert np.array_equal(view(p, 16 * MiB), expect)
+    finally:
+        e.close()

@@ -1,6 +1,6 @@
 """Property test of the swap engine's host logic (fake driver): arbitrary
-interleavings of alloc / write / evict(partial or all) / fetch / free never lose
-or mix up a byte, and the accounting identities always hold.  The model is a
+interleavings of alloc / write / evict(partial or all) / fetch / free / lock-free
+host copies (nvs_host_io) never lose or mix up a byte, and the accounting identities always hold.  The model is a
 plain dict of numpy arrays; contents are checked by direct reads (the fake
 driver's "HBM" is host-addressable while mapped)."""
 from __future__ import annotations
@@ -40,6 +40,9 @@ ops = st.lists(
         st.tuples(st.just("evict"), st.integers(0, 12), st.just(0)),            # 0 = all, else MiB
         st.tuples(st.just("fetch"), st.just(0), st.just(0)),
         st.tuples(st.just("free"), st.integers(0, 7), st.just(0)),
+        st.tuples(st.just("cold"), st.integers(1, 9), st.integers(0, 255)),     # allocate + load without the GPU
+        st.tuples(st.just("hio_w"), st.integers(0, 7), st.integers(0, 10**6)),  # host -> swapped-out range
+        st.tuples(st.just("hio_r"), st.integers(0, 7), st.integers(0, 10**6)),  # swapped-out range -> host
     ),
     min_size=4, max_size=28)
 
@@ -88,6 +91,38 @@ def test_any_interleaving_preserves_contents(fake, script, elide, chunk_slabs):
                 resident = False
             elif op == "fetch":
                 e.fetch_all(); resident = True
+            elif op == "cold":
+                size = a * SLAB - (77 if a > 2 else 0)
+                p = e.alloc(size)
+                data = np.random.default_rng(b).integers(0, 256, size, dtype=np.uint8)
+                lo = (b * 4099) % size                                  # load only [lo, size): the rest must read 0
+                rc = e.host_io(p + lo, data[lo:].ctypes.data, size - lo, True)
+                assert rc in (0, -9) and (rc == -9 or not resident)   # after a partial eviction the engine still maps new memory
+                if rc != 0:
+                    e.fetch_all()
+                    view(p, size)[lo:] = data[lo:]
+                    view(p, size)[:lo] = 0
+                data[:lo] = 0
+                model[p] = data
+                order.append(p)
+            elif op in ("hio_w", "hio_r") and order:
+                p = order[a % len(order)]
+                n = len(model[p])
+                lo = (b * 7919) % n
+                ln = 1 + (b * 104729) % min(n - lo, 5 * MiB)
+                if op == "hio_w":
+                    src = np.random.default_rng(b).integers(0, 256, ln, dtype=np.uint8)
+                    rc = e.host_io(p + lo, src.ctypes.data, ln, True)
+                    if rc == 0:
+                        model[p][lo:lo + ln] = src
+                else:
+                    dst = np.full(ln, 0xEE, dtype=np.uint8)
+                    rc = e.host_io(p + lo, dst.ctypes.data, ln, False)
+                    if rc == 0:
+                        assert np.array_equal(dst, model[p][lo:lo + ln])
+                assert rc in (0, -9)
+                if resident:
+                    assert rc == -9                                     # never served while the data is in HBM
             elif op == "free" and order:
                 p = order.pop(a % len(order))
                 e.free(p)

@@ -255,3 +255,44 @@ def test_torch_can_use_engine_memory(torch_cuda, engine):
     assert float((t + t).sum().item()) == 2.0 * n                                     # the add test's exact value
     del t
     engine.free(p)
+
+
+def test_host_io_upload_and_readback_without_the_gpu(torch_cuda, engine, oracle):
+    """SURVEY 8f rank 3 on the real driver: data uploaded with nvs_host_io into an
+    allocation that has never been on the GPU arrives in HBM with the next fetch
+    (checked by the device-side verifier), bytes nobody wrote read 0, and after
+    an eviction the range can be read back from the backing copy, bit-exact."""
+    torch = torch_cuda
+    size = 1 * GiB + 6 * MiB
+    words = size // 8
+    lo_words = (300 * MiB + 8) // 8                     # upload [lo, size): slabs before it stay untouched
+    host = np.empty(words, dtype=np.uint64)
+    oracle.oracle_pattern_fill(host.ctypes.data, words, 11, 77)
+    p = engine.alloc(size + 64 * MiB)                   # and a tail nobody writes either
+    free0, _ = torch.cuda.mem_get_info()
+    assert engine.host_io(p + lo_words * 8, host.ctypes.data + lo_words * 8, (words - lo_words) * 8, True) == 0
+    free1, _ = torch.cuda.mem_get_info()
+    assert abs(free1 - free0) < 64 * MiB                # no HBM was mapped for it
+    st = engine.stats()
+    assert st["resident_bytes"] == 0 and st["host_io_bytes_total"] == (words - lo_words) * 8
+    rep = engine.fetch_all()
+    assert rep["bytes"] <= size - 300 * MiB + 2 * MiB   # untouched slabs were not moved ...
+    assert engine.pattern_verify(p + lo_words * 8, words - lo_words, first_index=11 + lo_words, seed=77) == 0
+
+    class Raw:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+    # chunk 0 was never touched at all and is plain fresh memory (undefined, like cuMemAlloc's);
+    # the untouched slabs of chunks that DID get a backing copy must not show stale pool pages
+    head = torch.as_tensor(Raw(p + 256 * MiB, 44 * MiB // 8), device="cuda")
+    tail = torch.as_tensor(Raw(p + size, 64 * MiB // 8), device="cuda")
+    assert int(head.abs().max().item()) == 0 and int(tail.abs().max().item()) == 0     # ... and read 0
+    del head, tail
+    engine.evict(0)
+    back = np.full(words - lo_words, 0xEE, dtype=np.uint64)
+    assert engine.host_io(p + lo_words * 8, back.ctypes.data, back.nbytes, False) == 0
+    assert oracle.oracle_pattern_mismatches(back.ctypes.data, len(back), 11 + lo_words, 77) == 0
+    engine.fetch_all()
+    assert engine.host_io(p, back.ctypes.data, 4096, False) == -9                      # resident: device path only
+    engine.free(p)

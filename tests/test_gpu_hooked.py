@@ -103,3 +103,35 @@ def test_uvm_mode_add(artefacts, tmp_path):
     log, res = run_pair(tmp_path, "add", 8000, 4, "ones", tq=2, extra_env={"NVSHARE_ENGINE": "uvm"})
     for rc, out, err in res:
         assert rc == 0 and out.startswith("PASS"), out + err[-3000:]
+
+
+def test_loading_client_does_not_take_the_gpu(artefacts, tmp_path):
+    """SURVEY 8f rank 3 with the real CUDA runtime: while client A computes inside
+    a 30 s quantum, client B (tests/apps/torch_loader.py) allocates, uploads 2 x
+    256 MiB and reads them back WITHOUT asking for the lock -- the copies are
+    served from the pinned-host backing copy -- and only its first kernel waits."""
+    sock_dir = tmp_path / "nvs"
+    sock_dir.mkdir()
+    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
+    try:
+        d.ctl("-T", "30")
+        env = dict(os.environ, LD_PRELOAD=preload("ours"), NVSHARE_SOCK_DIR=str(sock_dir), PYTHONPATH=str(ROOT),
+                   NVSHARE_DEBUG="1")
+        a = subprocess.Popen(client_cmd("add", 8000, 14, "ones", tmp_path / "a.jsonl", "a"), env=env, cwd=ROOT,
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        deadline = time.time() + 120
+        while "Sent LOCK_OK" not in d.read_log():          # A holds the lock
+            assert time.time() < deadline and a.poll() is None
+            time.sleep(0.2)
+        b = subprocess.run([sys.executable, str(ROOT / "tests" / "apps" / "torch_loader.py")], env=env, cwd=ROOT,
+                           capture_output=True, text=True, timeout=600)
+        out_a, err_a = a.communicate(timeout=600)
+    finally:
+        d.stop()
+    assert a.returncode == 0 and out_a.startswith("PASS"), out_a + err_a[-3000:]
+    assert b.returncode == 0 and "RESULT PASS" in b.stdout, b.stdout + b.stderr[-3000:]
+    load = [l for l in b.stdout.splitlines() if l.startswith("LOAD_DONE")][0].split()
+    assert load[2] == "True" and float(load[1]) < 6.0, b.stdout                 # far inside A's 14 s of work
+    err = b.stderr
+    assert err.count("served from the backing copy") >= 4
+    assert err.index("served from the backing copy") < err.index("Sent REQ_LOCK")   # the lock was asked for afterwards
