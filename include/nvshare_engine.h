@@ -25,7 +25,7 @@
  *                    pages in; here it runs after cuda_sync_context() on
  *                    DROP_LOCK (src/client.c:308-317) and on early release
  *                    (src/client.c:472-476)
- *   nvs_host_io      src/hook.c:856-967 cuMemcpyHtoD/DtoH hook bodies, for the
+ *   nvs_host_io      src/hook.c:878-938 cuMemcpyDtoH/HtoD{,Async} hook bodies, for the
  *                    case the reference cannot have: the device range is not on
  *                    the GPU at all (swapped out / never materialised), so the
  *                    copy is host memory -> pinned host backing and needs
