@@ -117,7 +117,7 @@ def test_loading_client_does_not_take_the_gpu(artefacts, tmp_path):
         d.ctl("-T", "30")
         env = dict(os.environ, LD_PRELOAD=preload("ours"), NVSHARE_SOCK_DIR=str(sock_dir), PYTHONPATH=str(ROOT),
                    NVSHARE_DEBUG="1")
-        a = subprocess.Popen(client_cmd("add", 8000, 14, "ones", tmp_path / "a.jsonl", "a"), env=env, cwd=ROOT,
+        a = subprocess.Popen(client_cmd("add", 8000, 25, "ones", tmp_path / "a.jsonl", "a"), env=env, cwd=ROOT,
                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         deadline = time.time() + 120
         while "Sent LOCK_OK" not in d.read_log():          # A holds the lock
@@ -131,7 +131,7 @@ def test_loading_client_does_not_take_the_gpu(artefacts, tmp_path):
     assert a.returncode == 0 and out_a.startswith("PASS"), out_a + err_a[-3000:]
     assert b.returncode == 0 and "RESULT PASS" in b.stdout, b.stdout + b.stderr[-3000:]
     load = [l for l in b.stdout.splitlines() if l.startswith("LOAD_DONE")][0].split()
-    assert load[2] == "True" and float(load[1]) < 6.0, b.stdout                 # far inside A's 14 s of work
+    assert load[2] == "True" and float(load[1]) < 6.0, b.stdout                 # far inside A's 25 s of work
     err = b.stderr
     assert err.count("served from the backing copy") >= 4
     assert err.index("served from the backing copy") < err.index("Sent REQ_LOCK")   # the lock was asked for afterwards
