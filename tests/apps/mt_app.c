@@ -5,7 +5,7 @@
  * that already passed it (close_gate_and_drain in client.c), otherwise a thread
  * touches slabs that are being unmapped.
  *
- * usage: mt_app <MiB per buffer> <seconds> <seed> <threads>
+ * usage: mt_app <MiB per buffer> <seconds> <seed> <threads> [io]
  */
 #include <pthread.h>
 #include <stdint.h>
@@ -33,6 +33,7 @@ static CUcontext ctx;
 static size_t bytes;
 static double seconds;
 static uint64_t seed;
+static int io_mode; /* also round-trip a third buffer through DtoH / HtoD every iteration */
 static unsigned long total_bad, total_iters;
 static pthread_mutex_t sum_mu = PTHREAD_MUTEX_INITIALIZER;
 
@@ -58,10 +59,36 @@ static void *worker(void *arg)
 		h[i] = mix(i, seed * 1000 + (uint64_t)id);
 	if (cuMemcpyHtoD_v2(a, h, bytes))
 		exit(2);
+	/* io mode: a small third buffer whose contents change every iteration; whether a copy
+	 * is served by the "GPU" or from the backing copy depends on where the lock is right now */
+	const size_t io_bytes = 3u << 20, io_words = io_bytes / 8, io_off = 4096 + 8 * (size_t)id;
+	CUdeviceptr c = 0;
+	uint64_t *io = NULL, *io_back = NULL;
+	unsigned long io_bad = 0;
+	if (io_mode) {
+		if (cuMemAlloc_v2(&c, io_bytes + 2 * io_off))
+			exit(2);
+		io = malloc(io_bytes);
+		io_back = malloc(io_bytes);
+		for (size_t i = 0; i < io_words; ++i)
+			io[i] = mix(i, 77 + (uint64_t)id);
+		if (cuMemcpyHtoD_v2(c + io_off, io, io_bytes))
+			exit(2);
+	}
 	struct timespec t0, t;
 	clock_gettime(CLOCK_MONOTONIC, &t0);
 	unsigned long iters = 0;
 	for (;;) {
+		if (io_mode) {
+			if (cuMemcpyDtoH_v2(io_back, c + io_off, io_bytes))
+				exit(2);
+			for (size_t i = 0; i < io_words; ++i)
+				io_bad += io_back[i] != io[i];
+			for (size_t i = 0; i < io_words; i += 61)
+				io[i] = mix(i, iters * 131 + (uint64_t)id);
+			if (cuMemcpyHtoD_v2(c + io_off, io, io_bytes))
+				exit(2);
+		}
 		if (cuMemcpyDtoD_v2(iters & 1 ? a : b, iters & 1 ? b : a, bytes))
 			exit(2);
 		if (cuLaunchKernel((void *)0x1234, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL))
@@ -79,8 +106,10 @@ static void *worker(void *arg)
 		bad += back[i] != h[i];
 	cuMemFree_v2(a);
 	cuMemFree_v2(b);
+	if (io_mode)
+		cuMemFree_v2(c);
 	pthread_mutex_lock(&sum_mu);
-	total_bad += bad;
+	total_bad += bad + io_bad;
 	total_iters += iters;
 	pthread_mutex_unlock(&sum_mu);
 	return NULL;
@@ -92,6 +121,7 @@ int main(int argc, char **argv)
 	seconds = argc > 2 ? atof(argv[2]) : 2.0;
 	seed = argc > 3 ? strtoull(argv[3], NULL, 0) : 1;
 	long threads = argc > 4 ? atol(argv[4]) : 4;
+	io_mode = argc > 5 && atoi(argv[5]) != 0;
 	bytes = mib << 20;
 	if (cuInit(0) || cuDevicePrimaryCtxRetain(&ctx, 0) || cuCtxSetCurrent(ctx))
 		return 2;

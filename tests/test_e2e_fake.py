@@ -127,10 +127,14 @@ def test_anti_thrash_off_and_on_again(artefacts, sock_dir, tmp_path):
         assert "Scheduler status changed to OFF" in err and "Scheduler status changed to ON" in err
 
 
-def test_multithreaded_clients_oversubscribed(artefacts, sock_dir, tmp_path):
+@pytest.mark.parametrize("io", [0, 1])
+def test_multithreaded_clients_oversubscribed(artefacts, sock_dir, tmp_path, io):
     """Four application threads per client issue copies and launches concurrently while
     the lock changes hands every second: nothing may touch a slab that is being unmapped
-    (the fake driver would segfault) and every thread's data must survive."""
+    (the fake driver would segfault) and every thread's data must survive.  io=1: each
+    thread also reads back, checks and rewrites a buffer every iteration -- copies that are
+    served by the device path or from the backing copy (nvs_host_io) depending on where the
+    lock happens to be, and must agree with each other."""
     d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
     try:
         d.ctl("-T", "1")
@@ -141,7 +145,7 @@ def test_multithreaded_clients_oversubscribed(artefacts, sock_dir, tmp_path):
                                   "NVSHARE_DEBUG": 1, "NVSHARE_SOCK_DIR": sock_dir, "NVSHARE_POOL_GIB": 1})
             env["LD_PRELOAD"] = preload("ours")
             # 4 threads x 2 buffers x 16 MiB = 128 MiB per client on a 200 MiB "GPU"
-            procs.append(subprocess.Popen([str(ORACLE / "mt_app"), "16", "5", str(i), "4"], env=env,
+            procs.append(subprocess.Popen([str(ORACLE / "mt_app"), "16", "5", str(i), "4", str(io)], env=env,
                                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
         outs = [p.communicate(timeout=120) for p in procs]
     finally:
@@ -149,6 +153,10 @@ def test_multithreaded_clients_oversubscribed(artefacts, sock_dir, tmp_path):
     for p, (out, err) in zip(procs, outs):
         assert p.returncode == 0 and re.search(r"RESULT PASS iters=\d+ mismatches=0", out), out + err[-2500:]
     assert d.read_log().count("Sent DROP_LOCK") >= 3
+    if io:
+        served = sum(err.count("served from the backing copy") for _, err in outs)
+        assert served >= 1                                   # both paths were really taken
+        assert sum(err.count("Sent REQ_LOCK") for _, err in outs) >= 4
 
 
 def test_client_exits_when_scheduler_is_absent(artefacts, sock_dir, tmp_path):
