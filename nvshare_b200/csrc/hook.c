@@ -85,6 +85,7 @@ static CUresult (*real_cuGetErrorName)(CUresult, const char **);
 static CUresult (*real_cuCtxSetCurrent)(CUcontext);
 static CUresult (*real_cuCtxGetCurrent)(CUcontext *);
 static CUresult (*real_cuCtxSynchronize)(void);
+static CUresult (*real_cuStreamIsCapturing)(CUstream, int *); /* optional */
 
 static pthread_mutex_t acct_mu = PTHREAD_MUTEX_INITIALIZER;
 static size_t cap_bytes;     /* what cuMemGetInfo reports as free: the per-process cap */
@@ -163,7 +164,7 @@ static void *gate_real[G_COUNT][2];
 
 static void after_launch(void);
 
-static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_device);
+static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_device, CUstream s);
 #define NO_BYPASS 0
 
 /* `bypass`: an expression that is non-zero when the call has been served without
@@ -209,12 +210,12 @@ GATED(cuGraphLaunch, 1, (CUgraphExec g, CUstream s), (g, s))
 GATED(cuMemcpy, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n), (dst, src, n))
 GATED(cuMemcpyAsync, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
 /* host<->device copies whose device side is swapped out are host<->host copies: no GPU, no lock */
-GATED_(cuMemcpyHtoD, 0, (CUdeviceptr dst, const void *src, size_t n), (dst, src, n), host_io_bypass(dst, src, n, 1))
+GATED_(cuMemcpyHtoD, 0, (CUdeviceptr dst, const void *src, size_t n), (dst, src, n), host_io_bypass(dst, src, n, 1, NULL))
 GATED_(cuMemcpyHtoDAsync, 0, (CUdeviceptr dst, const void *src, size_t n, CUstream s), (dst, src, n, s),
-       host_io_bypass(dst, src, n, 1))
-GATED_(cuMemcpyDtoH, 0, (void *dst, CUdeviceptr src, size_t n), (dst, src, n), host_io_bypass(src, dst, n, 0))
+       host_io_bypass(dst, src, n, 1, s))
+GATED_(cuMemcpyDtoH, 0, (void *dst, CUdeviceptr src, size_t n), (dst, src, n), host_io_bypass(src, dst, n, 0, NULL))
 GATED_(cuMemcpyDtoHAsync, 0, (void *dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s),
-       host_io_bypass(src, dst, n, 0))
+       host_io_bypass(src, dst, n, 0, s))
 GATED(cuMemcpyDtoD, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n), (dst, src, n))
 GATED(cuMemcpyDtoDAsync, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
 GATED(cuMemcpyPeer, 0, (CUdeviceptr dst, CUcontext dc, CUdeviceptr src, CUcontext sc, size_t n), (dst, dc, src, sc, n))
@@ -395,6 +396,7 @@ static void bootstrap(void)
 	real_cuCtxGetCurrent = must_sym("cuCtxGetCurrent");
 	real_cuCtxSynchronize = must_sym("cuCtxSynchronize");
 	/* optional: runtimes < 11.3 / < 12.0 never ask for them */
+	real_cuStreamIsCapturing = real_dlsym(cuda_lib, "cuStreamIsCapturing");
 	real_cuGetProcAddress = real_dlsym(cuda_lib, "cuGetProcAddress");
 	real_cuGetProcAddress_v2 = real_dlsym(cuda_lib, "cuGetProcAddress_v2");
 
@@ -559,7 +561,7 @@ static nvs_engine *engine_get(void)
  * there first the range is resident and the call goes down the gated path.
  * NVSHARE_LOCKFREE_COPY=0 turns it off.
  */
-static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_device)
+static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_device, CUstream s)
 {
 	static int enabled = -1;
 	if (enabled < 0) {
@@ -571,6 +573,12 @@ static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_de
 	nvs_engine *e = __atomic_load_n(&engine, __ATOMIC_ACQUIRE);
 	if (!e)
 		return 0;
+	if (s && real_cuStreamIsCapturing) {
+		/* a copy issued into a capturing stream is a graph node to be recorded, not work to do now */
+		int capturing = 0;
+		if (real_cuStreamIsCapturing(s, &capturing) != CUDA_SUCCESS || capturing != 0)
+			return 0;
+	}
 	int rc = nvs_host_io(e, (uint64_t)dev, (void *)(uintptr_t)host, (uint64_t)n, to_device);
 	if (rc == 0)
 		nvs_debug("%s of %zu bytes served from the backing copy, no lock needed", to_device ? "HtoD" : "DtoH", n);
