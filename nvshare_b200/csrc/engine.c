@@ -1887,6 +1887,52 @@ static void fill_words(uint8_t *dst, uint64_t slab_off, uint64_t n, uint64_t val
 		dst[k] = v[(slab_off + k) & 7];
 }
 
+/* Large copies are split over a few threads: one core moves ~6 GB/s, the DRAM several times that. */
+struct memcpy_job {
+	uint8_t *dst;
+	const uint8_t *src;
+	size_t n;
+};
+
+static void *memcpy_worker(void *arg)
+{
+	struct memcpy_job *j = arg;
+	memcpy(j->dst, j->src, j->n);
+	return NULL;
+}
+
+static void par_memcpy(uint8_t *dst, const uint8_t *src, uint64_t n)
+{
+	enum { MAX_T = 6 };
+	const uint64_t piece_min = 16ull << 20;
+	unsigned t = (unsigned)(n / piece_min);
+	if (t > MAX_T)
+		t = MAX_T;
+	if (t < 2) {
+		memcpy(dst, src, n);
+		return;
+	}
+	pthread_t th[MAX_T];
+	struct memcpy_job jobs[MAX_T];
+	const uint64_t piece = (n / t + 4095) & ~4095ull;
+	unsigned started = 0;
+	uint64_t off = 0;
+	sigset_t all, old; /* the helpers must never run the application's signal handlers */
+	sigfillset(&all);
+	pthread_sigmask(SIG_BLOCK, &all, &old);
+	for (unsigned i = 0; i + 1 < t && off + piece < n; ++i, off += piece) {
+		jobs[i] = (struct memcpy_job){dst + off, src + off, piece};
+		if (pthread_create(&th[i], NULL, memcpy_worker, &jobs[i]) != 0)
+			break;
+		started++;
+	}
+	pthread_sigmask(SIG_SETMASK, &old, NULL);
+	off = (uint64_t)started * piece;
+	memcpy(dst + off, src + off, n - off); /* the calling thread takes the rest */
+	for (unsigned i = 0; i < started; ++i)
+		pthread_join(th[i], NULL);
+}
+
 int nvs_host_io(nvs_engine *e, uint64_t dptr, void *host, uint64_t bytes, int to_device)
 {
 	if (!e || !host || bytes == 0)
@@ -1951,24 +1997,34 @@ int nvs_host_io(nvs_engine *e, uint64_t dptr, void *host, uint64_t bytes, int to
 		pthread_mutex_unlock(&e->mu);
 		for (uint64_t at = lo; at < hi;) {
 			const uint32_t si = (uint32_t)(at / SLAB);
-			const uint64_t s_end = ((uint64_t)si + 1) * SLAB < hi ? ((uint64_t)si + 1) * SLAB : hi;
-			const uint64_t n = s_end - at;
-			if (slab_is_const(c, si)) {
-				if (to_device) {
-					/* the slab stops being same-filled: write it out in full first */
-					fill_words(b + (uint64_t)si * SLAB, 0, SLAB, c->cvals[si]);
-					c->cmask[si >> 6] &= ~(1ull << (si & 63));
-					c->n_const--;
-					memcpy(b + at, h, n);
-				} else {
-					fill_words(h, at - (uint64_t)si * SLAB, n, c->cvals[si]);
-				}
-			} else if (to_device) {
-				memcpy(b + at, h, n);
-			} else {
-				memcpy(h, b + at, n);
+			uint64_t s_end = ((uint64_t)si + 1) * SLAB < hi ? ((uint64_t)si + 1) * SLAB : hi;
+			if (slab_is_const(c, si) && !to_device) {
+				fill_words(h, at - (uint64_t)si * SLAB, s_end - at, c->cvals[si]);
+				h += s_end - at;
+				at = s_end;
+				continue;
 			}
-			h += n;
+			/* one copy for a whole run of slabs that have (or now get) real bytes in the backing */
+			for (uint32_t k = si;; ++k) {
+				if (slab_is_const(c, k)) {
+					if (!to_device)
+						break;
+					/* stops being same-filled: unless it is overwritten entirely, write it out first */
+					const uint64_t k_lo = (uint64_t)k * SLAB, k_hi = k_lo + SLAB;
+					if (at > k_lo || hi < k_hi)
+						fill_words(b + k_lo, 0, SLAB, c->cvals[k]);
+					c->cmask[k >> 6] &= ~(1ull << (k & 63));
+					c->n_const--;
+				}
+				s_end = ((uint64_t)k + 1) * SLAB < hi ? ((uint64_t)k + 1) * SLAB : hi;
+				if (s_end == hi)
+					break;
+			}
+			if (to_device)
+				par_memcpy(b + at, h, s_end - at);
+			else
+				par_memcpy(h, b + at, s_end - at);
+			h += s_end - at;
 			at = s_end;
 		}
 		pthread_mutex_lock(&e->mu);
