@@ -353,7 +353,8 @@ def run_rank0(args, torch, world):
         "first_iter_gap_ms": [1e3 * g for g in a["first_iter_gap_s"]],
         "gpu_busy_frac": a["gpu_busy_frac"],
         "config": {
-            "workload": f"2x {args.kind} fp32 [n,n] n={n} ({args.pattern}), restated tests/pytorch-add.py, "
+            "workload": f"2x {args.kind} fp32 [n,n] n={n} ({args.pattern}), restated "
+                        f"{'tests/pytorch-add.py' if args.kind == 'add' else 'tests/tf-matmul.py'}, "
                         f"footprint {footprint / 1e9:.1f} GB/client = {args.clients * footprint / hbm_avail:.2f}x of "
                         f"{hbm_avail / 1e9:.1f} GB HBM",
             "clients": args.clients, "oversubscription": args.clients * footprint / hbm_avail,
