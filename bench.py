@@ -387,6 +387,12 @@ def run_rank0(args, torch, world):
                           "wait_ms_mean": statistics_mean([r["wait_ms"] for r in fe]),
                           "wall_ms_mean": {"evict": statistics_mean([r["wall_ms"] for r in ev]),
                                            "fetch": statistics_mean([r["wall_ms"] for r in fe])}}
+        pins = [r for r in harness.engine_records([out_dir / f"engine{i}.jsonl" for i in range(args.clients)], 0, 1e18)
+                if r["op"] == "pin"]
+        if pins:        # where the pinned pool's pages ended up (engine.c numa_init): the last report covers the whole pool
+            last = max(pins, key=lambda r: r["t"])
+            line["device"]["pool_pages_per_numa_node"] = last["pages_per_node"]
+            line["device"]["pool_placed_from_cpus"] = last["near_cpus"]
         per_dir = [g for g in (ev_gbps, fe_gbps) if g]
         achieved = sum(per_dir) / len(per_dir) if per_dir else None
         link = "nvlink" if world > 1 else "pcie"

@@ -40,6 +40,7 @@
 #include <errno.h>
 #include <inttypes.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -317,6 +318,11 @@ struct nvs_engine {
 	uint64_t pin_target; /* bytes of host pool we want to have */
 
 	FILE *stats_file;
+
+	/* CPUs on the GPU's own NUMA node: threads that first-touch (i.e. place) pinned
+	 * backing pages run there, so that the DMA does not cross the socket interconnect */
+	cpu_set_t near_cpus;
+	int near_cpus_valid;
 };
 #define N_COUNTERS 1024u /* per stream; the scan stream uses the second half of the array */
 
@@ -475,6 +481,94 @@ static void ctx_leave(nvs_engine *e)
 	e->d.CtxPopCurrent(&junk);
 }
 
+/* -------------------------------------------------------------- NUMA ---- */
+
+/* "0-3,8,10-11" -> cpu_set_t; returns the number of CPUs */
+static int parse_cpulist(const char *s, cpu_set_t *set)
+{
+	CPU_ZERO(set);
+	int n = 0;
+	while (*s) {
+		char *end;
+		long a = strtol(s, &end, 10), b = a;
+		if (end == s)
+			break;
+		if (*end == '-') {
+			s = end + 1;
+			b = strtol(s, &end, 10);
+			if (end == s)
+				break;
+		}
+		for (long c = a; c <= b && c >= 0 && c < CPU_SETSIZE; ++c) {
+			CPU_SET((int)c, set);
+			n++;
+		}
+		s = *end == ',' ? end + 1 : end;
+		if (*end != ',')
+			break;
+	}
+	return n;
+}
+
+/*
+ * Where should pinned backing memory live?  On a two-socket host the GPU hangs off
+ * one socket; pages first-touched by a thread on the other one are reached by every
+ * DMA through the socket interconnect.  Linux places a page on the node of the CPU
+ * that faults it in, so the threads that populate the pool are confined to the
+ * GPU's local CPUs (sysfs local_cpulist of its PCI function) while they do so --
+ * sched_setaffinity needs no privilege, unlike mbind under the usual container
+ * seccomp profile.  NVSHARE_NUMA=0 turns it off; NVSHARE_NUMA_CPULIST overrides sysfs.
+ */
+static void numa_init(nvs_engine *e, CUdevice dev, nvs_resolve_fn resolve)
+{
+	const char *sw = getenv("NVSHARE_NUMA");
+	if (sw && *sw && atoi(sw) == 0)
+		return;
+	char list[512] = "";
+	const char *forced = getenv("NVSHARE_NUMA_CPULIST");
+	if (forced && *forced) {
+		snprintf(list, sizeof(list), "%s", forced);
+	} else {
+		CUresult (*get_bus_id)(char *, int, CUdevice) = (CUresult (*)(char *, int, CUdevice))resolve("cuDeviceGetPCIBusId");
+		char bdf[64] = "", path[160];
+		if (!get_bus_id || get_bus_id(bdf, (int)sizeof(bdf) - 1, dev) != CUDA_SUCCESS || !bdf[0])
+			return;
+		for (char *c = bdf; *c; ++c)
+			if (*c >= 'A' && *c <= 'F')
+				*c = (char)(*c - 'A' + 'a');
+		snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bdf);
+		FILE *f = fopen(path, "r");
+		if (!f)
+			return;
+		if (!fgets(list, sizeof(list), f))
+			list[0] = '\0';
+		fclose(f);
+	}
+	cpu_set_t want, allowed;
+	if (parse_cpulist(list, &want) == 0 || sched_getaffinity(0, sizeof(allowed), &allowed) != 0)
+		return;
+	CPU_AND(&e->near_cpus, &want, &allowed);
+	const int n_near = CPU_COUNT(&e->near_cpus), n_allowed = CPU_COUNT(&allowed);
+	if (n_near == 0 || n_near == n_allowed)
+		return; /* nothing to choose from, or a single node: leave the threads alone */
+	e->near_cpus_valid = 1;
+	nvs_debug("engine: pinned backing memory is placed from %d of %d CPUs (the GPU's NUMA node)", n_near, n_allowed);
+}
+
+/* confine the calling thread to the GPU's CPUs; returns 1 if *saved must be restored */
+static int near_push(nvs_engine *e, cpu_set_t *saved)
+{
+	if (!e->near_cpus_valid || pthread_getaffinity_np(pthread_self(), sizeof(*saved), saved) != 0)
+		return 0;
+	return pthread_setaffinity_np(pthread_self(), sizeof(e->near_cpus), &e->near_cpus) == 0;
+}
+
+static void near_pop(int pushed, const cpu_set_t *saved)
+{
+	if (pushed)
+		pthread_setaffinity_np(pthread_self(), sizeof(*saved), saved);
+}
+
 /* -------------------------------------------------------------- pool ---- */
 
 static inline int bit_get(const struct arena *a, uint32_t i)
@@ -592,16 +686,52 @@ static struct arena *arena_new(uint64_t bytes)
 struct touch_job {
 	volatile const uint8_t *p;
 	size_t bytes;
+	nvs_engine *e;
 };
 
 static void *touch_worker(void *arg)
 {
 	/* READ faults only: the pages may already hold another client's evicted data */
 	struct touch_job *j = arg;
+	cpu_set_t saved;
+	near_push(j->e, &saved); /* this thread ends here: nothing to restore */
 	uint8_t acc = 0;
 	for (size_t off = 0; off < j->bytes; off += 4096)
 		acc ^= j->p[off];
 	return (void *)(uintptr_t)acc;
+}
+
+/* Which NUMA nodes hold the pool's pages (whole mapping, from /proc/self/numa_maps): evidence for numa_init */
+static void report_placement(nvs_engine *e, struct shpool *sp, uint32_t window)
+{
+	FILE *f = fopen("/proc/self/numa_maps", "r");
+	if (!f)
+		return;
+	char want[32], *line = NULL;
+	size_t cap = 0;
+	snprintf(want, sizeof(want), "%lx ", (unsigned long)(uintptr_t)sp->hdr);
+	while (getline(&line, &cap, f) > 0) {
+		if (strncmp(line, want, strlen(want)) != 0)
+			continue;
+		unsigned long long pages[8] = {0};
+		for (char *t = strtok(line, " \n"); t; t = strtok(NULL, " \n")) {
+			unsigned node;
+			unsigned long long n;
+			if (sscanf(t, "N%u=%llu", &node, &n) == 2 && node < 8)
+				pages[node] = n;
+		}
+		nvs_debug("engine: shared pool window %u pinned; pages per NUMA node: N0=%llu N1=%llu N2=%llu N3=%llu", window,
+			  pages[0], pages[1], pages[2], pages[3]);
+		if (e->stats_file) {
+			fprintf(e->stats_file, "{\"op\":\"pin\",\"t\":%.6f,\"pid\":%d,\"window\":%u,\"near_cpus\":%d,"
+				"\"pages_per_node\":[%llu,%llu,%llu,%llu]}\n", wall_s(), (int)getpid(), window,
+				e->near_cpus_valid ? CPU_COUNT(&e->near_cpus) : 0, pages[0], pages[1], pages[2], pages[3]);
+			fflush(e->stats_file);
+		}
+		break;
+	}
+	free(line);
+	fclose(f);
 }
 
 /* Pin the next window of the shared pool into this process.  e->mu NOT held. */
@@ -624,13 +754,17 @@ static int shared_pool_grow_unlocked(nvs_engine *e)
 	for (int i = 0; i < NT; ++i) {
 		jobs[i].p = base + (win_bytes / NT) * (uint64_t)i;
 		jobs[i].bytes = win_bytes / NT;
+		jobs[i].e = e;
 		if (pthread_create(&th[i], NULL, touch_worker, &jobs[i]) != 0)
 			break;
 		started++;
 	}
 	for (int i = 0; i < started; ++i)
 		pthread_join(th[i], NULL);
+	cpu_set_t saved;
+	const int pushed = near_push(e, &saved); /* pages the workers left to the driver are placed from here */
 	CUresult r = e->d.MemHostRegister(base, win_bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP);
+	near_pop(pushed, &saved);
 	if (r != CUDA_SUCCESS) {
 		nvs_warn("engine: cuMemHostRegister of shared pool window %u failed: %s", w, cu_name(e, r));
 		return NVS_E_HOST_OOM;
@@ -638,6 +772,8 @@ static int shared_pool_grow_unlocked(nvs_engine *e)
 	CUdeviceptr dp = 0;
 	if (e->d.MemHostGetDevicePointer(&dp, base, 0) != CUDA_SUCCESS)
 		dp = (CUdeviceptr)(uintptr_t)base;
+	if (e->stats_file || nvs_debug_enabled)
+		report_placement(e, sp, w);
 	struct arena *a = calloc(1, sizeof(*a));
 	if (!a)
 		return NVS_E_HOST_OOM;
@@ -673,7 +809,10 @@ static int host_pool_grow_unlocked(nvs_engine *e)
 	if (!a)
 		return NVS_E_HOST_OOM;
 	void *p = NULL;
+	cpu_set_t saved;
+	const int pushed = near_push(e, &saved); /* the driver populates the pages from this thread */
 	CUresult r = e->d.MemHostAlloc(&p, a->bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP);
+	near_pop(pushed, &saved);
 	if (r != CUDA_SUCCESS) {
 		nvs_warn("engine: cuMemHostAlloc(%" PRIu64 " MiB) failed: %s", a->bytes >> 20, cu_name(e, r));
 		free(a->bitmap);
@@ -2219,6 +2358,7 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	CK(e, e->d.CtxGetDevice(&dev));
 	e->device = e->cfg.device >= 0 ? e->cfg.device : (int)dev;
 	CK(e, e->d.DeviceGetAttribute(&e->n_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+	numa_init(e, dev, resolve);
 
 	if (e->d.ModuleLoadData(&e->module, nvs_slab_copy_cubin) != CUDA_SUCCESS ||
 	    e->d.ModuleGetFunction(&e->fn_tma, e->module, "nvs_slab_copy_tma") != CUDA_SUCCESS ||

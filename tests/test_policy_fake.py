@@ -232,3 +232,40 @@ def test_units_of_a_client_that_dies_later_are_reclaimed_on_exhaustion(artefacts
     out, err = survivor.communicate(timeout=60)
     assert survivor.returncode == 0 and "BAD 0" in out, out + err
     assert struct.unpack("<QIIQQ", pool.open("rb").read(32))[4] == 0
+
+
+def test_pool_pages_are_placed_from_the_gpus_cpus(artefacts, tmp_path):
+    """engine.c numa_init: the threads that populate pinned backing memory are confined
+    to the CPUs next to the GPU (here forced with NVSHARE_NUMA_CPULIST, on the box read
+    from sysfs), the caller's own affinity is restored, and the stats file says where
+    the pages went."""
+    import json
+    import os
+    if len(os.sched_getaffinity(0)) < 2:
+        pytest.skip("needs two CPUs to tell 'near' from 'allowed'")
+    near = sorted(os.sched_getaffinity(0))[0]
+    pool, stats = tmp_path / "pool", tmp_path / "stats.jsonl"
+    code = textwrap.dedent(f"""
+        import ctypes as C, os, sys
+        sys.path.insert(0, {str(ROOT)!r})
+        fake = C.CDLL({str(FAKE_DIR / 'libcuda.so.1')!r}, mode=C.RTLD_GLOBAL)
+        fake.cuInit(0); ctx = C.c_void_p(); fake.cuDevicePrimaryCtxRetain(C.byref(ctx), 0); fake.cuCtxSetCurrent(ctx)
+        from nvshare_b200 import engine as E
+        before = os.sched_getaffinity(0)
+        e = E.Engine(chunk_bytes=8 << 20, host_arena_bytes=64 << 20, shared_pool_path={str(pool)!r},
+                     shared_pool_bytes=256 << 20, stats_path={str(stats)!r}, prepin=0)
+        p = e.alloc(48 << 20); e.fetch_all(); e.pattern_fill(p, (48 << 20) // 8, seed=3); e.evict(0)
+        assert os.sched_getaffinity(0) == before, "the caller's affinity was not restored"
+        e.fetch_all(); assert e.pattern_verify(p, (48 << 20) // 8, seed=3) == 0
+        e.free(p); e.close()
+        print("OK")
+    """)
+    env = dict(os.environ, NVSHARE_NUMA_CPULIST=str(near), NVSHARE_DEBUG="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=60)
+    assert "OK" in r.stdout, r.stdout + r.stderr
+    assert "placed from 1 of" in r.stderr
+    pins = [json.loads(l) for l in stats.read_text().splitlines() if '"op":"pin"' in l]
+    assert pins and pins[0]["near_cpus"] == 1 and sum(pins[0]["pages_per_node"]) > 0
+    r = subprocess.run([sys.executable, "-c", code], env=dict(env, NVSHARE_NUMA="0"), capture_output=True, text=True,
+                       timeout=60)
+    assert "OK" in r.stdout and "placed from" not in r.stderr
