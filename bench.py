@@ -327,8 +327,15 @@ def run_rank0(args, torch, world):
         a = harness.analyse(clients, args.warmup, args.steps)
     except Exception as ex:  # not enough hand-offs: report what happened, loudly
         tails = {f"client{i}": r["err_tail"][-600:] for i, r in enumerate(res)}
+        last_ops = {}
+        for i in range(args.clients):        # what the engines did last: the first thing one wants to know
+            f = out_dir / f"engine{i}.jsonl"
+            if f.exists():
+                last_ops[f"client{i}"] = [l[:400] for l in f.read_text().splitlines() if '"op":"pin"' not in l][-6:]
         return {"metric": "swap_GBps_at_1.5x_hbm_oversub_2_clients", "error": str(ex), "impl": args.impl,
-                "verified": False, "client_rc": [r["rc"] for r in res], "stderr_tails": tails}, wall
+                "verified": False, "client_rc": [r["rc"] for r in res], "stderr_tails": tails,
+                "engine_last_ops": last_ops, "n": n, "hbm_fraction_used": args.hbm_fraction, "scale_note": scale_note,
+                "host_memory_budget": host_memory_budget(), "wall_s_total": wall}, wall
 
     stall = a["stall_per_handoff_s"]
     e2e_gbps = (2 * algo_bytes_dir / 1e9) / stall if stall > 0 else None

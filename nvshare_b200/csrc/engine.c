@@ -325,6 +325,10 @@ struct nvs_engine {
 	int near_cpus_valid;
 };
 #define N_COUNTERS 1024u /* per stream; the scan stream uses the second half of the array */
+/* Memory pressure is only signalled once the free HBM has not grown for this long: while
+ * the previous holder is evicting for us it grows every few tens of ms, and a pressure
+ * message sent then would be handled AFTER that eviction and evict the same amount again. */
+#define PRESSURE_AFTER_MS 300.0
 
 static double now_ms(void)
 {
@@ -1229,7 +1233,8 @@ static int chunk_map(nvs_engine *e, struct chunk *c, double *wait_ms)
 	acc.location = prop.location;
 	acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
 
-	double t0 = now_ms(), warned = 0, next_pressure = 200;
+	double t0 = now_ms(), warned = 0, next_pressure = 0, last_progress = t0;
+	size_t last_free = 0;
 	for (;;) {
 		CUresult r = e->d.MemCreate(&c->handle, c->bytes, &prop, 0);
 		if (r == CUDA_SUCCESS)
@@ -1249,7 +1254,7 @@ static int chunk_map(nvs_engine *e, struct chunk *c, double *wait_ms)
 			nvs_debug("engine: waiting for HBM to be released by another client");
 			warned = 1;
 		}
-		if (e->cfg.pressure_cb && waited >= next_pressure) {
+		if (e->cfg.pressure_cb && now_ms() - last_progress >= PRESSURE_AFTER_MS && waited >= next_pressure) {
 			/* nobody is (any longer) freeing memory for us: say how much we still miss */
 			e->cfg.pressure_cb(e->cfg.pressure_user, e->st.swapped_bytes + e->st.unbacked_bytes);
 			next_pressure = waited + 1000;
@@ -1261,7 +1266,12 @@ static int chunk_map(nvs_engine *e, struct chunk *c, double *wait_ms)
 		for (int spin = 0; spin < 20; ++spin) {
 			size_t free_b = 0, total_b = 0;
 			usleep(1000);
-			if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= c->bytes + (64u << 20))
+			if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS)
+				break;
+			if (free_b > last_free)
+				last_progress = now_ms(); /* somebody is handing HBM back right now */
+			last_free = free_b;
+			if (free_b >= c->bytes + (64u << 20))
 				break;
 		}
 		pthread_mutex_lock(&e->mu);
@@ -1645,17 +1655,21 @@ static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report
 	if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= e->cfg.batch_bytes + e->cfg.chunk_bytes + slack ||
 	    free_b >= remaining + slack)
 		return 0; /* room for at least this batch: carry on with the current burst */
-	double t0 = now_ms(), next_pressure = 200;
+	double t0 = now_ms(), next_pressure = 0, last_progress = t0;
+	size_t last_free = free_b;
 	for (;;) {
 		if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= want + slack)
 			break;
-		double waited = now_ms() - t0;
+		const double now = now_ms(), waited = now - t0;
+		if (free_b > last_free)
+			last_progress = now; /* the previous holder is still handing HBM back: no need to press it */
+		last_free = free_b;
 		if (waited > e->cfg.oom_wait_ms) {
 			nvs_warn("engine: HBM still exhausted after %.0f ms", waited);
 			rep->wait_ms += waited;
 			return NVS_E_TIMEOUT;
 		}
-		if (e->cfg.pressure_cb && waited >= next_pressure) {
+		if (e->cfg.pressure_cb && now - last_progress >= PRESSURE_AFTER_MS && waited >= next_pressure) {
 			e->cfg.pressure_cb(e->cfg.pressure_user, remaining);
 			next_pressure = waited + 1000;
 		}

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-OUT=gpurun_out/call18
+OUT=gpurun_out/call19
 mkdir -p $OUT
 echo "== NUMA placement of the pinned pool: full-scale bench, placed from the GPU's CPUs (default) vs anywhere" | tee $OUT/summary.txt
 nvidia-smi topo -m 2>/dev/null | head -4 | cut -c1-200 | tee -a $OUT/summary.txt
