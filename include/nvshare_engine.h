@@ -179,6 +179,13 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep);
  */
 int nvs_host_io(nvs_engine *e, uint64_t dptr, void *host, uint64_t bytes, int to_device);
 
+/* Like nvs_evict, but never waits for room in the backing tier: it evicts what the
+ * tier can take right now and returns 0 (possibly having moved less than asked).
+ * For evictions done as a favour to another client (memory pressure) by a client
+ * that may itself be about to be granted the lock: waiting there for pool units
+ * that only its own next fetch would free is a deadlock. */
+int nvs_evict_best_effort(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep);
+
 int nvs_get_stats(nvs_engine *e, nvs_stats *out);
 
 /* Raw kernel access (parity tests, roofline).  All addresses must be

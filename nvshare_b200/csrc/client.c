@@ -167,6 +167,19 @@ static void do_evict(uint64_t mib)
 		nvs_fatal("eviction failed; cannot hand the GPU over safely");
 }
 
+/* An eviction done as a favour (memory pressure from the client that is mapping).  It
+ * must not wait for room in the backing pool: our own LOCK_OK may be queued right behind
+ * this message, and the fetch it triggers is what would free that room. */
+static void do_evict_as_a_favour(uint64_t mib)
+{
+	if (!dp.evict_best_effort) {
+		do_evict(mib);
+		return;
+	}
+	if (mib != 0 && dp.evict_best_effort(mib == EVICT_ALL ? 0 : mib << 20) != 0)
+		nvs_fatal("eviction failed; cannot hand the GPU over safely");
+}
+
 /* Give the lock back and get our slabs out of the next holder's way (mutex held). */
 static void release_lock_and_evict(int have_hint, unsigned waiters, uint64_t need_mib)
 {
@@ -326,7 +339,7 @@ static void *message_thread(void *arg)
 				/* memory pressure from the client that is mapping: get out of its way */
 				uint64_t mib = strtoull(in.data + 1, NULL, 10);
 				sync_app_context();
-				do_evict(mib ? mib + evict_margin_mib() : EVICT_ALL);
+				do_evict_as_a_favour(mib ? mib + evict_margin_mib() : EVICT_ALL);
 				if (need_lock) {
 					/* our queued request still advertises the old need: refresh it, or the
 					 * holder will free too little for us and we will have to press it again */

@@ -521,12 +521,16 @@ static int parse_cpulist(const char *s, cpu_set_t *set)
  * that faults it in, so the threads that populate the pool are confined to the
  * GPU's local CPUs (sysfs local_cpulist of its PCI function) while they do so --
  * sched_setaffinity needs no privilege, unlike mbind under the usual container
- * seccomp profile.  NVSHARE_NUMA=0 turns it off; NVSHARE_NUMA_CPULIST overrides sysfs.
+ * seccomp profile.  NVSHARE_NUMA=1 turns it on; NVSHARE_NUMA_CPULIST overrides sysfs.
  */
 static void numa_init(nvs_engine *e, CUdevice dev, nvs_resolve_fn resolve)
 {
+	/* Opt-in (NVSHARE_NUMA=1).  Measured on the r01 boxes (two sockets, profiles/r01_call18_*,
+	 * r01_call19_*): eviction 43.7 / fetch 51.9 GB/s with every page on the GPU's node versus
+	 * 44.3 / 52.0 GB/s with two thirds of them on the other one -- the socket interconnect is
+	 * not the bottleneck there, so the default stays what all other measurements were taken with. */
 	const char *sw = getenv("NVSHARE_NUMA");
-	if (sw && *sw && atoi(sw) == 0)
+	if (!(sw && *sw && atoi(sw) != 0))
 		return;
 	char list[512] = "";
 	const char *forced = getenv("NVSHARE_NUMA_CPULIST");
@@ -776,7 +780,8 @@ static int shared_pool_grow_unlocked(nvs_engine *e)
 	CUdeviceptr dp = 0;
 	if (e->d.MemHostGetDevicePointer(&dp, base, 0) != CUDA_SUCCESS)
 		dp = (CUdeviceptr)(uintptr_t)base;
-	if (e->stats_file || nvs_debug_enabled)
+	/* (walking numa_maps costs ~1 s once the mapping holds 100+ GB: never on every window) */
+	if (e->near_cpus_valid && (e->stats_file || nvs_debug_enabled) && (sp->n_windows <= 8 || (w + 1) % 32 == 0))
 		report_placement(e, sp, w);
 	struct arena *a = calloc(1, sizeof(*a));
 	if (!a)
@@ -905,7 +910,7 @@ fail:
 static uint64_t shp_reap_dead(struct shpool *sp);
 
 /* Find backing for a chunk: peers first (striped), then pinned host.  e->mu held. */
-static int backing_assign(nvs_engine *e, struct chunk *c)
+static int backing_assign(nvs_engine *e, struct chunk *c, int nowait)
 {
 	if (c->backing)
 		return 0;
@@ -927,7 +932,7 @@ static int backing_assign(nvs_engine *e, struct chunk *c)
 		int rc = host_pool_grow(e);
 		if (rc == 0)
 			continue;
-		if (!e->shp || now_ms() - t0 > e->cfg.oom_wait_ms)
+		if (!e->shp || nowait || now_ms() - t0 > e->cfg.oom_wait_ms)
 			return rc;
 		/* the shared pool is full and entirely pinned here: another client is about
 		 * to hand units back (its fetch releases them batch by batch) -- unless it died */
@@ -1507,7 +1512,19 @@ out:
 	return rc;
 }
 
+static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out, int best_effort);
+
 int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
+{
+	return evict_impl(e, min_bytes, rep_out, 0);
+}
+
+int nvs_evict_best_effort(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
+{
+	return evict_impl(e, min_bytes, rep_out, 1);
+}
+
+static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out, int best_effort)
 {
 	nvs_xfer_report rep;
 	memset(&rep, 0, sizeof(rep));
@@ -1574,11 +1591,22 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
 				goto out;
 			s->n_chunks = 0;
 		}
+		int tier_full = 0;
 		for (uint32_t k = 0; k < n_picked; ++k) {
 			struct chunk *c = picked[k];
 			const uint64_t moving = c->bytes - (uint64_t)c->n_const * SLAB;
-			if (moving && (rc = backing_assign(e, c)) != 0)
-				goto out;
+			if (moving && (rc = backing_assign(e, c, best_effort)) != 0) {
+				if (!(best_effort && rc == NVS_E_HOST_OOM))
+					goto out;
+				/* the tier is full: this chunk and the rest of the batch stay where they are */
+				rc = 0;
+				tier_full = 1;
+				for (uint32_t j = k; j < n_picked; ++j) {
+					memset(picked[j]->cmask, 0, sizeof(picked[j]->cmask));
+					picked[j]->n_const = 0;
+				}
+				break;
+			}
 			if (slot_push_chunk(s, c, 1, variant) != 0) {
 				rc = NVS_E_BAD_ARG;
 				goto out;
@@ -1601,6 +1629,8 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
 		rep.bytes += copied;
 		rep.slabs += copied / SLAB;
 		batch_no++;
+		if (tier_full)
+			break;
 	}
 	(void)started;
 	for (unsigned k = 0; k < N_SLOTS; ++k) {
@@ -1608,7 +1638,7 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out)
 		if (r != 0 && rc == 0)
 			rc = r;
 	}
-	if (min_bytes == 0)
+	if (min_bytes == 0 && e->st.resident_bytes == 0)
 		e->resident_mode = 0; /* everything is out: the owner no longer holds the GPU */
 	e->st.n_evicts++;
 	e->st.evicted_bytes_total += rep.bytes;
@@ -2121,7 +2151,7 @@ int nvs_host_io(nvs_engine *e, uint64_t dptr, void *host, uint64_t bytes, int to
 		if (to_device && !c->backing) {
 			/* never materialised, or every slab same-filled: it needs a backing copy now */
 			int need_ctx = ctx_enter(e) == 0; /* pinning a new arena needs the context */
-			rc = backing_assign(e, c);
+			rc = backing_assign(e, c, 0);
 			if (need_ctx)
 				ctx_leave(e);
 			if (rc != 0)

@@ -440,7 +440,11 @@ static int dp_fetch_all(void)
 	return rc;
 }
 
-static int dp_evict(uint64_t min_bytes)
+static int dp_evict_impl(uint64_t min_bytes, int best_effort);
+static int dp_evict(uint64_t min_bytes) { return dp_evict_impl(min_bytes, 0); }
+static int dp_evict_best_effort(uint64_t min_bytes) { return dp_evict_impl(min_bytes, 1); }
+
+static int dp_evict_impl(uint64_t min_bytes, int best_effort)
 {
 	if (nvs_process_exiting)
 		return 0;
@@ -450,7 +454,7 @@ static int dp_evict(uint64_t min_bytes)
 	if (!e)
 		return 0;
 	nvs_xfer_report rep;
-	int rc = nvs_evict(e, min_bytes, &rep);
+	int rc = best_effort ? nvs_evict_best_effort(e, min_bytes, &rep) : nvs_evict(e, min_bytes, &rep);
 	if (rc == NVS_E_SHUTDOWN || nvs_process_exiting)
 		return 0;
 	if (rc != 0)
@@ -510,7 +514,7 @@ static void reset_sync_window(void)
 static void start_client(void)
 {
 	static const struct nvs_client_datapath dp = {dp_fetch_all, dp_evict, dp_nonresident_mib, dp_lock_state,
-						       dp_free_hbm_mib, dp_total_hbm_mib};
+						       dp_free_hbm_mib, dp_total_hbm_mib, dp_evict_best_effort};
 	nvs_client_on_context_sync = reset_sync_window;
 	nvs_client_start(&client_drv, uvm_mode ? NULL : &dp);
 }

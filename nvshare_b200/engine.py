@@ -95,6 +95,7 @@ def load():
     lib.nvs_set_resident_mode.restype = None
     lib.nvs_fetch_all.argtypes = [C.c_void_p, P(XferReport)]
     lib.nvs_evict.argtypes = [C.c_void_p, C.c_uint64, P(XferReport)]
+    lib.nvs_evict_best_effort.argtypes = [C.c_void_p, C.c_uint64, P(XferReport)]
     lib.nvs_get_stats.argtypes = [C.c_void_p, P(Stats)]
     lib.nvs_host_io.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
     lib.nvs_copy_slabs.argtypes = [C.c_void_p, P(CopyDesc), C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_float)]
@@ -169,6 +170,11 @@ class Engine:
     def evict(self, min_bytes: int = 0) -> dict:
         rep = XferReport()
         _check(load().nvs_evict(self._h, min_bytes, C.byref(rep)), "nvs_evict")
+        return rep.as_dict()
+
+    def evict_best_effort(self, min_bytes: int = 0) -> dict:
+        rep = XferReport()
+        _check(load().nvs_evict_best_effort(self._h, min_bytes, C.byref(rep)), "nvs_evict_best_effort")
         return rep.as_dict()
 
     def stats(self) -> dict:

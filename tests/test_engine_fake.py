@@ -434,3 +434,36 @@ def test_host_io_on_same_filled_slabs(fake):
         assert np.array_equal(view(p, 16 * MiB), expect)
     finally:
         e.close()
+
+
+def test_best_effort_eviction_never_waits_for_backing_space(fake, tmp_path):
+    """nvs_evict_best_effort (used for evictions done as a favour under memory pressure):
+    with the backing pool full it moves what fits, returns 0 at once and leaves the rest
+    resident and intact; the ordinary nvs_evict waits (and here times out)."""
+    import time
+    from nvshare_b200 import engine as E
+    pool = tmp_path / "pool"
+    e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, batch_bytes=16 * MiB, shared_pool_path=str(pool),
+                 shared_pool_bytes=64 * MiB, oom_wait_ms=2500, elide_constant=0, prepin=0)
+    try:
+        p = e.alloc(96 * MiB); e.fetch_all()
+        e.pattern_fill(p, 96 * MiB // 8, seed=21)
+        t0 = time.time()
+        rep = e.evict_best_effort(0)
+        assert time.time() - t0 < 1.5
+        st = e.stats()
+        assert rep["bytes"] == 64 * MiB == st["swapped_bytes"] and st["resident_bytes"] == 32 * MiB
+        assert st["host_pool_used"] == 64 * MiB
+        with pytest.raises(E.EngineError) as ei:             # the blocking flavour waits for units nobody will free
+            e.evict(0)
+        assert ei.value.rc == -7                             # NVS_E_HOST_OOM after oom_wait_ms
+        e.fetch_all()
+        assert e.pattern_verify(p, 96 * MiB // 8, seed=21) == 0
+        assert e.stats()["host_pool_used"] == 0
+        rep = e.evict_best_effort(16 * MiB)                  # partial request, plenty of room: behaves like nvs_evict
+        assert rep["bytes"] == 16 * MiB
+        e.fetch_all()
+        assert e.pattern_verify(p, 96 * MiB // 8, seed=21) == 0
+        e.free(p)
+    finally:
+        e.close()

@@ -260,12 +260,12 @@ def test_pool_pages_are_placed_from_the_gpus_cpus(artefacts, tmp_path):
         e.free(p); e.close()
         print("OK")
     """)
-    env = dict(os.environ, NVSHARE_NUMA_CPULIST=str(near), NVSHARE_DEBUG="1")
+    env = dict(os.environ, NVSHARE_NUMA="1", NVSHARE_NUMA_CPULIST=str(near), NVSHARE_DEBUG="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=60)
     assert "OK" in r.stdout, r.stdout + r.stderr
     assert "placed from 1 of" in r.stderr
     pins = [json.loads(l) for l in stats.read_text().splitlines() if '"op":"pin"' in l]
     assert pins and pins[0]["near_cpus"] == 1 and sum(pins[0]["pages_per_node"]) > 0
-    r = subprocess.run([sys.executable, "-c", code], env=dict(env, NVSHARE_NUMA="0"), capture_output=True, text=True,
-                       timeout=60)
+    env.pop("NVSHARE_NUMA")                                # opt-in: off by default
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=60)
     assert "OK" in r.stdout and "placed from" not in r.stderr
