@@ -12,7 +12,10 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-BUILD = ROOT / "nvshare_b200" / "_build"
+# NVS_TEST_BUILD points the suite at another build of the product (e.g. one made with
+# -fsanitize=address,undefined: tools/sanitize.sh); NVS_TEST_PRELOAD_FIRST is put in front of
+# libnvshare.so in LD_PRELOAD (the sanitizer runtime must come first)
+BUILD = Path(os.environ.get("NVS_TEST_BUILD", ROOT / "nvshare_b200" / "_build"))
 ORACLE = ROOT / "oracle" / "_ref"
 FAKE_DIR = ORACLE / "fakecuda"
 
@@ -174,4 +177,6 @@ def fake_env(total_mib=4096, ledger=None, trace=None, devices=1, extra=None):
 
 
 def preload(lib_impl):
-    return str((BUILD if lib_impl == "ours" else ORACLE) / "libnvshare.so")
+    lib = str((BUILD if lib_impl == "ours" else ORACLE) / "libnvshare.so")
+    first = os.environ.get("NVS_TEST_PRELOAD_FIRST")
+    return f"{first}:{lib}" if first and lib_impl == "ours" else lib
