@@ -101,6 +101,7 @@ struct drv {
 	CUresult (*EventDestroy)(CUevent);
 	CUresult (*EventRecord)(CUevent, CUstream);
 	CUresult (*EventSynchronize)(CUevent);
+	CUresult (*EventQuery)(CUevent);
 	CUresult (*EventElapsedTime)(float *, CUevent, CUevent);
 	CUresult (*ModuleLoadData)(CUmodule *, const void *);
 	CUresult (*ModuleUnload)(CUmodule);
@@ -147,6 +148,7 @@ static const struct {
 	S(EventDestroy, "cuEventDestroy_v2"),
 	S(EventRecord, "cuEventRecord"),
 	S(EventSynchronize, "cuEventSynchronize"),
+	S(EventQuery, "cuEventQuery"),
 	S(EventElapsedTime, "cuEventElapsedTime"),
 	S(ModuleLoadData, "cuModuleLoadData"),
 	S(ModuleUnload, "cuModuleUnload"),
@@ -459,6 +461,8 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->stats_path = getenv("NVSHARE_STATS_FILE");
 	cfg->shared_pool_path = getenv("NVSHARE_POOL_PATH"); /* libnvshare.so derives one from the socket path */
 	cfg->shared_pool_bytes = env_u64("NVSHARE_POOL_GIB", 0) << 30;
+	if (getenv("NVSHARE_POOL_MIB")) /* finer grain, for tests of a tight pool */
+		cfg->shared_pool_bytes = env_u64("NVSHARE_POOL_MIB", 0) << 20;
 	const char *peers = getenv("NVSHARE_PEERS"); /* "1,2,3" */
 	if (peers && *peers) {
 		char buf[128];
@@ -1591,19 +1595,30 @@ static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_ou
 				goto out;
 			s->n_chunks = 0;
 		}
-		int tier_full = 0;
+		int tier_full = 0, must_drain = 0, any_busy = 0;
+		for (unsigned q = 0; q < N_SLOTS; ++q)
+			any_busy |= e->slots[q].busy;
 		for (uint32_t k = 0; k < n_picked; ++k) {
 			struct chunk *c = picked[k];
 			const uint64_t moving = c->bytes - (uint64_t)c->n_const * SLAB;
-			if (moving && (rc = backing_assign(e, c, best_effort)) != 0) {
-				if (!(best_effort && rc == NVS_E_HOST_OOM))
+			/* Only wait for room in the backing tier with nothing of ours in flight: the units we
+			 * wait for come back when another client fetches, and it can only fetch into the HBM
+			 * that our already-copied batches still hold until they are retired. */
+			const int nowait = best_effort || k > 0 || any_busy;
+			if (moving && (rc = backing_assign(e, c, nowait)) != 0) {
+				if (!(nowait && rc == NVS_E_HOST_OOM))
 					goto out;
-				/* the tier is full: this chunk and the rest of the batch stay where they are */
+				/* the tier is full: this chunk and the rest of the batch stay where they are ... */
 				rc = 0;
-				tier_full = 1;
 				for (uint32_t j = k; j < n_picked; ++j) {
 					memset(picked[j]->cmask, 0, sizeof(picked[j]->cmask));
 					picked[j]->n_const = 0;
+				}
+				if (best_effort) {
+					tier_full = 1; /* ... for good */
+				} else {
+					must_drain = 1; /* ... until what is in flight has left HBM; then we come back to them */
+					i -= n_picked - k;
 				}
 				break;
 			}
@@ -1618,19 +1633,25 @@ static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_ou
 			else
 				rep.host_bytes += moving;
 		}
-		started = 1;
-		CK(e, e->d.EventRecord(s->begin, e->stream));
-		if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, variant,
-				       grid_for(e, 0, peer_traffic))) != 0)
-			goto out;
-		CK(e, e->d.EventRecord(s->done, e->stream));
-		s->busy = 1;
-		rep.launches += variant == NVS_COPY_CE ? s->n_descs : (s->n_descs ? 1 : 0);
-		rep.bytes += copied;
-		rep.slabs += copied / SLAB;
-		batch_no++;
+		if (s->n_chunks) {
+			started = 1;
+			CK(e, e->d.EventRecord(s->begin, e->stream));
+			if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, variant,
+					       grid_for(e, 0, peer_traffic))) != 0)
+				goto out;
+			CK(e, e->d.EventRecord(s->done, e->stream));
+			s->busy = 1;
+			rep.launches += variant == NVS_COPY_CE ? s->n_descs : (s->n_descs ? 1 : 0);
+			rep.bytes += copied;
+			rep.slabs += copied / SLAB;
+			batch_no++;
+		}
 		if (tier_full)
 			break;
+		if (must_drain) /* release the HBM of every batch copied so far before waiting for units */
+			for (unsigned q = 0; q < N_SLOTS; ++q)
+				if ((rc = evict_retire(e, &e->slots[q], &rep)) != 0)
+					goto out;
 	}
 	(void)started;
 	for (unsigned k = 0; k < N_SLOTS; ++k) {
@@ -1676,6 +1697,20 @@ out:
  * runs: 2.59, 3.16, 4.21 s, eviction down to 35 GB/s; all-ones data 1.10 s vs
  * 0.30 s) -- profiles/r01_call11_burst_sweep_summary.txt, r01_call12_*.
  */
+static int fetch_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep);
+
+/* While a fetch waits for HBM: hand back the backing units of batches that have already
+ * landed.  The client that is evicting into a tight pool may be waiting for exactly those
+ * units, and we may be waiting for the HBM its eviction frees. */
+static void fetch_retire_completed(nvs_engine *e, nvs_xfer_report *rep)
+{
+	for (unsigned k = 0; k < N_SLOTS; ++k) {
+		struct slot *s = &e->slots[k];
+		if (s->busy && e->d.EventQuery(s->done) == CUDA_SUCCESS)
+			fetch_retire(e, s, rep);
+	}
+}
+
 static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report *rep)
 {
 	/* head-room kept below the releasing client's own margin (1/128 of the HBM, client.c) */
@@ -1703,6 +1738,7 @@ static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report
 			e->cfg.pressure_cb(e->cfg.pressure_user, remaining);
 			next_pressure = waited + 1000;
 		}
+		fetch_retire_completed(e, rep);
 		pthread_mutex_unlock(&e->mu);
 		usleep(2000);
 		pthread_mutex_lock(&e->mu);
@@ -1719,7 +1755,7 @@ static int fetch_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
 	if (s->busy) {
 		float ms = 0;
 		CK(e, e->d.EventSynchronize(s->done));
-		if (e->d.EventElapsedTime(&ms, s->begin, s->done) == CUDA_SUCCESS)
+		if (rep && e->d.EventElapsedTime(&ms, s->begin, s->done) == CUDA_SUCCESS)
 			rep->copy_ms += ms;
 		for (uint32_t i = 0; i < s->n_chunks; ++i)
 			backing_release(e, s->chunks[i]);

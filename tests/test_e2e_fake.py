@@ -214,3 +214,19 @@ def test_loading_client_waits_when_the_bypass_is_off(artefacts, sock_dir, tmp_pa
     assert b.returncode == 0 and "RESULT PASS" in b.stdout, b.stdout + b.stderr[-1500:]
     assert "Sent REQ_LOCK" in b.stderr and "served from the backing copy" not in b.stderr
     assert took > 2.5
+
+
+@pytest.mark.parametrize("policy", ["all", "need"])
+def test_tight_backing_pool_makes_progress(artefacts, sock_dir, tmp_path, policy):
+    """The shared pool (128 MiB) is smaller than what the two clients put into it when
+    both are swapped out (2 x 120 MiB with the evict-all policy): the releasing client's
+    eviction has to wait for units that only the next holder's fetch returns -- hand-offs
+    must keep flowing (regression: two clients evicting at once once filled the pool and
+    waited for each other until the time-out, profiles/r01_call19_deadlock_diagnostics.json)."""
+    log, results = run_clients("ours", "ours", sock_dir, tmp_path, seconds=6.0,
+                               extra={"NVSHARE_POOL_MIB": 128, "NVSHARE_EVICT_POLICY": policy,
+                                      "NVSHARE_OOM_WAIT_MS": 8000})
+    check(results)
+    assert log.count("Sent DROP_LOCK") >= 4
+    for _, _, err in results:
+        assert "backing tier exhausted" not in err and "timed out" not in err
