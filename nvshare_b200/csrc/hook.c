@@ -37,6 +37,10 @@
  *     entry has a legacy and a per-thread forwarder) and answers
  *     "cuGetProcAddress" with the v2 hook when asked by a >= 12.0 runtime.
  *   - the allocation table is thread-safe (the reference's list is not).
+ *   - cuMemcpyHtoD/DtoH{,Async} on memory that is not on the GPU (swapped out or
+ *     never materialised) do not wait for the lock: they are served from / into
+ *     the pinned-host backing copy (host_io_bypass -> nvs_host_io, SURVEY 8f
+ *     rank 3).  NVSHARE_LOCKFREE_COPY=0 gates them like the reference does.
  */
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
