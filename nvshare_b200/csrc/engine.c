@@ -331,6 +331,8 @@ struct nvs_engine {
  * the previous holder is evicting for us it grows every few tens of ms, and a pressure
  * message sent then would be handled AFTER that eviction and evict the same amount again. */
 #define PRESSURE_AFTER_MS 300.0
+/* how long an eviction waits for units of a full shared pool before it pins an overflow arena */
+#define POOL_FULL_GRACE_MS 2000.0
 
 static double now_ms(void)
 {
@@ -647,7 +649,7 @@ static int pool_take(nvs_engine *e, struct pool *p, uint32_t n, uint64_t *addr)
 	for (struct arena *a = p->arenas; a; a = a->next)
 		if (arena_take(a, n, addr) == 0) {
 			p->used += (uint64_t)n * SLAB;
-			if (sp)
+			if (sp && a->shared)
 				sp->hdr->used_slabs += n;
 			rc = 0;
 			break;
@@ -672,7 +674,7 @@ static void pool_give(nvs_engine *e, struct pool *p, uint64_t addr, uint32_t n)
 		if (!a->shared && first < a->hint)
 			a->hint = first;
 		p->used -= (uint64_t)n * SLAB;
-		if (sp)
+		if (sp && a->shared)
 			sp->hdr->used_slabs -= n;
 		break;
 	}
@@ -863,6 +865,48 @@ static int host_pool_grow(nvs_engine *e)
 	pthread_cond_broadcast(&e->grow_cv);
 	return rc;
 }
+/*
+ * The shared pool is full and nobody has returned a unit for a while: rather than fail the
+ * hand-off, pin a private arena beside it.  (The pool's capacity is a budget for the common
+ * case -- one HBM covers any two clients -- not a reason to kill a third large client.)
+ * Called with e->mu held; drops it while pinning.  The arena goes to the END of the list, so
+ * the shared windows stay preferred, and is kept for reuse until the engine goes away.
+ */
+static int host_pool_overflow(nvs_engine *e)
+{
+	struct arena *a = arena_new(e->cfg.host_arena_bytes);
+	if (!a)
+		return NVS_E_HOST_OOM;
+	pthread_mutex_unlock(&e->mu);
+	void *p = NULL;
+	cpu_set_t saved;
+	const int pushed = near_push(e, &saved);
+	CUresult r = e->d.MemHostAlloc(&p, a->bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP);
+	near_pop(pushed, &saved);
+	CUdeviceptr dp = 0;
+	if (r == CUDA_SUCCESS && e->d.MemHostGetDevicePointer(&dp, p, 0) != CUDA_SUCCESS)
+		dp = (CUdeviceptr)(uintptr_t)p;
+	pthread_mutex_lock(&e->mu);
+	if (r != CUDA_SUCCESS) {
+		nvs_warn("engine: the shared pool is full and cuMemHostAlloc(%" PRIu64 " MiB) for an overflow arena failed: %s",
+			 a->bytes >> 20, cu_name(e, r));
+		free(a->bitmap);
+		free(a);
+		return NVS_E_HOST_OOM;
+	}
+	a->host_base = p;
+	a->dev_base = dp;
+	a->window = UINT32_MAX;
+	struct arena **pp = &e->host_pool.arenas;
+	while (*pp)
+		pp = &(*pp)->next;
+	*pp = a;
+	e->host_pool.bytes += a->bytes;
+	e->st.host_pool_bytes = e->host_pool.bytes;
+	nvs_debug("engine: shared pool full; pinned a private overflow arena of %" PRIu64 " MiB", a->bytes >> 20);
+	return 0;
+}
+
 /* Create one arena of peer HBM mapped into this context.  Called with e->mu held. */
 static int peer_pool_grow(nvs_engine *e, int pi)
 {
@@ -931,6 +975,7 @@ static int backing_assign(nvs_engine *e, struct chunk *c, int nowait)
 		}
 	}
 	double t0 = now_ms(), next_reap = 0;
+	int overflow_failed = 0;
 	while (pool_take(e, &e->host_pool, n, &c->backing) != 0) {
 		/* pool empty: wait for the background pinning, or pin inline */
 		int rc = host_pool_grow(e);
@@ -944,6 +989,11 @@ static int backing_assign(nvs_engine *e, struct chunk *c, int nowait)
 			next_reap = now_ms() + 500;
 			if (shp_reap_dead(e->shp))
 				continue;
+		}
+		if (now_ms() - t0 > POOL_FULL_GRACE_MS && !overflow_failed) {
+			if (host_pool_overflow(e) == 0)
+				continue;
+			overflow_failed = 1; /* no host memory either: keep waiting for units */
 		}
 		pthread_mutex_unlock(&e->mu);
 		usleep(1000);
@@ -1006,7 +1056,12 @@ static void shp_close(nvs_engine *e)
 		return;
 	for (struct arena *a = e->host_pool.arenas, *nx; a; a = nx) {
 		nx = a->next;
-		e->d.MemHostUnregister(a->host_base);
+		if (a->shared) {
+			e->d.MemHostUnregister(a->host_base);
+		} else { /* overflow arena (host_pool_overflow) */
+			e->d.MemFreeHost(a->host_base);
+			free(a->bitmap);
+		}
 		free(a);
 	}
 	e->host_pool.arenas = NULL;

@@ -230,3 +230,29 @@ def test_tight_backing_pool_makes_progress(artefacts, sock_dir, tmp_path, policy
     assert log.count("Sent DROP_LOCK") >= 4
     for _, _, err in results:
         assert "backing tier exhausted" not in err and "timed out" not in err
+
+
+def test_pool_too_small_for_three_clients_overflows_instead_of_failing(artefacts, sock_dir, tmp_path):
+    """Three multi-threaded clients of ~84 MiB on a 200 MiB "GPU" with the evict-all policy
+    keep two of them fully swapped out (168 MiB) -- more than the 128 MiB shared pool can
+    ever hold.  After a grace period the evicting client pins a private overflow arena
+    beside the pool; every hand-off completes and every byte survives."""
+    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
+    try:
+        d.ctl("-T", "1")
+        procs = []
+        for i in (1, 2, 3):
+            env = fake_env(total_mib=200, ledger=tmp_path / "ledger",
+                           extra={"NVSHARE_HOST_ARENA_MIB": 64, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_BATCH_MIB": 32,
+                                  "NVSHARE_DEBUG": 1, "NVSHARE_SOCK_DIR": sock_dir, "NVSHARE_POOL_MIB": 128,
+                                  "NVSHARE_EVICT_POLICY": "all", "NVSHARE_OOM_WAIT_MS": 15000})
+            env["LD_PRELOAD"] = preload("ours")
+            procs.append(subprocess.Popen([str(ORACLE / "mt_app"), "12", "8", str(i), "3", "1"], env=env,
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=180) for p in procs]
+    finally:
+        d.stop()
+    for p, (out, err) in zip(procs, outs):
+        assert p.returncode == 0 and re.search(r"RESULT PASS iters=\d+ mismatches=0", out), out + err[-2500:]
+    assert sum(err.count("pinned a private overflow arena") for _, err in outs) >= 1
+    assert d.read_log().count("Sent DROP_LOCK") >= 4
