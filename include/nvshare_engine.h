@@ -25,6 +25,10 @@
  *                    pages in; here it runs after cuda_sync_context() on
  *                    DROP_LOCK (src/client.c:308-317) and on early release
  *                    (src/client.c:472-476)
+ *   nvs_evict_best_effort
+ *                    no counterpart: eviction as a favour to the client that is
+ *                    mapping (memory-pressure hint on the wire); never waits for
+ *                    backing space
  *   nvs_host_io      src/hook.c:878-938 cuMemcpyDtoH/HtoD{,Async} hook bodies, for the
  *                    case the reference cannot have: the device range is not on
  *                    the GPU at all (swapped out / never materialised), so the
