@@ -469,7 +469,8 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	if (peers && *peers) {
 		char buf[128];
 		snprintf(buf, sizeof(buf), "%s", peers);
-		for (char *tok = strtok(buf, ","); tok && cfg->n_peers < NVS_MAX_PEERS; tok = strtok(NULL, ","))
+		char *save = NULL; /* strtok_r: this library lives inside arbitrary applications */
+		for (char *tok = strtok_r(buf, ",", &save); tok && cfg->n_peers < NVS_MAX_PEERS; tok = strtok_r(NULL, ",", &save))
 			cfg->peers[cfg->n_peers++] = atoi(tok);
 	}
 	return 0;
@@ -728,7 +729,8 @@ static void report_placement(nvs_engine *e, struct shpool *sp, uint32_t window)
 		if (strncmp(line, want, strlen(want)) != 0)
 			continue;
 		unsigned long long pages[8] = {0};
-		for (char *t = strtok(line, " \n"); t; t = strtok(NULL, " \n")) {
+		char *save = NULL;
+		for (char *t = strtok_r(line, " \n", &save); t; t = strtok_r(NULL, " \n", &save)) {
 			unsigned node;
 			unsigned long long n;
 			if (sscanf(t, "N%u=%llu", &node, &n) == 2 && node < 8)
