@@ -142,3 +142,88 @@ def test_any_interleaving_preserves_contents(fake, script, elide, chunk_slabs):
     finally:
         e.close()
     assert fake.fake_cuda_phys_used() == base          # every physical byte went back to the "driver"
+
+
+ops_tight = st.lists(
+    st.one_of(
+        st.tuples(st.just("alloc"), st.integers(1, 6), st.booleans()),
+        st.tuples(st.just("write"), st.integers(0, 7), st.integers(0, 255)),
+        st.tuples(st.just("const"), st.integers(0, 7), st.integers(0, 255)),
+        st.tuples(st.just("evict_be"), st.integers(0, 12), st.just(0)),         # best effort: 0 = all, else MiB
+        st.tuples(st.just("fetch"), st.just(0), st.just(0)),
+        st.tuples(st.just("free"), st.integers(0, 7), st.just(0)),
+        st.tuples(st.just("hio_r"), st.integers(0, 7), st.integers(0, 10**6)),
+    ),
+    min_size=4, max_size=24)
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(script=ops_tight, elide=st.booleans(), chunk_slabs=st.sampled_from([1, 2, 4]))
+def test_best_effort_evictions_into_a_tight_shared_pool(fake, tmp_path_factory, script, elide, chunk_slabs):
+    """Same model, but the backing store is a shared pool of only 8 slabs and every eviction
+    is the best-effort flavour: it may move less than asked (never more than the pool holds),
+    never blocks, and whatever it leaves behind stays resident and intact."""
+    import time
+    from nvshare_b200 import engine as E
+    base = fake.fake_cuda_phys_used()
+    pool = tmp_path_factory.mktemp("pool") / "pool"
+    e = E.Engine(chunk_bytes=chunk_slabs * SLAB, host_arena_bytes=16 * MiB, batch_bytes=8 * MiB, oom_wait_ms=5000,
+                 elide_constant=int(elide), prepin=0, shared_pool_path=str(pool), shared_pool_bytes=16 * MiB)
+    model, order = {}, []
+    try:
+        e.fetch_all()
+        for op, a, b in script:
+            if op == "alloc":
+                size = a * SLAB - (99 if b and a > 1 else 0)
+                p = e.alloc(size)
+                e.fetch_all()
+                data = np.full(size, 5 if b else 0, dtype=np.uint8)
+                view(p, size)[:] = data
+                model[p] = data
+                order.append(p)
+            elif op in ("write", "const") and order:
+                p = order[a % len(order)]
+                e.fetch_all()
+                n = len(model[p])
+                if op == "write":
+                    model[p][:] = np.random.default_rng(b).integers(0, 256, n, dtype=np.uint8)
+                else:
+                    s0 = (b % max(1, n // SLAB)) * SLAB
+                    model[p][s0:min(n, s0 + SLAB)] = b
+                view(p, n)[:] = model[p]
+            elif op == "evict_be":
+                t0 = time.time()
+                rep = e.evict_best_effort(a * MiB)
+                assert time.time() - t0 < 1.0                            # never the 2 s grace period, never oom_wait
+                assert e.stats()["host_pool_used"] <= 16 * MiB
+                assert rep["bytes"] <= 16 * MiB
+            elif op == "fetch":
+                e.fetch_all()
+            elif op == "free" and order:
+                p = order.pop(a % len(order))
+                e.free(p)
+                del model[p]
+            elif op == "hio_r" and order:
+                p = order[a % len(order)]
+                n = len(model[p])
+                lo = (b * 7919) % n
+                ln = 1 + (b * 104729) % min(n - lo, 3 * MiB)
+                dst = np.full(ln, 0xEE, dtype=np.uint8)
+                rc = e.host_io(p + lo, dst.ctypes.data, ln, False)
+                assert rc in (0, -9)
+                if rc == 0:
+                    assert np.array_equal(dst, model[p][lo:lo + ln])
+            st_ = e.stats()
+            va = sum((len(d) + SLAB - 1) // SLAB * SLAB for d in model.values())
+            assert st_["va_bytes"] == va
+            assert st_["resident_bytes"] + st_["swapped_bytes"] + st_["unbacked_bytes"] == va
+        e.fetch_all()
+        for p, want in model.items():
+            assert np.array_equal(view(p, len(want)), want)
+        for p in list(model):
+            e.free(p)
+        st_ = e.stats()
+        assert st_["host_pool_used"] == 0 and st_["va_bytes"] == 0
+    finally:
+        e.close()
+    assert fake.fake_cuda_phys_used() == base
