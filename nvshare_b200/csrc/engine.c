@@ -325,6 +325,7 @@ struct nvs_engine {
 	 * backing pages run there, so that the DMA does not cross the socket interconnect */
 	cpu_set_t near_cpus;
 	int near_cpus_valid;
+	double pool_grace_ms; /* POOL_FULL_GRACE_MS, or NVSHARE_POOL_GRACE_MS */
 };
 #define N_COUNTERS 1024u /* per stream; the scan stream uses the second half of the array */
 /* Memory pressure is only signalled once the free HBM has not grown for this long: while
@@ -992,7 +993,7 @@ static int backing_assign(nvs_engine *e, struct chunk *c, int nowait)
 			if (shp_reap_dead(e->shp))
 				continue;
 		}
-		if (now_ms() - t0 > POOL_FULL_GRACE_MS && !overflow_failed) {
+		if (now_ms() - t0 >= e->pool_grace_ms && !overflow_failed) {
 			if (host_pool_overflow(e) == 0)
 				continue;
 			overflow_failed = 1; /* no host memory either: keep waiting for units */
@@ -2496,6 +2497,7 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	e->device = e->cfg.device >= 0 ? e->cfg.device : (int)dev;
 	CK(e, e->d.DeviceGetAttribute(&e->n_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
 	numa_init(e, dev, resolve);
+	e->pool_grace_ms = (double)env_u64("NVSHARE_POOL_GRACE_MS", (uint64_t)POOL_FULL_GRACE_MS);
 
 	if (e->d.ModuleLoadData(&e->module, nvs_slab_copy_cubin) != CUDA_SUCCESS ||
 	    e->d.ModuleGetFunction(&e->fn_tma, e->module, "nvs_slab_copy_tma") != CUDA_SUCCESS ||

@@ -50,10 +50,14 @@ ops = st.lists(
 @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(script=ops, elide=st.booleans(), chunk_slabs=st.sampled_from([1, 2, 4]))
 def test_any_interleaving_preserves_contents(fake, script, elide, chunk_slabs):
+    _run_model(fake, script, elide, chunk_slabs)
+
+
+def _run_model(fake, script, elide, chunk_slabs, **engine_kw):
     from nvshare_b200 import engine as E
     base = fake.fake_cuda_phys_used()
-    e = E.Engine(chunk_bytes=chunk_slabs * SLAB, host_arena_bytes=16 * MiB, batch_bytes=8 * MiB, oom_wait_ms=200,
-                 elide_constant=int(elide), prepin=0)
+    e = E.Engine(chunk_bytes=chunk_slabs * SLAB, host_arena_bytes=16 * MiB, batch_bytes=8 * MiB,
+                 oom_wait_ms=200 if not engine_kw else 5000, elide_constant=int(elide), prepin=0, **engine_kw)
     model = {}          # ptr -> expected bytes
     order = []
     resident = True     # what the owner believes: we fetch before touching memory
@@ -142,6 +146,17 @@ def test_any_interleaving_preserves_contents(fake, script, elide, chunk_slabs):
     finally:
         e.close()
     assert fake.fake_cuda_phys_used() == base          # every physical byte went back to the "driver"
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(script=ops, elide=st.booleans(), chunk_slabs=st.sampled_from([1, 2, 4]))
+def test_any_interleaving_with_overflow_arenas(fake, tmp_path_factory, monkeypatch, script, elide, chunk_slabs):
+    """The first property again, with a shared pool of 8 slabs that is far too small and no
+    grace period: ordinary evictions spill into private overflow arenas, so backing units
+    come from both kinds of arena (and host copies read and write both)."""
+    monkeypatch.setenv("NVSHARE_POOL_GRACE_MS", "0")
+    pool = tmp_path_factory.mktemp("pool") / "pool"
+    _run_model(fake, script, elide, chunk_slabs, shared_pool_path=str(pool), shared_pool_bytes=16 * MiB)
 
 
 ops_tight = st.lists(
