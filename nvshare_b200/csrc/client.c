@@ -330,13 +330,16 @@ static void *message_thread(void *arg)
 		case NVS_DROP_LOCK: {
 			in.data[NVS_MSG_DATA_LEN - 1] = '\0';
 			nvs_debug("Received %s %s", nvs_msg_type_name(in.type), in.data);
-			if (own_lock && scheduler_on) {
-				unsigned waiters = 0;
-				unsigned long long need = 0;
-				int have = sscanf(in.data, "w%un%llu", &waiters, &need) == 2;
-				release_lock_and_evict(have, waiters, need);
-			} else if (!own_lock && in.data[0] == NVS_HINT_EVICT_PREFIX) {
-				/* memory pressure from the client that is mapping: get out of its way */
+			if (in.data[0] == NVS_HINT_EVICT_PREFIX) {
+				/* Memory pressure forwarded by the daemon: never a quantum expiry, whoever holds the
+				 * lock.  A frame queued while we were busy (a long fetch) may only be looked at once
+				 * we are the holder: it is stale then -- the client that pressed has since released,
+				 * or is waiting behind us and will be served when our quantum ends. */
+				if (own_lock) {
+					nvs_debug("pressure hint reached the lock holder: ignored");
+					break;
+				}
+				/* the client that is mapping is short of HBM: get out of its way */
 				uint64_t mib = strtoull(in.data + 1, NULL, 10);
 				sync_app_context();
 				do_evict_as_a_favour(mib ? mib + evict_margin_mib() : EVICT_ALL);
@@ -348,6 +351,11 @@ static void *message_thread(void *arg)
 						 dp.nonresident_mib ? dp.nonresident_mib() : 0);
 					send_msg(NVS_REQ_LOCK, hint);
 				}
+			} else if (own_lock && scheduler_on) {
+				unsigned waiters = 0;
+				unsigned long long need = 0;
+				int have = sscanf(in.data, "w%un%llu", &waiters, &need) == 2;
+				release_lock_and_evict(have, waiters, need);
 			}
 			break;
 		}

@@ -73,6 +73,7 @@ struct drv {
 	CUresult (*CtxPushCurrent)(CUcontext);
 	CUresult (*CtxPopCurrent)(CUcontext *);
 	CUresult (*CtxGetDevice)(CUdevice *);
+	CUresult (*CtxSynchronize)(void);
 	CUresult (*DeviceGetAttribute)(int *, int, CUdevice);
 	CUresult (*DeviceCanAccessPeer)(int *, CUdevice, CUdevice);
 	CUresult (*MemGetInfo)(size_t *, size_t *);
@@ -121,6 +122,7 @@ static const struct {
 	S(CtxPushCurrent, "cuCtxPushCurrent_v2"),
 	S(CtxPopCurrent, "cuCtxPopCurrent_v2"),
 	S(CtxGetDevice, "cuCtxGetDevice"),
+	S(CtxSynchronize, "cuCtxSynchronize"),
 	S(DeviceGetAttribute, "cuDeviceGetAttribute"),
 	S(DeviceCanAccessPeer, "cuDeviceCanAccessPeer"),
 	S(MemGetInfo, "cuMemGetInfo_v2"),
@@ -226,6 +228,7 @@ struct arena {
 #define SHP_MAGIC 0x6e767368504f4f4cull /* "nvshPOOL" */
 #define SHP_HDR_BYTES (8ull << 20)
 #define SHP_MAX_SLABS (1u << 19) /* 1 TiB */
+#define SHP_VERSION 2
 
 struct shp_hdr {
 	volatile uint64_t magic;
@@ -1132,13 +1135,31 @@ static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
 			return -1;
 		}
 	}
-	sp->fd = open(path, O_RDWR | O_CREAT | O_EXCL | O_CLOEXEC, 0600);
+	sp->fd = open(path, O_RDWR | O_CREAT | O_EXCL | O_CLOEXEC | O_NOFOLLOW, 0600);
 	if (sp->fd < 0 && errno == EEXIST) {
 		creator = 0;
-		sp->fd = open(path, O_RDWR | O_CLOEXEC);
+		sp->fd = open(path, O_RDWR | O_CLOEXEC | O_NOFOLLOW);
 	}
 	if (sp->fd < 0)
 		goto fail;
+	{
+		/* The name is predictable and evicted GPU memory ends up in this file: only ever attach
+		 * to a regular file that this very user created with mode 0600 (anybody able to plant
+		 * such a file can already read our memory).  Otherwise: private pool. */
+		struct stat st;
+		if (creator)
+			(void)fchmod(sp->fd, 0600); /* whatever the umask said */
+		if (fstat(sp->fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_uid != geteuid() ||
+		    (st.st_mode & 07777) != 0600 || st.st_nlink != 1) {
+			nvs_warn("engine: %s is not a pool file of ours (owner %d, mode %o): not using it", path,
+				 (int)st.st_uid, (unsigned)(st.st_mode & 07777));
+			close(sp->fd);
+			sp->fd = -1;
+			creator = 0; /* it is somebody else's: do not unlink it either */
+			errno = EPERM;
+			goto fail;
+		}
+	}
 	if (creator && ftruncate(sp->fd, (off_t)(SHP_HDR_BYTES + cap_slabs * SLAB)) != 0)
 		goto fail;
 	if (!creator) {
@@ -1165,15 +1186,17 @@ static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
 		pthread_mutexattr_setrobust(&at, PTHREAD_MUTEX_ROBUST);
 		pthread_mutex_init(&sp->hdr->mu, &at);
 		pthread_mutexattr_destroy(&at);
-		sp->hdr->version = 1;
+		sp->hdr->version = SHP_VERSION;
 		sp->hdr->window_slabs = window_slabs;
 		sp->hdr->capacity_slabs = cap_slabs;
 		__atomic_store_n(&sp->hdr->magic, SHP_MAGIC, __ATOMIC_RELEASE);
 	} else {
 		for (int i = 0; i < 5000 && __atomic_load_n(&sp->hdr->magic, __ATOMIC_ACQUIRE) != SHP_MAGIC; ++i)
 			usleep(1000);
-		if (sp->hdr->magic != SHP_MAGIC || sp->hdr->version != 1 || sp->hdr->capacity_slabs != cap_slabs ||
-		    sp->hdr->window_slabs == 0 || (uint64_t)sp->hdr->window_slabs * SLAB < e->cfg.chunk_bytes) {
+		/* every field that later indexes the bitmap / owners arrays is checked against the file */
+		if (sp->hdr->magic != SHP_MAGIC || sp->hdr->version != SHP_VERSION || sp->hdr->capacity_slabs != cap_slabs ||
+		    cap_slabs > SHP_MAX_SLABS || sp->hdr->window_slabs == 0 || cap_slabs % sp->hdr->window_slabs != 0 ||
+		    sp->hdr->used_slabs > cap_slabs || (uint64_t)sp->hdr->window_slabs * SLAB < e->cfg.chunk_bytes) {
 			nvs_warn("engine: shared pool %s is not usable by this client (geometry/version)", path);
 			munmap(m, SHP_HDR_BYTES + cap_slabs * SLAB);
 			sp->hdr = NULL;
@@ -2105,6 +2128,16 @@ int nvs_free_sized(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes)
 		}
 		e->st.passthrough_bytes -= a->req_bytes;
 	} else {
+		/* cuMemFree synchronises implicitly (which is what the reference's hook ends up calling,
+		 * src/hook.c:691); cuMemUnmap / cuMemRelease are not documented to.  Work of the application
+		 * that is still in flight must not find its pages gone -- or handed to another client. */
+		for (uint32_t i = 0; i < a->n_chunks; ++i)
+			if (a->chunks[i].state == CH_RESIDENT) {
+				CUresult r = e->d.CtxSynchronize();
+				if (r != CUDA_SUCCESS && !is_shutdown_error(r))
+					nvs_warn("engine: cuCtxSynchronize before unmapping returned %s", cu_name(e, r));
+				break;
+			}
 		for (uint32_t i = 0; i < a->n_chunks; ++i) {
 			struct chunk *c = &a->chunks[i];
 			if (c->state == CH_RESIDENT)

@@ -534,7 +534,7 @@ static void ensure_init(void)
 static nvs_engine *engine_get(void)
 {
 	pthread_mutex_lock(&engine_mu);
-	if (!engine) {
+	if (!engine && !uvm_mode) {
 		CUcontext ctx = NULL;
 		if (real_cuCtxGetCurrent(&ctx) == CUDA_SUCCESS && ctx != NULL) {
 			nvs_engine_config cfg;
@@ -547,10 +547,20 @@ static nvs_engine *engine_get(void)
 			if (!(pool && strcmp(pool, "private") == 0) && nvs_pool_path(pool_path, sizeof(pool_path)) == 0)
 				cfg.shared_pool_path = pool_path;
 			int rc = nvs_engine_create(&cfg, &engine);
-			if (rc != 0)
+			if (rc == NVS_E_NO_KERNEL || rc == NVS_E_NO_DRIVER) {
+				/* not a B200 (only the sm_100a image is embedded), or a driver without the VMM entry
+				 * points: the drop-in still has to work, so this process runs on the reference's
+				 * managed-memory mechanism (cuMemAllocManaged + UVM faults) like NVSHARE_ENGINE=uvm */
+				nvs_warn("swap engine unavailable on this GPU/driver (%s): falling back to the reference's "
+					 "managed-memory mechanism for this process", nvs_strerror(rc));
+				engine = NULL;
+				uvm_mode = 1;
+			} else if (rc != 0) {
 				nvs_fatal("swap engine could not start (%s); set NVSHARE_ENGINE=uvm to run with "
 					  "the reference's managed-memory mechanism instead", nvs_strerror(rc));
-			nvs_set_resident_mode(engine, holds_lock);
+			} else {
+				nvs_set_resident_mode(engine, holds_lock);
+			}
 		}
 	}
 	nvs_engine *e = engine;
@@ -701,7 +711,7 @@ CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize)
 
 	nvs_debug("cuMemAlloc requested %zu bytes", bytesize);
 	CUresult r;
-	nvs_engine *e = uvm_mode ? NULL : engine_get();
+	nvs_engine *e = uvm_mode ? NULL : engine_get(); /* may switch uvm_mode on (no usable engine here) */
 	if (uvm_mode) {
 		r = real_cuMemAllocManaged(dptr, bytesize, CU_MEM_ATTACH_GLOBAL);
 		warn_if_error(r, "cuMemAllocManaged");

@@ -44,6 +44,8 @@
 #include <time.h>
 #include <unistd.h>
 #include <sys/epoll.h>
+#include <sys/ioctl.h>
+#include <linux/sockios.h>
 #include <sys/random.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
@@ -161,6 +163,24 @@ static void drop_client(struct client *c)
 	c->prev = NULL;
 	c->next = graveyard;
 	graveyard = c;
+}
+
+/*
+ * An advisory frame (the forwarded memory-pressure hint) for a client that may be busy for
+ * seconds inside a fetch or an eviction and not reading its socket.  Unlike the frames of
+ * the reference protocol it may simply be dropped: the client under pressure repeats it
+ * every second while it is stalled.  So it is only sent when the peer has consumed
+ * everything sent before (nothing of ours is still queued on its socket) -- which both
+ * coalesces the hints and keeps a slow but live client from ever filling its buffer with
+ * them and being mistaken for a dead one.  Returns 0 sent, 1 skipped, -1 peer dead.
+ */
+static int send_frame(struct client *c, const struct nvs_msg *m);
+static int send_advisory(struct client *c, const struct nvs_msg *m)
+{
+	int queued = 0;
+	if (ioctl(c->fd, SIOCOUTQ, &queued) == 0 && queued > 0)
+		return 1;
+	return send_frame(c, m);
 }
 
 /* Strict like the reference: any failure to push a whole frame means the peer is dead. */
@@ -350,7 +370,12 @@ static void on_message(struct client *c, const struct nvs_msg *in)
 			return;
 		if (in->data[0] == NVS_HINT_PRESSURE_PREFIX) {
 			/* the sender cannot map its working set: ask everybody else to get out of HBM.
-			 * Reference clients ignore a DROP_LOCK they do not hold the lock for. */
+			 * Reference clients ignore a DROP_LOCK they do not hold the lock for.
+			 * Only the client that has (been granted) the lock is in a position to press. */
+			if (c != q_head) {
+				nvs_debug("pressure hint from %s, which does not hold the lock: ignored", ids);
+				return;
+			}
 			struct nvs_msg m;
 			memset(&m, 0, sizeof(m));
 			m.type = NVS_DROP_LOCK;
@@ -361,7 +386,7 @@ static void on_message(struct client *c, const struct nvs_msg *in)
 				nx = o->next;
 				if (o == c || o->id == NVS_UNREGISTERED_ID)
 					continue;
-				if (send_frame(o, &m) != 0)
+				if (send_advisory(o, &m) < 0)
 					drop_client(o);
 			}
 			return;

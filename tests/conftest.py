@@ -68,6 +68,11 @@ def default_sock_lock():
 def pytest_collection_modifyitems(config, items):
     have_ref = build.reference_available() or Path("/root/reference/src/hook.c").exists()
     skip_ref = pytest.mark.skip(reason="compiled reference (oracle/_ref) not available")
+    # `pytest tests` on a box without a GPU: the gpu-marked tests are skipped, not errors
+    have_gpu = os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0")
+    skip_gpu = pytest.mark.skip(reason="needs a real GPU (no /dev/nvidia* here)")
     for item in items:
         if "reference" in item.keywords and not have_ref:
             item.add_marker(skip_ref)
+        if "gpu" in item.keywords and not have_gpu:
+            item.add_marker(skip_gpu)
