@@ -35,7 +35,8 @@
  *                    copy is host memory -> pinned host backing and needs
  *                    neither the GPU nor its lock
  *   nvs_get_stats    no counterpart (the reference has no counters)
- *   nvs_copy_slabs / nvs_pattern_fill / nvs_pattern_verify
+ *   nvs_touch        no counterpart (recency hint from the hooked cuMemcpy / cuMemset calls)
+ *   nvs_copy_slabs / nvs_scan_slabs / nvs_pattern_fill / nvs_pattern_verify
  *                    no counterpart: raw access to the sm_100a kernels for the
  *                    parity tests and the roofline measurement
  *
@@ -110,6 +111,14 @@ typedef struct nvs_engine_config {
 	/* fetch maps HBM in bursts of this many bytes once that much is free, instead of
 	 * chunk by chunk as it trickles in from the evicting process (8 GiB; probe K, calls 11-12) */
 	uint64_t burst_bytes;
+	/* 1 = keep the backing copy of a chunk after it has been fetched (as long as the pool has
+	 * room: retained units are the first to be reclaimed), record a 128-bit hash per slab when a
+	 * copy is written, and at the next eviction do not copy slabs whose hash is unchanged */
+	uint32_t retain;
+	/* copy variants for the peer-HBM tier (NVLink); evict_variant / fetch_variant above apply to
+	 * the pinned-host tier (PCIe), where the copy engines beat any SM kernel by the TLP size */
+	uint32_t peer_evict_variant;
+	uint32_t peer_fetch_variant;
 } nvs_engine_config;
 
 typedef struct nvs_xfer_report {
@@ -124,6 +133,12 @@ typedef struct nvs_xfer_report {
 	uint64_t host_bytes;   /* of `bytes`, how much went to / came from the host tier  */
 	uint64_t peer_bytes;   /* ... the peer-HBM tier                                   */
 	uint64_t elided_bytes; /* same-filled slabs: swapped without crossing the link    */
+	uint64_t clean_bytes;  /* evict: slabs whose retained backing copy was still valid
+	                          (hash unchanged): swapped out without being copied      */
+	uint64_t ce_calls;     /* cuMemcpyAsync calls (copy engines); `launches` counts
+	                          sm_100a kernel launches only                            */
+	uint64_t scanned_bytes; /* bytes the scan/hash kernel read from HBM                */
+	double   scan_ms;      /* CUDA-event time of the scan/hash launches               */
 } nvs_xfer_report;
 
 typedef struct nvs_stats {
@@ -142,6 +157,10 @@ typedef struct nvs_stats {
 	uint64_t evicted_bytes_total, fetched_bytes_total;
 	uint64_t kernel_launches_total; /* nvs_slab_copy_* launches since creation       */
 	uint64_t host_io_bytes_total;   /* nvs_host_io: bytes served from / into the backing copy */
+	uint64_t retained_bytes;        /* resident chunks whose backing copy is being kept        */
+	uint64_t clean_skipped_bytes_total; /* eviction bytes that did not have to be copied       */
+	uint64_t stolen_slabs_total;    /* retained units this engine took over from other chunks  */
+	uint64_t ce_calls_total;        /* cuMemcpyAsync calls issued by evict / fetch             */
 } nvs_stats;
 
 /* Fill *cfg with defaults, then apply NVSHARE_* environment overrides
@@ -192,10 +211,25 @@ int nvs_evict_best_effort(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *re
 
 int nvs_get_stats(nvs_engine *e, nvs_stats *out);
 
+/* The application is about to write [dptr, dptr+bytes) from the host side of the API (a
+ * cuMemcpy* / cuMemset* destination seen by the hook).  Only a hint: chunks touched recently
+ * are the last to be chosen by a partial eviction (they are the ones most likely to differ
+ * from their retained backing copy).  No reference counterpart. */
+int nvs_touch(nvs_engine *e, uint64_t dptr, uint64_t bytes);
+
 /* Raw kernel access (parity tests, roofline).  All addresses must be
  * device-accessible in the engine's context.  *ms = CUDA-event time. */
 int nvs_copy_slabs(nvs_engine *e, const nvs_copy_desc *descs, uint32_t n, uint32_t variant,
 		   uint32_t grid, float *ms);
+/* What the scan kernel reports per slab (nvs_slab_scan in slab_copy.cu). */
+typedef struct nvs_scan_out {
+	uint64_t value;    /* the slab's first 64-bit word                                  */
+	uint64_t is_const; /* 1: every 64-bit word of the slab equals `value`               */
+	uint64_t h0, h1;   /* 128-bit content hash (0, 0 when not asked for)                */
+} nvs_scan_out;
+/* Run the scan/hash kernel over descs[i].src / .bytes (dst ignored); out[n]. */
+int nvs_scan_slabs(nvs_engine *e, const nvs_copy_desc *descs, uint32_t n, int want_hash, nvs_scan_out *out,
+		   float *ms);
 int nvs_pattern_fill(nvs_engine *e, uint64_t addr, uint64_t n_words, uint64_t first_index, uint64_t seed);
 int nvs_pattern_verify(nvs_engine *e, uint64_t addr, uint64_t n_words, uint64_t first_index, uint64_t seed,
 		       uint64_t *mismatches);

@@ -184,7 +184,31 @@ struct chunk {
 	uint32_t n_const;
 	uint64_t cmask[MAX_CHUNK_SLABS / 64];
 	uint64_t *cvals;
+	/* Clean-slab skip.  `backing` may outlive a fetch (`retained`): the pool keeps the
+	 * units marked as reclaimable, anybody short of units may take them over, and the
+	 * owner finds out when it validates the run under the pool lock (backing_reclaim).
+	 * hash[i] is the content hash of the bytes slab i has in the backing, valid where
+	 * bvalid has bit i set; an eviction copies slab i only if its current hash differs. */
+	uint8_t retained;   /* RESIDENT with a backing copy that MAY still be ours             */
+	uint8_t stable;     /* ST_UNKNOWN / ST_STABLE (found clean last time) / ST_VOLATILE    */
+	uint8_t scanned;    /* this eviction has already scanned it: cpmask / nh / cmask valid */
+	uint8_t had_backing; /* ... and it went into the scan with a valid backing copy        */
+	uint8_t volatile_skips; /* fetches since a volatile chunk's backing was last retained  */
+	uint32_t btag;      /* tag written next to our units in the pool: proves they are still ours */
+	uint64_t touch;     /* engine touch clock of the last host-side write (nvs_touch)      */
+	uint64_t est_copy;  /* bytes this eviction would have to copy (from the scan)          */
+	uint64_t bvalid[MAX_CHUNK_SLABS / 64];
+	uint64_t cpmask[MAX_CHUNK_SLABS / 64]; /* slabs this eviction must copy               */
+	struct slab_hash *hash; /* [MAX_CHUNK_SLABS], lazily allocated                         */
+	struct slab_hash *nh;   /* hashes of the current contents, during an eviction only     */
 };
+
+struct slab_hash {
+	uint64_t h0, h1;
+};
+enum { ST_UNKNOWN = 0, ST_STABLE = 1, ST_VOLATILE = 2 };
+/* a volatile chunk's backing is kept again every so many fetches, to notice that it calmed down */
+#define VOLATILE_REPROBE 8
 
 struct alloc {
 	uint64_t va;
@@ -206,7 +230,9 @@ struct arena {
 	uint32_t hint;      /* private pool: first slab worth scanning     */
 	uint64_t *bitmap;   /* 1 = slab in use                             */
 	int32_t *owners;    /* shared pool only: pid owning each slab      */
-	int shared;         /* bitmap/owners live in the shared pool header */
+	uint8_t *rstate;    /* per slab: 0 = free or live, RS_* = retained (reclaimable) */
+	uint32_t *ctag;     /* per slab: tag of the chunk the unit was handed to         */
+	int shared;         /* bitmap/owners/rstate/ctag live in the shared pool header  */
 	uint64_t bit_base;  /* index of this arena's slab 0 in `bitmap` / `owners` (shared pool: global) */
 	uint32_t window;    /* shared pool only: index of this 1 GiB window */
 	struct arena *next;
@@ -239,7 +265,10 @@ struct shp_hdr {
 	pthread_mutex_t mu;
 	uint64_t bitmap[SHP_MAX_SLABS / 64];
 	int32_t owners[SHP_MAX_SLABS];
+	uint8_t rstate[SHP_MAX_SLABS]; /* RS_*: the unit holds a copy its owner can do without */
+	uint32_t ctag[SHP_MAX_SLABS];
 };
+enum { RS_NONE = 0, RS_PLAIN = 1, RS_STABLE = 2 }; /* reclaim order: free, then PLAIN, then STABLE */
 _Static_assert(sizeof(struct shp_hdr) <= SHP_HDR_BYTES, "shared pool header too large");
 
 struct shpool {
@@ -260,9 +289,12 @@ struct pool {
 
 struct scan_result;
 struct slot {
-	nvs_copy_desc *descs; /* pinned, device-mapped */
+	nvs_copy_desc *descs; /* pinned, device-mapped: what the sm_100a copy kernel consumes */
 	uint64_t descs_dev;
 	uint32_t n_descs, cap_descs;
+	nvs_copy_desc *ce;    /* plain host memory: runs handed to the copy engines            */
+	uint32_t n_ce, cap_ce;
+	int peer_traffic;     /* the kernel list touches peer HBM: wants the NVLink-sized grid */
 	struct chunk **chunks;
 	uint32_t n_chunks, cap_chunks;
 	CUevent begin, done; /* around this batch's copy: device time of the copy alone */
@@ -278,7 +310,9 @@ struct slot {
 struct scan_result {
 	uint64_t value;
 	uint64_t is_const;
+	uint64_t h0, h1;
 };
+_Static_assert(sizeof(struct scan_result) == sizeof(nvs_scan_out), "scan result layout is part of the C-ABI");
 
 #define HASH_BITS 12
 #define HASH_SIZE (1u << HASH_BITS)
@@ -293,8 +327,10 @@ struct nvs_engine {
 	CUfunction fn_tma, fn_ldg, fn_fill, fn_verify, fn_scan, fn_splat;
 	CUstream stream;
 	CUstream scan_stream; /* the scan of batch b+1 runs beside the copy of batch b */
-	CUevent scan_done;
+	CUevent scan_done, scan_begin;
 	uint32_t scan_counter_next;
+	uint64_t touch_clock;
+	uint32_t tag_next;
 	CUevent ev_begin, ev_end;
 	CUdeviceptr counters; /* u32[N_COUNTERS], device memory */
 	uint32_t counter_next;
@@ -305,6 +341,8 @@ struct nvs_engine {
 	pthread_mutex_t mu;     /* inner: table, pools, stats (shared with the pinning thread) */
 	struct alloc *buckets[HASH_SIZE];
 	struct alloc *head, *tail;
+	struct alloc **by_va; /* every allocation, sorted by address: range lookups in O(log n) */
+	size_t n_by_va, cap_by_va;
 	struct pool host_pool;
 	struct shpool *shp; /* non-NULL: host_pool's arenas are windows of the shared pool */
 	struct pool peer_pools[NVS_MAX_PEERS];
@@ -385,7 +423,7 @@ static int is_shutdown_error(CUresult r)
 
 const char *nvs_engine_version(void)
 {
-	return "nvshare_b200 engine r1 (sm_100a slab copy: tma|ldg|ce)";
+	return "nvshare_b200 engine r2 (sm_100a: slab copy tma|ldg, scan+hash, splat; copy engines for the PCIe tier)";
 }
 
 const char *nvs_strerror(int rc)
@@ -443,15 +481,20 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->batch_bytes = env_u64("NVSHARE_BATCH_MIB", 1024) << 20;
 	cfg->burst_bytes = env_u64("NVSHARE_BURST_MIB", 8192) << 20;
 	cfg->host_arena_bytes = env_u64("NVSHARE_HOST_ARENA_MIB", 1024) << 20;
-	cfg->evict_variant = parse_variant(getenv("NVSHARE_EVICT_VARIANT"),
-					   parse_variant(getenv("NVSHARE_COPY_VARIANT"), NVS_COPY_TMA));
-	/* Fetch runs in the process that is being granted the lock, usually WHILE the
-	 * previous holder's eviction kernel is still running in another process.  The
-	 * GPU time-slices compute work of different processes, so kernel+kernel gets
-	 * 22+22 GB/s, kernel(evict)+copy-engine(fetch) 49+44 GB/s (B200, probe G):
-	 * fetch defaults to the copy engines, eviction to the sm_100a kernel. */
-	cfg->fetch_variant = parse_variant(getenv("NVSHARE_FETCH_VARIANT"),
-					   parse_variant(getenv("NVSHARE_COPY_VARIANT"), NVS_COPY_CE));
+	/* Pinned-host tier (PCIe Gen5 x16), B200 probes D and G: the copy engines move 55.4 (out) /
+	 * 55.2 (in) GB/s alone and 50.2 + 48.7 with both directions busy in two processes; the
+	 * sm_100a kernel 52.7 / 51.5 alone (SM-issued transfers travel as 128-byte TLPs) and, being
+	 * compute work, is time-sliced against the other process's kernel (22 + 22).  So both
+	 * directions of this tier run on the copy engines; the SMs scan, hash and splat.
+	 * Peer tier (NVLink 5): the kernel (3.3 TB/s device-to-device against 0.5 TB/s of
+	 * per-chunk cuMemcpyAsync) for both directions.
+	 * NVSHARE_COPY_VARIANT sets all four; the specific variables override it. */
+	const char *all = getenv("NVSHARE_COPY_VARIANT");
+	cfg->evict_variant = parse_variant(getenv("NVSHARE_EVICT_VARIANT"), parse_variant(all, NVS_COPY_CE));
+	cfg->fetch_variant = parse_variant(getenv("NVSHARE_FETCH_VARIANT"), parse_variant(all, NVS_COPY_CE));
+	cfg->peer_evict_variant = parse_variant(getenv("NVSHARE_PEER_EVICT_VARIANT"), parse_variant(all, NVS_COPY_TMA));
+	cfg->peer_fetch_variant = parse_variant(getenv("NVSHARE_PEER_FETCH_VARIANT"), parse_variant(all, NVS_COPY_TMA));
+	cfg->retain = (uint32_t)env_u64("NVSHARE_RETAIN", 1);
 	/* B200 probe: 2 CTAs already saturate PCIe Gen5 x16 in one direction
 	 * (52.7 GB/s); 8 leaves head-room when SMs are shared; the peer tier
 	 * (NVLink 5) wants ~74. */
@@ -596,7 +639,7 @@ static inline int bit_get(const struct arena *a, uint32_t i)
 	return (a->bitmap[k >> 6] >> (k & 63)) & 1;
 }
 
-static inline void bit_put(struct arena *a, uint32_t i, int v, int32_t owner)
+static inline void bit_put(struct arena *a, uint32_t i, int v, int32_t owner, uint32_t tag)
 {
 	uint64_t k = a->bit_base + i;
 	if (v)
@@ -605,27 +648,46 @@ static inline void bit_put(struct arena *a, uint32_t i, int v, int32_t owner)
 		a->bitmap[k >> 6] &= ~(1ull << (k & 63));
 	if (a->owners)
 		a->owners[k] = owner;
+	a->rstate[k] = RS_NONE;
+	a->ctag[k] = tag;
 }
 
-static int arena_take(struct arena *a, uint32_t n, uint64_t *addr)
+/* may slab i be handed out?  free always; a retained unit if its class is <= steal_class */
+static inline int slab_available(const struct arena *a, uint32_t i, int steal_class)
 {
-	if (!a->shared && a->n_slabs - a->used < n)
+	if (!bit_get(a, i))
+		return 1;
+	const uint8_t rs = a->rstate[a->bit_base + i];
+	return rs != RS_NONE && (int)rs <= steal_class;
+}
+
+/*
+ * First fit of n adjacent units (runs never straddle arenas).  steal_class 0 takes free
+ * units only; 1 / 2 also take over retained units (RS_PLAIN / RS_STABLE) -- copies their
+ * owners can do without, whoever they are.  The owner notices through the tag
+ * (backing_reclaim).  *fresh = how many of the n units were free before.
+ */
+static int arena_take(struct arena *a, uint32_t n, uint64_t *addr, int steal_class, uint32_t tag, uint32_t *fresh)
+{
+	if (!a->shared && steal_class == 0 && a->n_slabs - a->used < n)
 		return -1;
-	/* first fit over the bitmap; runs never straddle arenas */
 	uint32_t run = 0;
-	for (uint32_t i = a->shared ? 0 : a->hint; i < a->n_slabs; ++i) {
-		if (bit_get(a, i)) {
+	for (uint32_t i = (a->shared || steal_class) ? 0 : a->hint; i < a->n_slabs; ++i) {
+		if (!slab_available(a, i, steal_class)) {
 			run = 0;
 			continue;
 		}
 		if (++run == n) {
-			uint32_t first = i + 1 - n;
-			for (uint32_t k = first; k <= i; ++k)
-				bit_put(a, k, 1, (int32_t)getpid());
-			a->used += n;
+			uint32_t first = i + 1 - n, was_free = 0;
+			for (uint32_t k = first; k <= i; ++k) {
+				was_free += !bit_get(a, k);
+				bit_put(a, k, 1, (int32_t)getpid(), tag);
+			}
+			a->used += was_free;
 			while (!a->shared && a->hint < a->n_slabs && bit_get(a, a->hint))
 				a->hint++;
 			*addr = a->dev_base + (uint64_t)first * SLAB;
+			*fresh = was_free;
 			return 0;
 		}
 	}
@@ -645,46 +707,117 @@ static void shp_unlock(struct shpool *sp)
 	pthread_mutex_unlock(&sp->hdr->mu);
 }
 
-static int pool_take(nvs_engine *e, struct pool *p, uint32_t n, uint64_t *addr)
+static int pool_take(nvs_engine *e, struct pool *p, uint32_t n, uint64_t *addr, int steal_class, uint32_t tag)
 {
 	struct shpool *sp = (p == &e->host_pool) ? e->shp : NULL;
 	int rc = -1;
 	if (sp)
 		shp_lock(sp);
-	for (struct arena *a = p->arenas; a; a = a->next)
-		if (arena_take(a, n, addr) == 0) {
-			p->used += (uint64_t)n * SLAB;
+	for (struct arena *a = p->arenas; a; a = a->next) {
+		uint32_t fresh = 0;
+		if (arena_take(a, n, addr, steal_class, tag, &fresh) == 0) {
+			p->used += (uint64_t)fresh * SLAB;
 			if (sp && a->shared)
-				sp->hdr->used_slabs += n;
+				sp->hdr->used_slabs += fresh;
+			e->st.stolen_slabs_total += n - fresh;
 			rc = 0;
 			break;
 		}
+	}
 	if (sp)
 		shp_unlock(sp);
 	return rc;
 }
 
-static void pool_give(nvs_engine *e, struct pool *p, uint64_t addr, uint32_t n)
+static struct arena *arena_of(struct pool *p, uint64_t addr)
+{
+	for (struct arena *a = p->arenas; a; a = a->next)
+		if (addr >= a->dev_base && addr < a->dev_base + a->bytes)
+			return a;
+	return NULL;
+}
+
+/* Hand back the units of a run that are (still) ours: tag and, in the shared pool, pid match. */
+static void pool_give(nvs_engine *e, struct pool *p, uint64_t addr, uint32_t n, uint32_t tag)
 {
 	struct shpool *sp = (p == &e->host_pool) ? e->shp : NULL;
 	if (sp)
 		shp_lock(sp);
-	for (struct arena *a = p->arenas; a; a = a->next) {
-		if (addr < a->dev_base || addr >= a->dev_base + a->bytes)
-			continue;
-		uint32_t first = (uint32_t)((addr - a->dev_base) / SLAB);
-		for (uint32_t k = first; k < first + n; ++k)
-			bit_put(a, k, 0, 0);
-		a->used -= n;
+	struct arena *a = arena_of(p, addr);
+	if (a) {
+		const uint32_t first = (uint32_t)((addr - a->dev_base) / SLAB);
+		uint32_t given = 0;
+		for (uint32_t k = first; k < first + n; ++k) {
+			const uint64_t g = a->bit_base + k;
+			if (!bit_get(a, k) || a->ctag[g] != tag || (a->owners && a->owners[g] != (int32_t)getpid()))
+				continue; /* taken over by somebody else meanwhile */
+			bit_put(a, k, 0, 0, 0);
+			given++;
+		}
+		a->used -= given;
 		if (!a->shared && first < a->hint)
 			a->hint = first;
-		p->used -= (uint64_t)n * SLAB;
+		p->used -= (uint64_t)given * SLAB;
 		if (sp && a->shared)
-			sp->hdr->used_slabs -= n;
-		break;
+			sp->hdr->used_slabs -= given;
 	}
 	if (sp)
 		shp_unlock(sp);
+}
+
+/* The chunk has been fetched: its units stay, marked as reclaimable by anybody. */
+static void pool_mark_retained(nvs_engine *e, struct pool *p, uint64_t addr, uint32_t n, uint8_t rs)
+{
+	struct shpool *sp = (p == &e->host_pool) ? e->shp : NULL;
+	if (sp)
+		shp_lock(sp);
+	struct arena *a = arena_of(p, addr);
+	if (a) {
+		const uint32_t first = (uint32_t)((addr - a->dev_base) / SLAB);
+		for (uint32_t k = first; k < first + n; ++k)
+			a->rstate[a->bit_base + k] = rs;
+	}
+	if (sp)
+		shp_unlock(sp);
+}
+
+/* Is the retained run still entirely ours?  Yes: it becomes live again (nobody can take it
+ * over any more), returns 1.  No: what is left of it is given back, returns 0. */
+static int pool_reclaim(nvs_engine *e, struct pool *p, uint64_t addr, uint32_t n, uint32_t tag)
+{
+	struct shpool *sp = (p == &e->host_pool) ? e->shp : NULL;
+	int ok = 0;
+	if (sp)
+		shp_lock(sp);
+	struct arena *a = arena_of(p, addr);
+	if (a) {
+		const uint32_t first = (uint32_t)((addr - a->dev_base) / SLAB);
+		ok = 1;
+		for (uint32_t k = first; k < first + n && ok; ++k) {
+			const uint64_t g = a->bit_base + k;
+			ok = bit_get(a, k) && a->ctag[g] == tag && a->rstate[g] != RS_NONE &&
+			     (!a->owners || a->owners[g] == (int32_t)getpid());
+		}
+		if (ok)
+			for (uint32_t k = first; k < first + n; ++k)
+				a->rstate[a->bit_base + k] = RS_NONE;
+	}
+	if (sp)
+		shp_unlock(sp);
+	if (!ok)
+		pool_give(e, p, addr, n, tag);
+	return ok;
+}
+
+/* a private arena's own bookkeeping (a shared window's lives in the pool header) */
+static void arena_free(struct arena *a)
+{
+	if (!a->shared) {
+		free(a->bitmap);
+		free(a->rstate);
+		free(a->ctag);
+	}
+	free(a);
 }
 
 static struct arena *arena_new(uint64_t bytes)
@@ -695,8 +828,10 @@ static struct arena *arena_new(uint64_t bytes)
 	a->bytes = bytes;
 	a->n_slabs = (uint32_t)(bytes / SLAB);
 	a->bitmap = calloc((a->n_slabs + 63) / 64, sizeof(uint64_t));
-	if (!a->bitmap) {
-		free(a);
+	a->rstate = calloc(a->n_slabs ? a->n_slabs : 1, 1);
+	a->ctag = calloc(a->n_slabs ? a->n_slabs : 1, sizeof(uint32_t));
+	if (!a->bitmap || !a->rstate || !a->ctag) {
+		arena_free(a);
 		return NULL;
 	}
 	return a;
@@ -804,6 +939,8 @@ static int shared_pool_grow_unlocked(nvs_engine *e)
 	a->n_slabs = sp->hdr->window_slabs;
 	a->bitmap = sp->hdr->bitmap;
 	a->owners = sp->hdr->owners;
+	a->rstate = sp->hdr->rstate;
+	a->ctag = sp->hdr->ctag;
 	a->bit_base = (uint64_t)w * sp->hdr->window_slabs;
 	a->host_base = base;
 	a->dev_base = dp;
@@ -836,8 +973,7 @@ static int host_pool_grow_unlocked(nvs_engine *e)
 	near_pop(pushed, &saved);
 	if (r != CUDA_SUCCESS) {
 		nvs_warn("engine: cuMemHostAlloc(%" PRIu64 " MiB) failed: %s", a->bytes >> 20, cu_name(e, r));
-		free(a->bitmap);
-		free(a);
+		arena_free(a);
 		return NVS_E_HOST_OOM;
 	}
 	CUdeviceptr dp = 0;
@@ -896,8 +1032,7 @@ static int host_pool_overflow(nvs_engine *e)
 	if (r != CUDA_SUCCESS) {
 		nvs_warn("engine: the shared pool is full and cuMemHostAlloc(%" PRIu64 " MiB) for an overflow arena failed: %s",
 			 a->bytes >> 20, cu_name(e, r));
-		free(a->bitmap);
-		free(a);
+		arena_free(a);
 		return NVS_E_HOST_OOM;
 	}
 	a->host_base = p;
@@ -956,8 +1091,7 @@ static int peer_pool_grow(nvs_engine *e, int pi)
 	e->st.peer_pool_bytes += bytes;
 	return 0;
 fail:
-	free(a->bitmap);
-	free(a);
+	arena_free(a);
 	return NVS_E_HOST_OOM;
 }
 
@@ -969,12 +1103,15 @@ static int backing_assign(nvs_engine *e, struct chunk *c, int nowait)
 	if (c->backing)
 		return 0;
 	const uint32_t n = (uint32_t)(c->bytes / SLAB);
+	const uint32_t tag = ++e->tag_next ? e->tag_next : ++e->tag_next; /* never 0 */
+	memset(c->bvalid, 0, sizeof(c->bvalid));
 	for (int t = 0; t < e->cfg.n_peers; ++t) {
 		int pi = (int)((e->peer_rr + (uint32_t)t) % (uint32_t)e->cfg.n_peers);
 		struct pool *p = &e->peer_pools[pi];
-		if (pool_take(e, p, n, &c->backing) == 0 ||
-		    (peer_pool_grow(e, pi) == 0 && pool_take(e, p, n, &c->backing) == 0)) {
+		if (pool_take(e, p, n, &c->backing, 0, tag) == 0 ||
+		    (peer_pool_grow(e, pi) == 0 && pool_take(e, p, n, &c->backing, 0, tag) == 0)) {
 			c->tier = (uint8_t)(TIER_PEER0 + pi);
+			c->btag = tag;
 			e->peer_rr = (uint32_t)pi + 1;
 			e->st.peer_pool_used += c->bytes;
 			return 0;
@@ -982,11 +1119,23 @@ static int backing_assign(nvs_engine *e, struct chunk *c, int nowait)
 	}
 	double t0 = now_ms(), next_reap = 0;
 	int overflow_failed = 0;
-	while (pool_take(e, &e->host_pool, n, &c->backing) != 0) {
+	for (;;) {
+		if (pool_take(e, &e->host_pool, n, &c->backing, 0, tag) == 0)
+			break;
+		/* A private pool takes over retained copies before it pins more host memory; the shared
+		 * pool first grows to its capacity (a budget fixed when it was created), then does. */
+		if (!e->shp && e->cfg.retain &&
+		    (pool_take(e, &e->host_pool, n, &c->backing, RS_PLAIN, tag) == 0 ||
+		     pool_take(e, &e->host_pool, n, &c->backing, RS_STABLE, tag) == 0))
+			break;
 		/* pool empty: wait for the background pinning, or pin inline */
 		int rc = host_pool_grow(e);
 		if (rc == 0)
 			continue;
+		if (e->shp && e->cfg.retain &&
+		    (pool_take(e, &e->host_pool, n, &c->backing, RS_PLAIN, tag) == 0 ||
+		     pool_take(e, &e->host_pool, n, &c->backing, RS_STABLE, tag) == 0))
+			break;
 		if (!e->shp || nowait || now_ms() - t0 > e->cfg.oom_wait_ms)
 			return rc;
 		/* the shared pool is full and entirely pinned here: another client is about
@@ -1006,6 +1155,7 @@ static int backing_assign(nvs_engine *e, struct chunk *c, int nowait)
 		pthread_mutex_lock(&e->mu);
 	}
 	c->tier = TIER_HOST;
+	c->btag = tag;
 	e->st.host_pool_used = e->host_pool.used;
 	if (e->shp && e->cfg.prepin) {
 		/* keep a few windows pinned ahead of the eviction front (pinning a window of
@@ -1019,17 +1169,43 @@ static int backing_assign(nvs_engine *e, struct chunk *c, int nowait)
 	return 0;
 }
 
+static struct pool *pool_of_tier(nvs_engine *e, uint8_t tier)
+{
+	return tier == TIER_HOST ? &e->host_pool : tier >= TIER_PEER0 ? &e->peer_pools[tier - TIER_PEER0] : NULL;
+}
+
+/* A RESIDENT chunk is about to rely on the backing copy it kept: is it still there?
+ * 1: yes, and from now on nobody can take it (it is live again).  0: gone. */
+static int backing_reclaim(nvs_engine *e, struct chunk *c)
+{
+	if (!c->retained)
+		return c->backing != 0;
+	c->retained = 0;
+	e->st.retained_bytes -= c->bytes;
+	struct pool *p = pool_of_tier(e, c->tier);
+	if (p && c->backing && pool_reclaim(e, p, c->backing, (uint32_t)(c->bytes / SLAB), c->btag))
+		return 1;
+	/* somebody needed the units more: the copy is gone, the next eviction moves everything */
+	c->backing = 0;
+	c->tier = TIER_NONE;
+	memset(c->bvalid, 0, sizeof(c->bvalid));
+	e->st.host_pool_used = e->host_pool.used;
+	return 0;
+}
+
 static void backing_release(nvs_engine *e, struct chunk *c)
 {
+	if (c->retained && !backing_reclaim(e, c))
+		return;
 	if (!c->backing)
 		return;
 	const uint32_t n = (uint32_t)(c->bytes / SLAB);
 	if (c->tier == TIER_HOST) {
-		pool_give(e, &e->host_pool, c->backing, n);
+		pool_give(e, &e->host_pool, c->backing, n, c->btag);
 		e->st.host_pool_used = e->host_pool.used;
 	} else if (c->tier >= TIER_PEER0) {
 		struct pool *p = &e->peer_pools[c->tier - TIER_PEER0];
-		pool_give(e, p, c->backing, n);
+		pool_give(e, p, c->backing, n, c->btag);
 		e->st.peer_pool_used -= c->bytes;
 		/* peer HBM is per-process (no shared pool yet): hand empty arenas back to the peer
 		 * GPU at once, so that the client evicting right now finds room there */
@@ -1045,12 +1221,47 @@ static void backing_release(nvs_engine *e, struct chunk *c)
 			e->d.MemRelease(a->handle);
 			p->bytes -= a->bytes;
 			e->st.peer_pool_bytes -= a->bytes;
-			free(a->bitmap);
-			free(a);
+			arena_free(a);
 		}
 	}
 	c->backing = 0;
 	c->tier = TIER_NONE;
+	memset(c->bvalid, 0, sizeof(c->bvalid));
+}
+
+/* The chunk is resident and its backing copy stays in the pool, reclaimable by anybody. */
+static void backing_mark_retained(nvs_engine *e, struct chunk *c)
+{
+	if (!c->backing || c->retained || c->tier != TIER_HOST)
+		return;
+	pool_mark_retained(e, &e->host_pool, c->backing, (uint32_t)(c->bytes / SLAB),
+			   c->stable == ST_STABLE ? RS_STABLE : RS_PLAIN);
+	c->retained = 1;
+	e->st.retained_bytes += c->bytes;
+}
+
+/*
+ * A fetched chunk's backing copy: keep it or give it back?  Keeping costs host memory
+ * that anybody may take over when the pool runs short, and buys an eviction that only
+ * copies what changed.  Chunks that turned out dirty last time are not worth it --
+ * except every VOLATILE_REPROBE-th time, to notice that they calmed down.
+ */
+static void backing_after_fetch(nvs_engine *e, struct chunk *c)
+{
+	if (!c->backing)
+		return;
+	int keep = e->cfg.retain && c->tier == TIER_HOST;
+	if (keep && c->stable == ST_VOLATILE) {
+		if (++c->volatile_skips < VOLATILE_REPROBE)
+			keep = 0;
+		else
+			c->volatile_skips = 0;
+	}
+	if (!keep) {
+		backing_release(e, c);
+		return;
+	}
+	backing_mark_retained(e, c);
 }
 
 /* ------------------------------------------------------ shared pool ---- */
@@ -1066,9 +1277,8 @@ static void shp_close(nvs_engine *e)
 			e->d.MemHostUnregister(a->host_base);
 		} else { /* overflow arena (host_pool_overflow) */
 			e->d.MemFreeHost(a->host_base);
-			free(a->bitmap);
 		}
-		free(a);
+		arena_free(a);
 	}
 	e->host_pool.arenas = NULL;
 	if (sp->hdr)
@@ -1100,6 +1310,8 @@ static uint64_t shp_reap_dead(struct shpool *sp)
 			continue;
 		sp->hdr->bitmap[k >> 6] &= ~(1ull << (k & 63));
 		sp->hdr->owners[k] = 0;
+		sp->hdr->rstate[k] = RS_NONE;
+		sp->hdr->ctag[k] = 0;
 		sp->hdr->used_slabs--;
 		reaped++;
 	}
@@ -1260,8 +1472,36 @@ static struct alloc *table_find(nvs_engine *e, uint64_t va)
 	return NULL;
 }
 
+/* index of the first allocation whose address is > va */
+static size_t by_va_upper(const nvs_engine *e, uint64_t va)
+{
+	size_t lo = 0, hi = e->n_by_va;
+	while (lo < hi) {
+		size_t mid = (lo + hi) / 2;
+		if (e->by_va[mid]->va <= va)
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	return lo;
+}
+
 static void table_insert(nvs_engine *e, struct alloc *a)
 {
+	if (e->n_by_va == e->cap_by_va) {
+		size_t cap = e->cap_by_va ? 2 * e->cap_by_va : 256;
+		struct alloc **nv = realloc(e->by_va, cap * sizeof(*nv));
+		if (nv) {
+			e->by_va = nv;
+			e->cap_by_va = cap;
+		}
+	}
+	if (e->n_by_va < e->cap_by_va) {
+		size_t at = by_va_upper(e, a->va);
+		memmove(&e->by_va[at + 1], &e->by_va[at], (e->n_by_va - at) * sizeof(*e->by_va));
+		e->by_va[at] = a;
+		e->n_by_va++;
+	}
 	unsigned h = hash_va(a->va);
 	a->hnext = e->buckets[h];
 	e->buckets[h] = a;
@@ -1278,6 +1518,11 @@ static void table_insert(nvs_engine *e, struct alloc *a)
 
 static void table_remove(nvs_engine *e, struct alloc *a)
 {
+	size_t at = by_va_upper(e, a->va);
+	if (at > 0 && e->by_va[at - 1] == a) {
+		memmove(&e->by_va[at - 1], &e->by_va[at], (e->n_by_va - at) * sizeof(*e->by_va));
+		e->n_by_va--;
+	}
 	struct alloc **pp = &e->buckets[hash_va(a->va)];
 	while (*pp && *pp != a)
 		pp = &(*pp)->hnext;
@@ -1440,8 +1685,10 @@ out:
 static void slot_reset(struct slot *s)
 {
 	s->n_descs = 0;
+	s->n_ce = 0;
 	s->n_chunks = 0;
 	s->n_aux = 0;
+	s->peer_traffic = 0;
 }
 
 static inline int slab_is_const(const struct chunk *c, uint32_t i)
@@ -1449,27 +1696,72 @@ static inline int slab_is_const(const struct chunk *c, uint32_t i)
 	return (c->cmask[i >> 6] >> (i & 63)) & 1;
 }
 
-/* Copy descriptors for the slabs of `c` that really have to move (same-filled
- * slabs are skipped).  Kernel variants get one descriptor per slab; the copy
- * engines get one per run of adjacent slabs (a chunk's backing is contiguous). */
-static int slot_push_chunk(struct slot *s, struct chunk *c, int to_backing, uint32_t variant)
+static inline int mask_get(const uint64_t *m, uint32_t i)
+{
+	return (m[i >> 6] >> (i & 63)) & 1;
+}
+
+static inline void mask_set(uint64_t *m, uint32_t i)
+{
+	m[i >> 6] |= 1ull << (i & 63);
+}
+
+static void mask_fill(uint64_t *m, uint32_t n)
+{
+	memset(m, 0, sizeof(uint64_t) * (MAX_CHUNK_SLABS / 64));
+	for (uint32_t i = 0; i < n; ++i)
+		mask_set(m, i);
+}
+
+/* Which engine moves a chunk between HBM and its backing tier?  Measured on B200 (probes D, G):
+ * over PCIe a copy-engine transfer carries 256-byte TLPs, an SM-issued one 128-byte TLPs --
+ * 55.4 vs 52.7 GB/s alone, 50+49 vs 49+44 with both directions busy -- so the pinned-host tier
+ * moves on the copy engines and the SMs do what those cannot (scan, hash, splat).  Over NVLink
+ * the kernel wins (3.3 TB/s device-to-device against 0.5 TB/s of per-chunk cuMemcpyAsync). */
+/* one launch consumes the whole kernel list of a slot: the peer tier's kernel if it has one */
+static uint32_t kernel_variant(const nvs_engine *e, int to_backing)
+{
+	const uint32_t peer = to_backing ? e->cfg.peer_evict_variant : e->cfg.peer_fetch_variant;
+	const uint32_t host = to_backing ? e->cfg.evict_variant : e->cfg.fetch_variant;
+	return peer != NVS_COPY_CE ? peer : host != NVS_COPY_CE ? host : NVS_COPY_TMA;
+}
+
+static uint32_t variant_for(const nvs_engine *e, uint8_t tier, int to_backing)
+{
+	if (tier >= TIER_PEER0)
+		return to_backing ? e->cfg.peer_evict_variant : e->cfg.peer_fetch_variant;
+	return to_backing ? e->cfg.evict_variant : e->cfg.fetch_variant;
+}
+
+/* Copy descriptors for the slabs of `c` selected by `mask`.  Kernel variants get one
+ * descriptor per slab; the copy engines get one per run of adjacent slabs (a chunk's
+ * backing is contiguous). */
+static int slot_push_chunk(nvs_engine *e, struct slot *s, struct chunk *c, int to_backing, const uint64_t *mask)
 {
 	if (s->n_chunks == s->cap_chunks)
 		return -1;
 	s->chunks[s->n_chunks++] = c;
+	const uint32_t variant = variant_for(e, c->tier, to_backing);
 	const uint32_t n = (uint32_t)(c->bytes / SLAB);
 	for (uint32_t i = 0; i < n;) {
-		if (slab_is_const(c, i)) {
+		if (!mask_get(mask, i)) {
 			++i;
 			continue;
 		}
 		uint32_t run = 1;
-		if (variant == NVS_COPY_CE)
-			while (i + run < n && !slab_is_const(c, i + run))
+		nvs_copy_desc *d;
+		if (variant == NVS_COPY_CE) {
+			while (i + run < n && mask_get(mask, i + run))
 				++run;
-		if (s->n_descs == s->cap_descs)
-			return -1;
-		nvs_copy_desc *d = &s->descs[s->n_descs++];
+			if (s->n_ce == s->cap_ce)
+				return -1;
+			d = &s->ce[s->n_ce++];
+		} else {
+			if (s->n_descs == s->cap_descs)
+				return -1;
+			d = &s->descs[s->n_descs++];
+			s->peer_traffic |= c->tier >= TIER_PEER0;
+		}
 		const uint64_t off = (uint64_t)i * SLAB;
 		d->src = (to_backing ? c->va : c->backing) + off;
 		d->dst = (to_backing ? c->backing : c->va) + off;
@@ -1480,7 +1772,27 @@ static int slot_push_chunk(struct slot *s, struct chunk *c, int to_backing, uint
 	return 0;
 }
 
-static int launch_aux(nvs_engine *e, CUfunction fn, struct slot *s, CUstream stream, int with_out)
+/* Enqueue everything a slot has gathered on e->stream: one sm_100a kernel launch for the
+ * kernel list, one cuMemcpyAsync per run of the copy-engine list. */
+static int slot_launch(nvs_engine *e, struct slot *s, uint32_t kernel_variant, nvs_xfer_report *rep)
+{
+	int rc = 0;
+	if (s->n_descs) {
+		if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, kernel_variant,
+				       grid_for(e, 0, s->peer_traffic))) != 0)
+			return rc;
+		rep->launches++;
+	}
+	if (s->n_ce) {
+		if ((rc = launch_descs(e, 0, s->ce, s->n_ce, NVS_COPY_CE, 0)) != 0)
+			return rc;
+		rep->ce_calls += s->n_ce;
+		e->st.ce_calls_total += s->n_ce;
+	}
+	return 0;
+}
+
+static int launch_aux(nvs_engine *e, CUfunction fn, struct slot *s, CUstream stream, int with_out, uint32_t want_hash)
 {
 	int rc = 0;
 	if (s->n_aux == 0)
@@ -1491,8 +1803,10 @@ static int launch_aux(nvs_engine *e, CUfunction fn, struct slot *s, CUstream str
 	}
 	CUdeviceptr counter = e->counters + 4ull * (N_COUNTERS + e->scan_counter_next++);
 	uint32_t n = s->n_aux;
-	unsigned grid = n < (unsigned)e->n_sms * 8 ? n : (unsigned)e->n_sms * 8;
-	void *p_scan[] = {&s->aux_dev, &n, &counter, &s->scan_out_dev};
+	/* 256 threads per CTA is part of the hash's definition (lane = thread) */
+	unsigned per_sm = with_out ? 4u : 8u;
+	unsigned grid = n < (unsigned)e->n_sms * per_sm ? n : (unsigned)e->n_sms * per_sm;
+	void *p_scan[] = {&s->aux_dev, &n, &counter, &s->scan_out_dev, &want_hash};
 	void *p_splat[] = {&s->aux_dev, &n, &counter};
 	CK(e, e->d.LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 0, stream, with_out ? p_scan : p_splat, NULL));
 	e->st.kernel_launches_total++;
@@ -1500,11 +1814,19 @@ out:
 	return rc;
 }
 
-/* Find the same-filled slabs of the chunks gathered in `s` (evict side). */
+/*
+ * Look at the chunks gathered in `s` before they leave HBM: one pass of the scan kernel
+ * tells, per slab, whether it is same-filled (described by 8 bytes, not moved) and -- with
+ * retention on -- its 128-bit content hash, from which follows what this eviction has to
+ * copy (c->cpmask): every slab that is neither same-filled nor identical to what the
+ * chunk's retained backing copy already holds.
+ */
 static int scan_slot(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
 {
 	int rc = 0;
+	const uint32_t want_hash = e->cfg.retain ? 1u : 0u;
 	s->n_aux = 0;
+	uint64_t bytes = 0;
 	for (uint32_t k = 0; k < s->n_chunks; ++k) {
 		struct chunk *c = s->chunks[k];
 		for (uint64_t off = 0; off < c->bytes; off += SLAB) {
@@ -1516,27 +1838,56 @@ static int scan_slot(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
 			d->bytes = SLAB;
 			d->tag = 0;
 		}
+		bytes += c->bytes;
 	}
-	if ((rc = launch_aux(e, e->fn_scan, s, e->scan_stream, 1)) != 0)
+	CK(e, e->d.EventRecord(e->scan_begin, e->scan_stream));
+	if ((rc = launch_aux(e, e->fn_scan, s, e->scan_stream, 1, want_hash)) != 0)
 		return rc;
 	CK(e, e->d.EventRecord(e->scan_done, e->scan_stream));
 	CK(e, e->d.EventSynchronize(e->scan_done));
+	{
+		float ms = 0;
+		if (e->d.EventElapsedTime(&ms, e->scan_begin, e->scan_done) == CUDA_SUCCESS)
+			rep->scan_ms += ms;
+		rep->launches++;
+		/* the early-exit scan reads one 32 KiB tile of a slab that is not same-filled */
+		rep->scanned_bytes += want_hash ? bytes : 0;
+	}
 	uint32_t at = 0;
 	for (uint32_t k = 0; k < s->n_chunks; ++k) {
 		struct chunk *c = s->chunks[k];
 		const uint32_t n = (uint32_t)(c->bytes / SLAB);
 		memset(c->cmask, 0, sizeof(c->cmask));
+		memset(c->cpmask, 0, sizeof(c->cpmask));
 		c->n_const = 0;
+		c->est_copy = 0;
+		if (want_hash && !c->nh && !(c->nh = malloc(MAX_CHUNK_SLABS * sizeof(struct slab_hash))))
+			return NVS_E_HOST_OOM;
 		for (uint32_t i = 0; i < n; ++i, ++at) {
-			if (!s->scan_out[at].is_const)
+			const struct scan_result *r = &s->scan_out[at];
+			if (want_hash) {
+				c->nh[i].h0 = r->h0;
+				c->nh[i].h1 = r->h1;
+			}
+			if (r->is_const && e->cfg.elide_constant) {
+				if (!c->cvals && !(c->cvals = calloc(MAX_CHUNK_SLABS, sizeof(uint64_t))))
+					return NVS_E_HOST_OOM;
+				c->cvals[i] = r->value;
+				mask_set(c->cmask, i);
+				c->n_const++;
+				if (!want_hash)
+					rep->scanned_bytes += SLAB;
 				continue;
-			if (!c->cvals && !(c->cvals = calloc(MAX_CHUNK_SLABS, sizeof(uint64_t))))
-				return NVS_E_HOST_OOM;
-			c->cvals[i] = s->scan_out[at].value;
-			c->cmask[i >> 6] |= 1ull << (i & 63);
-			c->n_const++;
+			}
+			if (!want_hash)
+				rep->scanned_bytes += 32768;
+			if (want_hash && c->had_backing && c->hash && mask_get(c->bvalid, i) &&
+			    c->hash[i].h0 == r->h0 && c->hash[i].h1 == r->h1)
+				continue; /* the backing copy of this slab is still good */
+			mask_set(c->cpmask, i);
+			c->est_copy += SLAB;
 		}
-		rep->elided_bytes += (uint64_t)c->n_const * SLAB;
+		c->scanned = 1;
 	}
 out:
 	return rc;
@@ -1544,9 +1895,21 @@ out:
 
 /* ------------------------------------------------------------- evict ---- */
 
-static int cmp_chunk_lru(const void *a, const void *b)
+/*
+ * Victim order of a partial eviction.  Every chunk has to be resident again before its
+ * owner may run (VMM memory cannot fault), so WHICH chunks are out never costs a miss
+ * later: what differs between chunks is what it costs to put them out now.  Cheapest
+ * first -- chunks whose retained backing copy is still valid or that are same-filled go
+ * for free -- then the ones the host side has not written for longest (nvs_touch), then
+ * least recently fetched; the address only breaks ties.
+ */
+static int cmp_chunk_victim(const void *a, const void *b)
 {
 	const struct chunk *x = *(struct chunk *const *)a, *y = *(struct chunk *const *)b;
+	if (x->est_copy != y->est_copy)
+		return x->est_copy < y->est_copy ? -1 : 1;
+	if (x->touch != y->touch)
+		return x->touch < y->touch ? -1 : 1;
 	if (x->epoch != y->epoch)
 		return x->epoch < y->epoch ? -1 : 1;
 	return x->va < y->va ? -1 : x->va > y->va;
@@ -1554,19 +1917,36 @@ static int cmp_chunk_lru(const void *a, const void *b)
 
 static void report_emit(nvs_engine *e, const char *what, const nvs_xfer_report *r)
 {
-	nvs_debug("engine: %s %" PRIu64 " MiB (+%" PRIu64 " MiB same-filled, not moved) in %.1f ms (copy %.1f ms = %.1f GB/s, "
-		  "map %.1f ms, wait %.1f ms)", what, r->bytes >> 20, r->elided_bytes >> 20, r->wall_ms, r->copy_ms,
-		  r->copy_ms > 0 ? r->bytes / 1e6 / r->copy_ms : 0.0, r->map_ms, r->wait_ms);
+	nvs_debug("engine: %s %" PRIu64 " MiB (+%" PRIu64 " MiB same-filled, +%" PRIu64 " MiB clean: not moved) in %.1f ms "
+		  "(copy %.1f ms = %.1f GB/s, map %.1f ms, wait %.1f ms, scan %.1f ms)", what, r->bytes >> 20,
+		  r->elided_bytes >> 20, r->clean_bytes >> 20, r->wall_ms, r->copy_ms,
+		  r->copy_ms > 0 ? r->bytes / 1e6 / r->copy_ms : 0.0, r->map_ms, r->wait_ms, r->scan_ms);
 	if (!e->stats_file)
 		return;
 	fprintf(e->stats_file,
 		"{\"op\":\"%s\",\"t\":%.6f,\"pid\":%d,\"bytes\":%" PRIu64 ",\"slabs\":%" PRIu64
-		",\"chunks\":%" PRIu64 ",\"launches\":%" PRIu64 ",\"wall_ms\":%.3f,\"copy_ms\":%.3f,"
-		"\"map_ms\":%.3f,\"wait_ms\":%.3f,\"host_bytes\":%" PRIu64 ",\"peer_bytes\":%" PRIu64
-		",\"elided_bytes\":%" PRIu64 "}\n",
-		what, wall_s(), (int)getpid(), r->bytes, r->slabs, r->chunks, r->launches, r->wall_ms, r->copy_ms,
-		r->map_ms, r->wait_ms, r->host_bytes, r->peer_bytes, r->elided_bytes);
+		",\"chunks\":%" PRIu64 ",\"launches\":%" PRIu64 ",\"ce_calls\":%" PRIu64 ",\"wall_ms\":%.3f,\"copy_ms\":%.3f,"
+		"\"map_ms\":%.3f,\"wait_ms\":%.3f,\"scan_ms\":%.3f,\"host_bytes\":%" PRIu64 ",\"peer_bytes\":%" PRIu64
+		",\"elided_bytes\":%" PRIu64 ",\"clean_bytes\":%" PRIu64 ",\"scanned_bytes\":%" PRIu64
+		",\"retained_bytes\":%" PRIu64 ",\"pool_used\":%" PRIu64 "}\n",
+		what, wall_s(), (int)getpid(), r->bytes, r->slabs, r->chunks, r->launches, r->ce_calls, r->wall_ms, r->copy_ms,
+		r->map_ms, r->wait_ms, r->scan_ms, r->host_bytes, r->peer_bytes, r->elided_bytes, r->clean_bytes,
+		r->scanned_bytes, e->st.retained_bytes, e->host_pool.used);
 	fflush(e->stats_file);
+}
+
+/* forget what this eviction learned about a chunk (it stays resident, or the eviction failed) */
+static void scan_forget(struct chunk *c)
+{
+	free(c->nh);
+	c->nh = NULL;
+	c->scanned = 0;
+	c->had_backing = 0;
+	c->est_copy = 0;
+	if (c->state == CH_RESIDENT) {
+		memset(c->cmask, 0, sizeof(c->cmask));
+		c->n_const = 0;
+	}
 }
 
 /* wait for a slot's copy, then give its chunks' HBM back */
@@ -1578,16 +1958,40 @@ static int evict_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
 	CK(e, e->d.EventSynchronize(s->done));
 	{
 		float ms = 0;
-		if (e->d.EventElapsedTime(&ms, s->begin, s->done) == CUDA_SUCCESS)
+		if ((s->n_descs || s->n_ce) && e->d.EventElapsedTime(&ms, s->begin, s->done) == CUDA_SUCCESS)
 			rep->copy_ms += ms;
 	}
 	double t0 = now_ms();
 	for (uint32_t i = 0; i < s->n_chunks; ++i) {
 		struct chunk *c = s->chunks[i];
+		const uint32_t n = (uint32_t)(c->bytes / SLAB);
 		int r = chunk_unmap(e, c);
 		if (r != 0 && rc == 0)
 			rc = r;
 		state_account(e, c, CH_SWAPPED);
+		/* what the backing copy holds now, slab by slab: the bytes just copied, or the bytes that
+		 * were already there and still match; same-filled slabs have no bytes there at all */
+		if (c->nh && c->backing) {
+			if (!c->hash)
+				c->hash = malloc(MAX_CHUNK_SLABS * sizeof(struct slab_hash));
+			if (c->hash) {
+				for (uint32_t k = 0; k < n; ++k)
+					if (mask_get(c->cpmask, k))
+						c->hash[k] = c->nh[k];
+				for (uint32_t k = 0; k < MAX_CHUNK_SLABS / 64; ++k)
+					c->bvalid[k] = ~c->cmask[k];
+			} else {
+				memset(c->bvalid, 0, sizeof(c->bvalid));
+			}
+		} else {
+			memset(c->bvalid, 0, sizeof(c->bvalid));
+		}
+		if (c->had_backing) /* worth keeping a copy of: at most half of it had changed */
+			c->stable = 2 * c->est_copy <= c->bytes - (uint64_t)c->n_const * SLAB ? ST_STABLE : ST_VOLATILE;
+		free(c->nh);
+		c->nh = NULL;
+		c->scanned = 0;
+		c->had_backing = 0;
 		rep->chunks++;
 	}
 	rep->map_ms += now_ms() - t0;
@@ -1609,6 +2013,29 @@ int nvs_evict_best_effort(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *re
 	return evict_impl(e, min_bytes, rep_out, 1);
 }
 
+/* scan `n` chunks (which all fit one slot; the slot is empty) unless this eviction has done so already */
+static int scan_chunks(nvs_engine *e, struct slot *s, struct chunk **cs, uint32_t n, nvs_xfer_report *rep)
+{
+	uint32_t m = 0;
+	int rc = 0;
+	if (s->n_chunks != 0 || n > s->cap_chunks)
+		return NVS_E_BAD_ARG;
+	for (uint32_t k = 0; k < n; ++k) {
+		struct chunk *c = cs[k];
+		if (c->scanned)
+			continue;
+		/* does it still have the backing copy it kept?  (from here on nobody can take it) */
+		c->had_backing = (uint8_t)(c->backing && backing_reclaim(e, c));
+		s->chunks[m++] = c;
+	}
+	if (m) {
+		s->n_chunks = m;
+		rc = scan_slot(e, s, rep);
+	}
+	s->n_chunks = 0;
+	return rc;
+}
+
 static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out, int best_effort)
 {
 	nvs_xfer_report rep;
@@ -1623,8 +2050,8 @@ static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_ou
 	pthread_mutex_lock(&e->api_mu);
 	pthread_mutex_lock(&e->mu);
 
-	/* victims: resident chunks, least recently fetched first */
-	size_t n_res = 0, n_vict = 0;
+	size_t n_res = 0, n_all = 0, n_vict = 0;
+	uint64_t resident = 0;
 	for (struct alloc *a = e->head; a; a = a->next)
 		if (!a->passthrough)
 			n_res += a->n_chunks;
@@ -1637,20 +2064,48 @@ static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_ou
 		if (a->passthrough)
 			continue;
 		for (uint32_t i = 0; i < a->n_chunks; ++i)
-			if (a->chunks[i].state == CH_RESIDENT)
-				victims[n_vict++] = &a->chunks[i];
+			if (a->chunks[i].state == CH_RESIDENT) {
+				victims[n_all++] = &a->chunks[i];
+				resident += a->chunks[i].bytes;
+				a->chunks[i].est_copy = 0;
+			}
 	}
-	qsort(victims, n_vict, sizeof(*victims), cmp_chunk_lru);
-	if (min_bytes) {
+	n_vict = n_all;
+	const int can_scan = e->cfg.elide_constant || e->cfg.retain;
+	if (min_bytes && min_bytes < resident) {
+		/* a partial eviction chooses: learn first what each chunk would cost (one pass of the
+		 * scan kernel over everything resident, at HBM speed), then take the cheapest */
+		if (can_scan) {
+			struct slot *s = &e->slots[0];
+			for (size_t i = 0; i < n_all;) {
+				uint32_t n = 0;
+				uint64_t b = 0;
+				while (i + n < n_all && n < s->cap_chunks && (b + victims[i + n]->bytes) / SLAB <= s->cap_aux &&
+				       b < 4 * e->cfg.batch_bytes) {
+					b += victims[i + n]->bytes;
+					++n;
+				}
+				if ((rc = scan_chunks(e, s, &victims[i], n, &rep)) != 0)
+					goto out;
+				i += n;
+			}
+		}
+		qsort(victims, n_all, sizeof(*victims), cmp_chunk_victim);
 		uint64_t acc = 0;
 		size_t k = 0;
-		while (k < n_vict && acc < min_bytes)
+		while (k < n_all && acc < min_bytes)
 			acc += victims[k++]->bytes;
 		n_vict = k;
+		/* the rest stays: a backing copy it had validated goes back to being reclaimable */
+		for (size_t j = n_vict; j < n_all; ++j) {
+			struct chunk *c = victims[j];
+			const int had = c->had_backing;
+			scan_forget(c);
+			if (had)
+				backing_mark_retained(e, c);
+		}
 	}
 
-	const uint32_t variant = e->cfg.evict_variant;
-	int started = 0;
 	unsigned batch_no = 0;
 	size_t i = 0;
 	while (i < n_vict) {
@@ -1658,8 +2113,7 @@ static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_ou
 		if ((rc = evict_retire(e, s, &rep)) != 0)
 			goto out;
 		uint64_t batch = 0, copied = 0;
-		int peer_traffic = 0;
-		/* 1. which chunks, 2. which of their slabs are same-filled, 3. backing + descriptors */
+		/* 1. which chunks, 2. what do their slabs need, 3. backing + descriptors */
 		struct chunk **picked = &victims[i];
 		uint32_t n_picked = 0;
 		while (i < n_vict && batch < e->cfg.batch_bytes && n_picked < s->cap_chunks &&
@@ -1668,33 +2122,36 @@ static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_ou
 			++n_picked;
 			++i;
 		}
-		if (e->cfg.elide_constant) {
-			for (uint32_t k = 0; k < n_picked; ++k)
-				s->chunks[k] = picked[k];
-			s->n_chunks = n_picked;
-			if ((rc = scan_slot(e, s, &rep)) != 0)
+		if (can_scan) {
+			if ((rc = scan_chunks(e, s, picked, n_picked, &rep)) != 0)
 				goto out;
-			s->n_chunks = 0;
+		} else {
+			for (uint32_t k = 0; k < n_picked; ++k) {
+				struct chunk *c = picked[k];
+				c->had_backing = (uint8_t)(c->backing && backing_reclaim(e, c));
+				mask_fill(c->cpmask, (uint32_t)(c->bytes / SLAB));
+				c->est_copy = c->bytes;
+				c->scanned = 1;
+			}
 		}
 		int tier_full = 0, must_drain = 0, any_busy = 0;
 		for (unsigned q = 0; q < N_SLOTS; ++q)
 			any_busy |= e->slots[q].busy;
 		for (uint32_t k = 0; k < n_picked; ++k) {
 			struct chunk *c = picked[k];
-			const uint64_t moving = c->bytes - (uint64_t)c->n_const * SLAB;
+			const uint32_t n = (uint32_t)(c->bytes / SLAB);
+			const uint64_t moving = c->est_copy;
+			if (c->n_const == n && c->backing)
+				backing_release(e, c); /* nothing but same-filled slabs: 8 bytes each describe it */
 			/* Only wait for room in the backing tier with nothing of ours in flight: the units we
 			 * wait for come back when another client fetches, and it can only fetch into the HBM
 			 * that our already-copied batches still hold until they are retired. */
 			const int nowait = best_effort || k > 0 || any_busy;
-			if (moving && (rc = backing_assign(e, c, nowait)) != 0) {
+			if (c->n_const != n && !c->backing && (rc = backing_assign(e, c, nowait)) != 0) {
 				if (!(nowait && rc == NVS_E_HOST_OOM))
 					goto out;
 				/* the tier is full: this chunk and the rest of the batch stay where they are ... */
 				rc = 0;
-				for (uint32_t j = k; j < n_picked; ++j) {
-					memset(picked[j]->cmask, 0, sizeof(picked[j]->cmask));
-					picked[j]->n_const = 0;
-				}
 				if (best_effort) {
 					tier_full = 1; /* ... for good */
 				} else {
@@ -1703,26 +2160,24 @@ static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_ou
 				}
 				break;
 			}
-			if (slot_push_chunk(s, c, 1, variant) != 0) {
+			if (slot_push_chunk(e, s, c, 1, c->cpmask) != 0) {
 				rc = NVS_E_BAD_ARG;
 				goto out;
 			}
 			copied += moving;
-			peer_traffic |= c->tier >= TIER_PEER0;
 			if (c->tier >= TIER_PEER0)
 				rep.peer_bytes += moving;
 			else
 				rep.host_bytes += moving;
+			rep.elided_bytes += (uint64_t)c->n_const * SLAB;
+			rep.clean_bytes += c->bytes - (uint64_t)c->n_const * SLAB - moving;
 		}
 		if (s->n_chunks) {
-			started = 1;
 			CK(e, e->d.EventRecord(s->begin, e->stream));
-			if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, variant,
-					       grid_for(e, 0, peer_traffic))) != 0)
+			if ((rc = slot_launch(e, s, kernel_variant(e, 1), &rep)) != 0)
 				goto out;
 			CK(e, e->d.EventRecord(s->done, e->stream));
 			s->busy = 1;
-			rep.launches += variant == NVS_COPY_CE ? s->n_descs : (s->n_descs ? 1 : 0);
 			rep.bytes += copied;
 			rep.slabs += copied / SLAB;
 			batch_no++;
@@ -1734,7 +2189,6 @@ static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_ou
 				if ((rc = evict_retire(e, &e->slots[q], &rep)) != 0)
 					goto out;
 	}
-	(void)started;
 	for (unsigned k = 0; k < N_SLOTS; ++k) {
 		int r = evict_retire(e, &e->slots[(batch_no + k) % N_SLOTS], &rep);
 		if (r != 0 && rc == 0)
@@ -1744,6 +2198,7 @@ static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_ou
 		e->resident_mode = 0; /* everything is out: the owner no longer holds the GPU */
 	e->st.n_evicts++;
 	e->st.evicted_bytes_total += rep.bytes;
+	e->st.clean_skipped_bytes_total += rep.clean_bytes;
 out:
 	if (rc != 0) /* never leave copies in flight behind an error */
 		e->d.StreamSynchronize(e->stream);
@@ -1751,12 +2206,22 @@ out:
 		e->slots[k].busy = 0;
 		slot_reset(&e->slots[k]);
 	}
+	/* chunks this call looked at but did not put out (it stopped early, or failed) */
+	for (size_t j = 0; victims && j < n_all; ++j) {
+		struct chunk *c = victims[j];
+		if (c->state == CH_RESIDENT && (c->scanned || c->nh || c->had_backing)) {
+			const int had = c->had_backing;
+			scan_forget(c);
+			if (had)
+				backing_mark_retained(e, c);
+		}
+	}
 	rep.wall_ms = now_ms() - t_begin;
 	pthread_mutex_unlock(&e->mu);
 	pthread_mutex_unlock(&e->api_mu);
 	ctx_leave(e);
 	free(victims);
-	if (rc == 0 && (rep.bytes || rep.elided_bytes))
+	if (rc == 0 && (rep.bytes || rep.elided_bytes || rep.clean_bytes))
 		report_emit(e, "evict", &rep);
 	if (rep_out)
 		*rep_out = rep;
@@ -1839,7 +2304,7 @@ static int fetch_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
 		if (rep && e->d.EventElapsedTime(&ms, s->begin, s->done) == CUDA_SUCCESS)
 			rep->copy_ms += ms;
 		for (uint32_t i = 0; i < s->n_chunks; ++i)
-			backing_release(e, s->chunks[i]);
+			backing_after_fetch(e, s->chunks[i]); /* kept (reclaimable) or given back at once */
 	}
 out:
 	s->busy = 0;
@@ -1861,7 +2326,6 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 	pthread_mutex_lock(&e->mu);
 	e->epoch++;
 
-	const uint32_t variant = e->cfg.fetch_variant;
 	int started = 0, deferred = 0;
 	unsigned batch_no = 0;
 	struct alloc *a = e->head;
@@ -1875,7 +2339,6 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 		if (remaining && (rc = wait_for_hbm_burst(e, remaining, &rep)) != 0)
 			goto out;
 		uint64_t batch = 0, copy_bytes = 0;
-		int peer_traffic = 0;
 		double t0 = now_ms();
 		while (a && batch < e->cfg.batch_bytes) {
 			if (a->passthrough || ci >= a->n_chunks) {
@@ -1889,7 +2352,7 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 				continue;
 			}
 			if (s->n_chunks == s->cap_chunks || s->n_descs + c->bytes / SLAB > s->cap_descs ||
-			    s->n_aux + c->bytes / SLAB > s->cap_aux)
+			    s->n_ce + c->bytes / SLAB > s->cap_ce || s->n_aux + c->bytes / SLAB > s->cap_aux)
 				break;
 			double w = 0;
 			if ((deferred = chunk_map(e, c, &w)) != 0)
@@ -1898,7 +2361,11 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 			rep.chunks++;
 			if (c->state == CH_SWAPPED) {
 				const uint64_t moving = c->bytes - (uint64_t)c->n_const * SLAB;
-				slot_push_chunk(s, c, 0, variant);
+				uint64_t want[MAX_CHUNK_SLABS / 64]; /* every slab that has bytes in the backing */
+				mask_fill(want, (uint32_t)(c->bytes / SLAB));
+				for (uint32_t k = 0; k < MAX_CHUNK_SLABS / 64; ++k)
+					want[k] &= ~c->cmask[k];
+				slot_push_chunk(e, s, c, 0, want);
 				/* same-filled slabs are re-created on the device instead of copied */
 				for (uint32_t k = 0; c->n_const && k < c->bytes / SLAB; ++k) {
 					if (!slab_is_const(c, k) || s->n_aux == s->cap_aux)
@@ -1911,7 +2378,6 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 				}
 				rep.elided_bytes += (uint64_t)c->n_const * SLAB;
 				copy_bytes += moving;
-				peer_traffic |= c->tier >= TIER_PEER0;
 				if (c->tier >= TIER_PEER0)
 					rep.peer_bytes += moving;
 				else
@@ -1931,17 +2397,16 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 				rc = NVS_E_BAD_ARG;
 			break;
 		}
-		if (s->n_descs || s->n_aux) {
+		if (s->n_descs || s->n_ce || s->n_aux) {
 			started = 1;
 			CK(e, e->d.EventRecord(s->begin, e->stream));
-			if ((rc = launch_descs(e, s->descs_dev, s->descs, s->n_descs, variant,
-					       grid_for(e, 0, peer_traffic))) != 0)
+			if ((rc = slot_launch(e, s, kernel_variant(e, 0), &rep)) != 0)
 				goto out;
-			if ((rc = launch_aux(e, e->fn_splat, s, e->stream, 0)) != 0)
+			if ((rc = launch_aux(e, e->fn_splat, s, e->stream, 0, 0)) != 0)
 				goto out;
 			CK(e, e->d.EventRecord(s->done, e->stream));
 			s->busy = 1;
-			rep.launches += (variant == NVS_COPY_CE ? s->n_descs : (s->n_descs ? 1 : 0)) + (s->n_aux ? 1 : 0);
+			rep.launches += s->n_aux ? 1 : 0;
 			rep.bytes += copy_bytes;
 			rep.slabs += copy_bytes / SLAB;
 		}
@@ -1966,7 +2431,7 @@ out:
 		/* batches already launched have landed: their backing is no longer needed */
 		for (unsigned k = 0; k < N_SLOTS; ++k)
 			for (uint32_t i = 0; e->slots[k].busy && i < e->slots[k].n_chunks; ++i)
-				backing_release(e, e->slots[k].chunks[i]);
+				backing_after_fetch(e, e->slots[k].chunks[i]);
 	}
 	for (unsigned k = 0; k < N_SLOTS; ++k) {
 		e->slots[k].busy = 0;
@@ -2144,7 +2609,10 @@ int nvs_free_sized(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes)
 				chunk_unmap(e, c);
 			backing_release(e, c);
 			free(c->cvals);
+			free(c->hash);
+			free(c->nh);
 			c->cvals = NULL;
+			c->hash = c->nh = NULL;
 			uint64_t *ctr = c->state == CH_RESIDENT ? &e->st.resident_bytes
 					: c->state == CH_SWAPPED ? &e->st.swapped_bytes
 								 : &e->st.unbacked_bytes;
@@ -2169,9 +2637,12 @@ out:
 
 static struct alloc *table_find_range(nvs_engine *e, uint64_t addr, uint64_t bytes)
 {
-	for (struct alloc *a = e->head; a; a = a->next)
-		if (addr >= a->va && addr - a->va < a->va_bytes)
-			return bytes <= a->va_bytes - (addr - a->va) ? a : NULL;
+	const size_t at = by_va_upper(e, addr);
+	if (at == 0)
+		return NULL;
+	struct alloc *a = e->by_va[at - 1];
+	if (addr - a->va < a->va_bytes)
+		return bytes <= a->va_bytes - (addr - a->va) ? a : NULL;
 	return NULL;
 }
 
@@ -2330,9 +2801,12 @@ int nvs_host_io(nvs_engine *e, uint64_t dptr, void *host, uint64_t bytes, int to
 				if (s_end == hi)
 					break;
 			}
-			if (to_device)
+			if (to_device) {
+				/* the backing copy changes under its recorded hashes: they no longer describe it */
+				for (uint32_t k = (uint32_t)(at / SLAB); (uint64_t)k * SLAB < s_end; ++k)
+					c->bvalid[k >> 6] &= ~(1ull << (k & 63));
 				par_memcpy(b + at, h, s_end - at);
-			else
+			} else
 				par_memcpy(h, b + at, s_end - at);
 			h += s_end - at;
 			at = s_end;
@@ -2343,6 +2817,23 @@ int nvs_host_io(nvs_engine *e, uint64_t dptr, void *host, uint64_t bytes, int to
 out:
 	pthread_mutex_unlock(&e->mu);
 	pthread_mutex_unlock(&e->api_mu);
+	return rc;
+}
+
+int nvs_touch(nvs_engine *e, uint64_t dptr, uint64_t bytes)
+{
+	if (!e || bytes == 0)
+		return NVS_E_BAD_ARG;
+	int rc = NVS_E_NOT_OURS;
+	pthread_mutex_lock(&e->mu);
+	struct alloc *a = table_find_range(e, dptr, bytes);
+	if (a && !a->passthrough) {
+		const uint64_t off0 = dptr - a->va, now = ++e->touch_clock;
+		for (uint32_t ci = (uint32_t)(off0 / e->cfg.chunk_bytes); ci <= (uint32_t)((off0 + bytes - 1) / e->cfg.chunk_bytes); ++ci)
+			a->chunks[ci].touch = now;
+		rc = 0;
+	}
+	pthread_mutex_unlock(&e->mu);
 	return rc;
 }
 
@@ -2392,6 +2883,54 @@ int nvs_copy_slabs(nvs_engine *e, const nvs_copy_desc *descs, uint32_t n, uint32
 	CK(e, e->d.EventSynchronize(e->ev_end));
 	if (ms_out)
 		CK(e, e->d.EventElapsedTime(ms_out, e->ev_begin, e->ev_end));
+out:
+	if (rc != 0)
+		e->d.StreamSynchronize(e->stream);
+	if (staging)
+		e->d.MemFreeHost(staging);
+	pthread_mutex_unlock(&e->mu);
+	pthread_mutex_unlock(&e->api_mu);
+	ctx_leave(e);
+	return rc;
+}
+
+int nvs_scan_slabs(nvs_engine *e, const nvs_copy_desc *descs, uint32_t n, int want_hash, nvs_scan_out *out, float *ms_out)
+{
+	if (!e || (!descs && n) || (!out && n))
+		return NVS_E_BAD_ARG;
+	for (uint32_t i = 0; i < n; ++i)
+		if ((descs[i].src & 15ull) || (descs[i].bytes & 15ull) || descs[i].bytes == 0)
+			return NVS_E_BAD_ARG;
+	if (n == 0)
+		return 0;
+	int rc = 0;
+	void *staging = NULL;
+	if (ctx_enter(e) != 0)
+		return CTX_GONE;
+	pthread_mutex_lock(&e->api_mu);
+	pthread_mutex_lock(&e->mu);
+	const size_t in_bytes = (size_t)n * sizeof(nvs_copy_desc), out_bytes = (size_t)n * sizeof(struct scan_result);
+	CUdeviceptr dev = 0;
+	CK(e, e->d.MemHostAlloc(&staging, in_bytes + out_bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+	memcpy(staging, descs, in_bytes);
+	if (e->d.MemHostGetDevicePointer(&dev, staging, 0) != CUDA_SUCCESS)
+		dev = (CUdeviceptr)(uintptr_t)staging;
+	{
+		/* a private counter: this entry point may be handed any number of descriptors */
+		CUdeviceptr counter = e->scratch + 16, out_dev = dev + in_bytes;
+		uint32_t nn = n, wh = want_hash ? 1u : 0u;
+		unsigned grid = n < (unsigned)e->n_sms * 4u ? n : (unsigned)e->n_sms * 4u;
+		void *params[] = {&dev, &nn, &counter, &out_dev, &wh};
+		CK(e, e->d.MemsetD32Async(counter, 0, 1, e->stream));
+		CK(e, e->d.EventRecord(e->ev_begin, e->stream));
+		CK(e, e->d.LaunchKernel(e->fn_scan, grid, 1, 1, 256, 1, 1, 0, e->stream, params, NULL));
+		CK(e, e->d.EventRecord(e->ev_end, e->stream));
+		CK(e, e->d.EventSynchronize(e->ev_end));
+		e->st.kernel_launches_total++;
+		if (ms_out)
+			CK(e, e->d.EventElapsedTime(ms_out, e->ev_begin, e->ev_end));
+		memcpy(out, (char *)staging + in_bytes, out_bytes);
+	}
 out:
 	if (rc != 0)
 		e->d.StreamSynchronize(e->stream);
@@ -2467,6 +3006,7 @@ static void slots_free(nvs_engine *e)
 		if (s->begin)
 			e->d.EventDestroy(s->begin);
 		free(s->chunks);
+		free(s->ce);
 		memset(s, 0, sizeof(*s));
 	}
 }
@@ -2497,6 +3037,11 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	    (uint64_t)e->cfg.tma_warps * e->cfg.tma_stages * e->cfg.tma_tile_bytes > 200u * 1024u ||
 	    e->cfg.ldg_threads == 0 || e->cfg.ldg_threads > 1024 || (e->cfg.ldg_threads & 31) ||
 	    e->cfg.n_peers < 0 || e->cfg.n_peers > NVS_MAX_PEERS) {
+		free(e);
+		return NVS_E_BAD_ARG;
+	}
+	if (e->cfg.evict_variant > NVS_COPY_CE || e->cfg.fetch_variant > NVS_COPY_CE ||
+	    e->cfg.peer_evict_variant > NVS_COPY_CE || e->cfg.peer_fetch_variant > NVS_COPY_CE) {
 		free(e);
 		return NVS_E_BAD_ARG;
 	}
@@ -2546,7 +3091,8 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	CK(e, e->d.FuncSetAttribute(e->fn_tma, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024));
 	CK(e, e->d.StreamCreate(&e->stream, CU_STREAM_NON_BLOCKING));
 	CK(e, e->d.StreamCreate(&e->scan_stream, CU_STREAM_NON_BLOCKING));
-	CK(e, e->d.EventCreate(&e->scan_done, CU_EVENT_DISABLE_TIMING));
+	CK(e, e->d.EventCreate(&e->scan_done, CU_EVENT_DEFAULT));
+	CK(e, e->d.EventCreate(&e->scan_begin, CU_EVENT_DEFAULT));
 	CK(e, e->d.EventCreate(&e->ev_begin, CU_EVENT_DEFAULT));
 	CK(e, e->d.EventCreate(&e->ev_end, CU_EVENT_DEFAULT));
 	CK(e, e->d.MemAlloc(&e->counters, 4 * 2 * N_COUNTERS));
@@ -2557,9 +3103,17 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	{
 		/* one slot holds one batch: batch_bytes / SLAB descriptors (+ one chunk of slack) */
 		uint32_t cap_descs = (uint32_t)((e->cfg.batch_bytes + e->cfg.chunk_bytes) / SLAB);
-		uint32_t cap_chunks = cap_descs; /* worst case: every chunk is a single slab */
+		/* the scan lists are longer: a partial eviction first scans everything resident, 4 batches per launch */
+		uint32_t cap_aux = (uint32_t)((4 * e->cfg.batch_bytes + e->cfg.chunk_bytes) / SLAB);
+		uint32_t cap_chunks = cap_aux; /* worst case: every chunk is a single slab */
 		for (unsigned k = 0; k < N_SLOTS; ++k) {
 			struct slot *s = &e->slots[k];
+			s->ce = calloc(cap_descs, sizeof(nvs_copy_desc));
+			s->cap_ce = cap_descs;
+			if (!s->ce) {
+				rc = CUDA_ERROR_OUT_OF_MEMORY;
+				goto out;
+			}
 			CK(e, e->d.MemHostAlloc((void **)&s->descs, (size_t)cap_descs * sizeof(nvs_copy_desc),
 						CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
 			CUdeviceptr dp = 0;
@@ -2567,13 +3121,13 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 				dp = (CUdeviceptr)(uintptr_t)s->descs;
 			s->descs_dev = dp;
 			s->cap_descs = cap_descs;
-			CK(e, e->d.MemHostAlloc((void **)&s->aux, (size_t)cap_descs * sizeof(nvs_copy_desc),
+			CK(e, e->d.MemHostAlloc((void **)&s->aux, (size_t)cap_aux * sizeof(nvs_copy_desc),
 						CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
 			if (e->d.MemHostGetDevicePointer(&dp, s->aux, 0) != CUDA_SUCCESS)
 				dp = (CUdeviceptr)(uintptr_t)s->aux;
 			s->aux_dev = dp;
-			s->cap_aux = cap_descs;
-			CK(e, e->d.MemHostAlloc((void **)&s->scan_out, (size_t)cap_descs * sizeof(struct scan_result),
+			s->cap_aux = cap_aux;
+			CK(e, e->d.MemHostAlloc((void **)&s->scan_out, (size_t)cap_aux * sizeof(struct scan_result),
 						CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
 			if (e->d.MemHostGetDevicePointer(&dp, s->scan_out, 0) != CUDA_SUCCESS)
 				dp = (CUdeviceptr)(uintptr_t)s->scan_out;
@@ -2659,8 +3213,7 @@ void nvs_engine_destroy(nvs_engine *e)
 		for (struct arena *a = e->host_pool.arenas, *nx; a; a = nx) {
 			nx = a->next;
 			e->d.MemFreeHost(a->host_base);
-			free(a->bitmap);
-			free(a);
+			arena_free(a);
 		}
 		for (int i = 0; i < NVS_MAX_PEERS; ++i)
 			for (struct arena *a = e->peer_pools[i].arenas, *nx; a; a = nx) {
@@ -2668,8 +3221,7 @@ void nvs_engine_destroy(nvs_engine *e)
 				e->d.MemUnmap(a->dev_base, a->bytes);
 				e->d.MemAddressFree(a->dev_base, a->bytes);
 				e->d.MemRelease(a->handle);
-				free(a->bitmap);
-				free(a);
+				arena_free(a);
 			}
 		slots_free(e);
 		if (e->counters)
@@ -2686,6 +3238,8 @@ void nvs_engine_destroy(nvs_engine *e)
 			e->d.StreamDestroy(e->scan_stream);
 		if (e->scan_done)
 			e->d.EventDestroy(e->scan_done);
+		if (e->scan_begin)
+			e->d.EventDestroy(e->scan_begin);
 		if (e->module)
 			e->d.ModuleUnload(e->module);
 		ctx_leave(e);
@@ -2696,5 +3250,6 @@ void nvs_engine_destroy(nvs_engine *e)
 	pthread_mutex_destroy(&e->api_mu);
 	pthread_cond_destroy(&e->pin_cv);
 	pthread_cond_destroy(&e->grow_cv);
+	free(e->by_va);
 	free(e);
 }

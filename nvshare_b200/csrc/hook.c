@@ -169,6 +169,7 @@ static void *gate_real[G_COUNT][2];
 static void after_launch(void);
 
 static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_device, CUstream s);
+static int touch_dst(CUdeviceptr dev, size_t n);
 #define NO_BYPASS 0
 
 /* `bypass`: an expression that is non-zero when the call has been served without
@@ -220,8 +221,8 @@ GATED_(cuMemcpyHtoDAsync, 0, (CUdeviceptr dst, const void *src, size_t n, CUstre
 GATED_(cuMemcpyDtoH, 0, (void *dst, CUdeviceptr src, size_t n), (dst, src, n), host_io_bypass(src, dst, n, 0, NULL))
 GATED_(cuMemcpyDtoHAsync, 0, (void *dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s),
        host_io_bypass(src, dst, n, 0, s))
-GATED(cuMemcpyDtoD, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n), (dst, src, n))
-GATED(cuMemcpyDtoDAsync, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
+GATED_(cuMemcpyDtoD, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n), (dst, src, n), touch_dst(dst, n))
+GATED_(cuMemcpyDtoDAsync, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s), touch_dst(dst, n))
 GATED(cuMemcpyPeer, 0, (CUdeviceptr dst, CUcontext dc, CUdeviceptr src, CUcontext sc, size_t n), (dst, dc, src, sc, n))
 GATED(cuMemcpyPeerAsync, 0, (CUdeviceptr dst, CUcontext dc, CUdeviceptr src, CUcontext sc, size_t n, CUstream s),
       (dst, dc, src, sc, n, s))
@@ -232,12 +233,12 @@ GATED(cuMemcpy3D, 0, (const void *p), (p))
 GATED(cuMemcpy3DAsync, 0, (const void *p, CUstream s), (p, s))
 GATED(cuMemcpy3DPeer, 0, (const void *p), (p))
 GATED(cuMemcpy3DPeerAsync, 0, (const void *p, CUstream s), (p, s))
-GATED(cuMemsetD8, 0, (CUdeviceptr d, unsigned char v, size_t n), (d, v, n))
-GATED(cuMemsetD16, 0, (CUdeviceptr d, unsigned short v, size_t n), (d, v, n))
-GATED(cuMemsetD32, 0, (CUdeviceptr d, u32 v, size_t n), (d, v, n))
-GATED(cuMemsetD8Async, 0, (CUdeviceptr d, unsigned char v, size_t n, CUstream s), (d, v, n, s))
-GATED(cuMemsetD16Async, 0, (CUdeviceptr d, unsigned short v, size_t n, CUstream s), (d, v, n, s))
-GATED(cuMemsetD32Async, 0, (CUdeviceptr d, u32 v, size_t n, CUstream s), (d, v, n, s))
+GATED_(cuMemsetD8, 0, (CUdeviceptr d, unsigned char v, size_t n), (d, v, n), touch_dst(d, n))
+GATED_(cuMemsetD16, 0, (CUdeviceptr d, unsigned short v, size_t n), (d, v, n), touch_dst(d, 2 * n))
+GATED_(cuMemsetD32, 0, (CUdeviceptr d, u32 v, size_t n), (d, v, n), touch_dst(d, 4 * n))
+GATED_(cuMemsetD8Async, 0, (CUdeviceptr d, unsigned char v, size_t n, CUstream s), (d, v, n, s), touch_dst(d, n))
+GATED_(cuMemsetD16Async, 0, (CUdeviceptr d, unsigned short v, size_t n, CUstream s), (d, v, n, s), touch_dst(d, 2 * n))
+GATED_(cuMemsetD32Async, 0, (CUdeviceptr d, u32 v, size_t n, CUstream s), (d, v, n, s), touch_dst(d, 4 * n))
 GATED(cuMemsetD2D8, 0, (CUdeviceptr d, size_t pitch, unsigned char v, size_t w, size_t h), (d, pitch, v, w, h))
 GATED(cuMemsetD2D16, 0, (CUdeviceptr d, size_t pitch, unsigned short v, size_t w, size_t h), (d, pitch, v, w, h))
 GATED(cuMemsetD2D32, 0, (CUdeviceptr d, size_t pitch, u32 v, size_t w, size_t h), (d, pitch, v, w, h))
@@ -579,9 +580,21 @@ static nvs_engine *engine_get(void)
  * there first the range is resident and the call goes down the gated path.
  * NVSHARE_LOCKFREE_COPY=0 turns it off.
  */
+/* Recency hint for partial evictions: the application is writing this range from the host side of
+ * the API.  Always 0: the call itself still goes through the gate. */
+static int touch_dst(CUdeviceptr dev, size_t n)
+{
+	nvs_engine *e = __atomic_load_n(&engine, __ATOMIC_ACQUIRE);
+	if (e && n)
+		nvs_touch(e, (uint64_t)dev, (uint64_t)n);
+	return 0;
+}
+
 static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_device, CUstream s)
 {
 	static int enabled = -1;
+	if (to_device)
+		touch_dst(dev, n);
 	if (enabled < 0) {
 		const char *v = getenv("NVSHARE_LOCKFREE_COPY");
 		enabled = !(v && *v && atoi(v) == 0);

@@ -238,64 +238,140 @@ nvs_slab_copy_ldg(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uin
 	}
 }
 
-/* ------------------------------------------- same-filled slab elision ----- */
+/* --------------------------- same-filled slab elision + clean-slab hash ----- */
 
 /*
- * A slab whose 64-bit words are all equal (zero-initialised buffers, ones(),
- * padding, freshly memset workspaces -- the reference's own test tensors are
- * torch.ones) does not have to cross the link at all: 8 bytes describe it.
- * HBM is ~120x faster than PCIe Gen5 x16 on this part, so looking at every
- * byte before moving it costs ~1 % of the move it may save.  The copy engines
- * cannot do this; it is what the SMs are for on this path.
+ * Two ways of not moving a slab at all, both decided by ONE pass of the SMs over it
+ * at HBM speed (~120x the PCIe link, ~9x NVLink) -- the copy engines cannot do either:
  *
- *   nvs_slab_scan    one CTA per slab: out[i] = {word 0, all words equal?},
- *                    leaving the slab at the first 32 KiB tile that differs
- *   nvs_slab_splat   the inverse: fill dst with the 64-bit value held in src
+ *  - same-filled: all 64-bit words equal (zero-initialised buffers, ones(), padding,
+ *    memset workspaces -- the reference's own test tensors are torch.ones): 8 bytes
+ *    describe it, nvs_slab_splat re-creates it at fetch.
+ *  - clean: the backing copy kept from the last hand-off still matches.  VMM memory
+ *    has no dirty bits, so "matches" is decided by a 128-bit content hash of the slab
+ *    compared with the hash recorded when that backing copy was written.
+ *
+ *   nvs_slab_scan    one CTA (256 threads) per slab: out[i] = {word 0, all words
+ *                    equal?, h0, h1}.  want_hash == 0: leaves the slab at the first
+ *                    32 KiB tile that differs (h0 = h1 = 0).  want_hash != 0: reads
+ *                    every byte.
+ *   nvs_slab_splat   the inverse of same-filled: fill dst with the 64-bit value
+ *
+ * The hash (restated in C by oracle/nvshare_oracle.c: oracle_slab_hash, and checked
+ * against it bit for bit on the GPU).  The slab is a sequence of 16-byte vectors
+ * (x, y, z, w); lane t of 256 owns vectors t, t+256, t+512, ... in that order and runs
+ * four independent xxHash32 rounds over them,
+ *      a_k = rotl32(a_k + word_k * P2, 13) * P1        a_k(0) = SEED_k ^ (t * P1)
+ * each of which is a bijection of a_k for a fixed word and injective in the word for a
+ * fixed a_k.  A lane's four accumulators go through a 128-bit bijection (two Feistel
+ * steps + SplitMix64 finalisers, lane index mixed in) and the slab hash is the pair of
+ * 64-bit sums over the lanes.  Consequences: ANY change confined to one lane's stream
+ * (in particular any single-word change) is detected with certainty; changes spread
+ * over several lanes escape with probability ~2^-128.  12 integer instructions per
+ * 16 bytes: the pass stays HBM-bound (148 SMs x 128 lanes x 1.9 GHz / 12 x 16 B = 48 TB/s
+ * of hashing capacity against 6.5-7.7 TB/s of HBM).
  */
 struct nvs_scan_result {
 	unsigned long long value;
 	unsigned long long is_const;
+	unsigned long long h0, h1;
 };
 
+#define NVS_SCAN_THREADS 256
 #define NVS_SCAN_UNROLL 8
+#define NVS_H_P1 0x9E3779B1u
+#define NVS_H_P2 0x85EBCA77u
 
-extern "C" __global__ void __launch_bounds__(256)
+__host__ __device__ __forceinline__ uint32_t nvs_rotl32(uint32_t x, int r)
+{
+	return (x << r) | (x >> (32 - r));
+}
+
+__host__ __device__ __forceinline__ unsigned long long nvs_mix64(unsigned long long z)
+{
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+#define NVS_H_ROUND(a, w) a = nvs_rotl32((a) + (w) * NVS_H_P2, 13) * NVS_H_P1
+
+extern "C" __global__ void __launch_bounds__(NVS_SCAN_THREADS)
 nvs_slab_scan(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uint32_t *counter,
-	      nvs_scan_result *__restrict__ out)
+	      nvs_scan_result *__restrict__ out, uint32_t want_hash)
 {
 	__shared__ uint32_t s_idx;
+	__shared__ unsigned long long s_red[2][NVS_SCAN_THREADS / 32];
+	const uint32_t t = threadIdx.x;
 	for (;;) {
 		__syncthreads();
-		if (threadIdx.x == 0)
+		if (t == 0)
 			s_idx = atomicAdd(counter, 1u);
 		__syncthreads();
 		const uint32_t idx = s_idx;
 		if (idx >= n_descs)
 			return;
-		const ulonglong2 *__restrict__ p = reinterpret_cast<const ulonglong2 *>(descs[idx].src);
+		const uint4 *__restrict__ p = reinterpret_cast<const uint4 *>(descs[idx].src);
 		const uint64_t n16 = descs[idx].bytes >> 4;
 		const unsigned long long v0 = reinterpret_cast<const unsigned long long *>(descs[idx].src)[0];
-		const uint64_t step = (uint64_t)blockDim.x * NVS_SCAN_UNROLL;
+		const uint32_t v0lo = (uint32_t)v0, v0hi = (uint32_t)(v0 >> 32);
+		const uint64_t step = (uint64_t)NVS_SCAN_THREADS * NVS_SCAN_UNROLL;
+		uint32_t a0 = 0x243F6A88u ^ (t * NVS_H_P1), a1 = 0x85A308D3u ^ (t * NVS_H_P1);
+		uint32_t a2 = 0x13198A2Eu ^ (t * NVS_H_P1), a3 = 0x03707344u ^ (t * NVS_H_P1);
 		int differs = 0;
 		for (uint64_t base = 0; base < n16; base += step) {
-			ulonglong2 v[NVS_SCAN_UNROLL];
+			uint4 v[NVS_SCAN_UNROLL];
+			bool live[NVS_SCAN_UNROLL];
 #pragma unroll
 			for (int u = 0; u < NVS_SCAN_UNROLL; ++u) {
-				const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
-				v[u] = i < n16 ? __ldcs(p + i) : make_ulonglong2(v0, v0);
+				const uint64_t i = base + (uint64_t)u * NVS_SCAN_THREADS + t;
+				live[u] = i < n16;
+				v[u] = live[u] ? __ldcs(p + i) : make_uint4(v0lo, v0hi, v0lo, v0hi);
 			}
 			int d = 0;
 #pragma unroll
-			for (int u = 0; u < NVS_SCAN_UNROLL; ++u)
-				d |= (v[u].x != v0) | (v[u].y != v0);
-			if (__syncthreads_or(d)) {
+			for (int u = 0; u < NVS_SCAN_UNROLL; ++u) {
+				d |= (v[u].x != v0lo) | (v[u].y != v0hi) | (v[u].z != v0lo) | (v[u].w != v0hi);
+				if (live[u]) {
+					NVS_H_ROUND(a0, v[u].x);
+					NVS_H_ROUND(a1, v[u].y);
+					NVS_H_ROUND(a2, v[u].z);
+					NVS_H_ROUND(a3, v[u].w);
+				}
+			}
+			differs |= d;
+			if (!want_hash && __syncthreads_or(d)) {
 				differs = 1;
 				break;
 			}
 		}
-		if (threadIdx.x == 0) {
+		/* lane (a0..a3) -> 128 bits, bijectively, with the lane index mixed in */
+		unsigned long long u64 = ((unsigned long long)a0 << 32) | a1, w64 = ((unsigned long long)a2 << 32) | a3;
+		u64 ^= (unsigned long long)(t + 1) * 0x9E3779B97F4A7C15ull;
+		w64 ^= nvs_mix64(u64);
+		u64 ^= nvs_mix64(w64 + 0xD1B54A32D192ED03ull);
+		unsigned long long h0 = nvs_mix64(u64), h1 = nvs_mix64(w64);
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			h0 += __shfl_xor_sync(0xffffffffu, h0, o);
+			h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+		}
+		if ((t & 31u) == 0) {
+			s_red[0][t >> 5] = h0;
+			s_red[1][t >> 5] = h1;
+		}
+		const int any_differs = __syncthreads_or(differs);
+		if (t == 0) {
+			unsigned long long s0 = 0, s1 = 0;
+#pragma unroll
+			for (int w = 0; w < NVS_SCAN_THREADS / 32; ++w) {
+				s0 += s_red[0][w];
+				s1 += s_red[1][w];
+			}
 			out[idx].value = v0;
-			out[idx].is_const = !differs && (descs[idx].bytes & 15ull) == 0;
+			out[idx].is_const = !any_differs && (descs[idx].bytes & 15ull) == 0;
+			out[idx].h0 = want_hash ? s0 : 0ull;
+			out[idx].h1 = want_hash ? s1 : 0ull;
 		}
 	}
 }

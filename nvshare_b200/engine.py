@@ -36,7 +36,8 @@ class EngineConfig(C.Structure):
         ("peer_capacity_bytes", C.c_uint64), ("stats_path", C.c_char_p),
         ("pressure_cb", C.c_void_p), ("pressure_user", C.c_void_p),
         ("shared_pool_path", C.c_char_p), ("shared_pool_bytes", C.c_uint64), ("elide_constant", C.c_uint32),
-        ("burst_bytes", C.c_uint64),
+        ("burst_bytes", C.c_uint64), ("retain", C.c_uint32), ("peer_evict_variant", C.c_uint32),
+        ("peer_fetch_variant", C.c_uint32),
     ]
 
 
@@ -45,6 +46,7 @@ class XferReport(C.Structure):
         ("bytes", C.c_uint64), ("slabs", C.c_uint64), ("chunks", C.c_uint64), ("launches", C.c_uint64),
         ("wall_ms", C.c_double), ("copy_ms", C.c_double), ("map_ms", C.c_double), ("wait_ms", C.c_double),
         ("host_bytes", C.c_uint64), ("peer_bytes", C.c_uint64), ("elided_bytes", C.c_uint64),
+        ("clean_bytes", C.c_uint64), ("ce_calls", C.c_uint64), ("scanned_bytes", C.c_uint64), ("scan_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -56,10 +58,14 @@ class Stats(C.Structure):
         "n_allocs", "requested_bytes", "va_bytes", "resident_bytes", "swapped_bytes", "unbacked_bytes",
         "passthrough_bytes", "host_pool_bytes", "host_pool_used", "peer_pool_bytes", "peer_pool_used",
         "n_evicts", "n_fetches", "evicted_bytes_total", "fetched_bytes_total", "kernel_launches_total",
-        "host_io_bytes_total")]
+        "host_io_bytes_total", "retained_bytes", "clean_skipped_bytes_total", "stolen_slabs_total", "ce_calls_total")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class ScanOut(C.Structure):
+    _fields_ = [("value", C.c_uint64), ("is_const", C.c_uint64), ("h0", C.c_uint64), ("h1", C.c_uint64)]
 
 
 class EngineError(RuntimeError):
@@ -98,7 +104,9 @@ def load():
     lib.nvs_evict_best_effort.argtypes = [C.c_void_p, C.c_uint64, P(XferReport)]
     lib.nvs_get_stats.argtypes = [C.c_void_p, P(Stats)]
     lib.nvs_host_io.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
+    lib.nvs_touch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     lib.nvs_copy_slabs.argtypes = [C.c_void_p, P(CopyDesc), C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_float)]
+    lib.nvs_scan_slabs.argtypes = [C.c_void_p, P(CopyDesc), C.c_uint32, C.c_int, P(ScanOut), P(C.c_float)]
     lib.nvs_pattern_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
     lib.nvs_pattern_verify.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, P(C.c_uint64)]
     lib.nvs_strerror.argtypes = [C.c_int]
@@ -126,7 +134,7 @@ class Engine:
         lib = load()
         cfg = cfg or default_config()
         for k, v in overrides.items():
-            if k in ("evict_variant", "fetch_variant") and isinstance(v, str):
+            if k in ("evict_variant", "fetch_variant", "peer_evict_variant", "peer_fetch_variant") and isinstance(v, str):
                 v = VARIANTS[v]
             if k == "peers":
                 cfg.n_peers = len(v)
@@ -182,6 +190,9 @@ class Engine:
         _check(load().nvs_get_stats(self._h, C.byref(st)), "nvs_get_stats")
         return st.as_dict()
 
+    def touch(self, dptr: int, nbytes: int):
+        _check(load().nvs_touch(self._h, dptr, nbytes), "nvs_touch")
+
     def host_io(self, dptr: int, host_ptr: int, nbytes: int, to_device: bool) -> int:
         """nvs_host_io: 0 = served from / into the backing copy, NVS_E_NOT_OURS / NVS_E_NOT_SWAPPED =
         the caller must use the device path; anything else raises."""
@@ -209,3 +220,16 @@ class Engine:
         _check(load().nvs_pattern_verify(self._h, addr, n_words, first_index, seed, C.byref(bad)),
                "nvs_pattern_verify")
         return bad.value
+
+
+def scan_slabs(engine: Engine, descs, want_hash=True, with_ms=False):
+    """nvs_scan_slabs: run the sm_100a scan/hash kernel over (src, _, nbytes) ranges."""
+    descs = list(descs)
+    arr = (CopyDesc * max(len(descs), 1))()
+    for i, (s, _d, b) in enumerate(descs):
+        arr[i].src, arr[i].dst, arr[i].bytes, arr[i].tag = s, 0, b, i
+    out = (ScanOut * max(len(descs), 1))()
+    ms = C.c_float()
+    _check(load().nvs_scan_slabs(engine._h, arr, len(descs), 1 if want_hash else 0, out, C.byref(ms)), "nvs_scan_slabs")
+    res = [{"value": o.value, "is_const": o.is_const, "h0": o.h0, "h1": o.h1} for o in out[:len(descs)]]
+    return (res, ms.value) if with_ms else res

@@ -51,6 +51,8 @@ typedef unsigned long long CUmemGenericAllocationHandle;
 
 #define SLAB (2ull << 20)
 
+#include "slab_hash_ref.h"
+
 struct ledger {
 	volatile uint64_t used; /* physical "HBM" bytes in use across all attached processes */
 };
@@ -545,16 +547,21 @@ CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, uns
 		const struct desc *d = *(const struct desc **)params[0];
 		uint32_t n = *(uint32_t *)params[1];
 		uint32_t *counter = *(uint32_t **)params[2];
-		struct { uint64_t value, is_const; } *out = *(void **)params[3];
-		if (*counter != 0)
+		struct { uint64_t value, is_const, h0, h1; } *out = *(void **)params[3];
+		uint32_t want_hash = *(uint32_t *)params[4];
+		if (*counter != 0 || bx != 256)
 			return 999;
 		for (uint32_t i = 0; i < n; ++i) {
 			const uint64_t *p = (const uint64_t *)(uintptr_t)d[i].src;
-			uint64_t words = d[i].bytes / 8, k = 1;
+			uint64_t words = d[i].bytes / 8, k = 1, h[2] = {0, 0};
 			while (k < words && p[k] == p[0])
 				++k;
 			out[i].value = p[0];
 			out[i].is_const = (k == words) && (d[i].bytes & 15) == 0;
+			if (want_hash)
+				slab_hash_ref(p, d[i].bytes, h);
+			out[i].h0 = h[0];
+			out[i].h1 = h[1];
 		}
 		*counter = n + gx;
 		return OK;

@@ -51,7 +51,7 @@ def engine(fake):
     from nvshare_b200 import engine as E
     # elision off: most tests below move freshly mapped (all-zero) memory on purpose
     e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, batch_bytes=24 * MiB, oom_wait_ms=300,
-                 elide_constant=0)
+                 elide_constant=0, retain=0)
     yield e
     e.close()
 
@@ -65,7 +65,9 @@ def test_version_and_default_config(fake):
     assert b"sm_100a" in E.load().nvs_engine_version()
     cfg = E.default_config()
     assert cfg.chunk_bytes == 256 * MiB and cfg.host_arena_bytes == 1024 * MiB
-    assert cfg.evict_variant == E.COPY_TMA and cfg.fetch_variant == E.COPY_CE     # see engine.c: probe G
+    # pinned-host tier on the copy engines (256-byte TLPs), peer tier on the sm_100a kernel: engine.c, probes D/G
+    assert cfg.evict_variant == E.COPY_CE and cfg.fetch_variant == E.COPY_CE
+    assert cfg.peer_evict_variant == E.COPY_TMA and cfg.peer_fetch_variant == E.COPY_TMA and cfg.retain == 1
     assert cfg.tma_stages == 6 and cfg.tma_tile_bytes == 32768 and cfg.tma_warps == 1
 
 
@@ -251,7 +253,7 @@ def test_timed_out_fetch_leaves_a_consistent_table(fake, tmp_path):
         e.fetch_all()
         print("BAD", e.pattern_verify(p, 24 * MiB // 8, first_index=3, seed=99))
         st = e.stats()
-        print("POOL_USED", st["host_pool_used"])
+        print("POOL_USED", st["host_pool_used"] - st["retained_bytes"])    # kept copies are reclaimable, not in use
     """)
     env = dict(__import__("os").environ, FAKE_CUDA_TOTAL_MIB="40", FAKE_CUDA_LEDGER=str(ledger))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=60)
@@ -333,7 +335,9 @@ def test_same_filled_slabs_are_not_moved(fake, oracle):
         # a second cycle after the application changed a formerly same-filled slab
         view(p, 16)[:] = 9
         rep = e.evict(0)
-        assert rep["bytes"] == 4 * SLAB and rep["elided_bytes"] == 16 * SLAB
+        # slab 0 is no longer same-filled and has to go out; slabs 3, 8 and 9 still match the backing
+        # copies kept from the first cycle (clean-slab skip) and are not copied again
+        assert rep["bytes"] == 1 * SLAB and rep["elided_bytes"] == 16 * SLAB and rep["clean_bytes"] == 3 * SLAB
         e.fetch_all()
         want.view(np.uint8)[:16] = 9
         assert np.array_equal(view(p, 40 * MiB).view(np.uint32), want)
@@ -444,7 +448,7 @@ def test_best_effort_eviction_never_waits_for_backing_space(fake, tmp_path):
     from nvshare_b200 import engine as E
     pool = tmp_path / "pool"
     e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, batch_bytes=16 * MiB, shared_pool_path=str(pool),
-                 shared_pool_bytes=64 * MiB, oom_wait_ms=10000, elide_constant=0, prepin=0)
+                 shared_pool_bytes=64 * MiB, oom_wait_ms=10000, elide_constant=0, prepin=0, retain=0)
     try:
         p = e.alloc(96 * MiB); e.fetch_all()
         e.pattern_fill(p, 96 * MiB // 8, seed=21)

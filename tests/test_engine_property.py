@@ -37,6 +37,7 @@ ops = st.lists(
         st.tuples(st.just("alloc"), st.integers(1, 9), st.booleans()),          # size in slabs (+ ragged bytes), constant fill?
         st.tuples(st.just("write"), st.integers(0, 7), st.integers(0, 255)),    # which allocation, seed
         st.tuples(st.just("const"), st.integers(0, 7), st.integers(0, 255)),    # make one slab same-filled
+        st.tuples(st.just("poke"), st.integers(0, 7), st.integers(0, 10**7)),   # flip ONE byte (clean-slab detection)
         st.tuples(st.just("evict"), st.integers(0, 12), st.just(0)),            # 0 = all, else MiB
         st.tuples(st.just("fetch"), st.just(0), st.just(0)),
         st.tuples(st.just("free"), st.integers(0, 7), st.just(0)),
@@ -48,16 +49,16 @@ ops = st.lists(
 
 
 @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
-@given(script=ops, elide=st.booleans(), chunk_slabs=st.sampled_from([1, 2, 4]))
-def test_any_interleaving_preserves_contents(fake, script, elide, chunk_slabs):
-    _run_model(fake, script, elide, chunk_slabs)
+@given(script=ops, elide=st.booleans(), chunk_slabs=st.sampled_from([1, 2, 4]), retain=st.booleans())
+def test_any_interleaving_preserves_contents(fake, script, elide, chunk_slabs, retain):
+    _run_model(fake, script, elide, chunk_slabs, retain=int(retain))
 
 
 def _run_model(fake, script, elide, chunk_slabs, **engine_kw):
     from nvshare_b200 import engine as E
     base = fake.fake_cuda_phys_used()
     e = E.Engine(chunk_bytes=chunk_slabs * SLAB, host_arena_bytes=16 * MiB, batch_bytes=8 * MiB,
-                 oom_wait_ms=200 if not engine_kw else 5000, elide_constant=int(elide), prepin=0, **engine_kw)
+                 oom_wait_ms=200 if set(engine_kw) <= {"retain"} else 5000, elide_constant=int(elide), prepin=0, **engine_kw)
     model = {}          # ptr -> expected bytes
     order = []
     resident = True     # what the owner believes: we fetch before touching memory
@@ -75,6 +76,13 @@ def _run_model(fake, script, elide, chunk_slabs, **engine_kw):
                 view(p, size)[:] = data
                 model[p] = data
                 order.append(p)
+            elif op == "poke" and order:
+                p = order[a % len(order)]
+                if not resident:
+                    e.fetch_all(); resident = True
+                at = (b * 2654435761) % len(model[p])
+                model[p][at] ^= 1 + (b & 0x7f)
+                view(p, len(model[p]))[at] = model[p][at]
             elif op in ("write", "const") and order:
                 p = order[a % len(order)]
                 if not resident:
