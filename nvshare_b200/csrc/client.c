@@ -70,7 +70,7 @@ static int early_release = 1;
 static int sched_v2;          /* the daemon speaks the data-field hints (include/nvshare_wire.h)   */
 static int evict_all_policy;  /* NVSHARE_EVICT_POLICY=all: never keep slabs resident without lock */
 static pthread_mutex_t send_mu = PTHREAD_MUTEX_INITIALIZER; /* frames from several threads      */
-/* head-room left free beyond what the next client asked for: 1/128 of the HBM, 16 MiB..1 GiB */
+/* head-room left free beyond what the next client asked for: 1/512 of the HBM, 16 MiB..1 GiB */
 static uint64_t evict_margin_mib(void);
 static uint64_t client_id;
 static CUcontext app_ctx;
@@ -135,8 +135,12 @@ void nvs_client_pressure(uint64_t mib)
 
 static uint64_t evict_margin_mib(void)
 {
+	/* 1/512 of the HBM (357 MiB on a B200): covers the 64 MiB of slack the fetching side wants to
+	 * see free beyond what it maps (engine.c wait_for_hbm_burst) and the context growth of a client
+	 * that starts using a library between two hand-offs.  Every MiB of it crosses the link twice per
+	 * hand-off for nothing, hence no more than that (round 1 used 1/128: 1.5 GiB). */
 	uint64_t total = dp.total_hbm_mib ? dp.total_hbm_mib() : 0;
-	uint64_t m = total / 128;
+	uint64_t m = total / 512;
 	return m < 16 ? 16 : m > 1024 ? 1024 : m;
 }
 

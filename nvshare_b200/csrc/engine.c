@@ -673,6 +673,13 @@ static int arena_take(struct arena *a, uint32_t n, uint64_t *addr, int steal_cla
 		return -1;
 	uint32_t run = 0;
 	for (uint32_t i = (a->shared || steal_class) ? 0 : a->hint; i < a->n_slabs; ++i) {
+		/* 64 units in use at a stroke (the common case in a busy pool) */
+		if (steal_class == 0 && ((a->bit_base + i) & 63) == 0 && i + 64 <= a->n_slabs &&
+		    a->bitmap[(a->bit_base + i) >> 6] == ~0ull) {
+			run = 0;
+			i += 63;
+			continue;
+		}
 		if (!slab_available(a, i, steal_class)) {
 			run = 0;
 			continue;
@@ -1319,6 +1326,48 @@ static uint64_t shp_reap_dead(struct shpool *sp)
 	return reaped;
 }
 
+static uint64_t read_u64_file(const char *path, uint64_t dflt)
+{
+	FILE *f = fopen(path, "r");
+	if (!f)
+		return dflt;
+	char buf[64] = "";
+	uint64_t v = dflt;
+	if (fgets(buf, sizeof(buf), f) && buf[0] >= '0' && buf[0] <= '9')
+		v = strtoull(buf, NULL, 10);
+	fclose(f);
+	return v;
+}
+
+/* Host memory this process may still take: the memory cgroup's limit minus its usage (v2, then
+ * v1), capped by MemAvailable.  UINT64_MAX when nothing can be read. */
+static uint64_t host_memory_room(void)
+{
+	uint64_t room = UINT64_MAX;
+	uint64_t lim = read_u64_file("/sys/fs/cgroup/memory.max", UINT64_MAX);
+	uint64_t cur = read_u64_file("/sys/fs/cgroup/memory.current", 0);
+	if (lim == UINT64_MAX) {
+		lim = read_u64_file("/sys/fs/cgroup/memory/memory.limit_in_bytes", UINT64_MAX);
+		cur = read_u64_file("/sys/fs/cgroup/memory/memory.usage_in_bytes", 0);
+	}
+	if (lim != UINT64_MAX && lim < (1ull << 60))
+		room = lim > cur ? lim - cur : 0;
+	FILE *f = fopen("/proc/meminfo", "r");
+	if (f) {
+		char line[128];
+		while (fgets(line, sizeof(line), f)) {
+			unsigned long long kb;
+			if (sscanf(line, "MemAvailable: %llu kB", &kb) == 1) {
+				if (kb * 1024ull < room)
+					room = kb * 1024ull;
+				break;
+			}
+		}
+		fclose(f);
+	}
+	return room;
+}
+
 /* Open (or create) the pool file.  Returns 0, or -1 to fall back to a private pool. */
 static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
 {
@@ -1331,20 +1380,33 @@ static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
 	if (cap_slabs > SHP_MAX_SLABS)
 		cap_slabs = SHP_MAX_SLABS / window_slabs * window_slabs;
 	int creator = 1;
-	{
-		/* a tmpfs smaller than the pool (docker's default /dev/shm is 64 MiB) would turn
-		 * page faults into SIGBUS: only use the shared pool where it really fits */
+	if (access(path, F_OK) != 0) {
+		/* Whoever creates the pool fixes its capacity, and with kept copies the pool WILL fill up
+		 * to it.  A tmpfs smaller than the pool (docker's default /dev/shm is 64 MiB) would turn
+		 * page faults into SIGBUS, a memory cgroup smaller than it (pinned and tmpfs pages are
+		 * charged to it: profiles/r01_probe_h_pinned_accounting.txt) into an OOM kill: shrink the
+		 * budget to what the box can really give, and only fall back to private pools when that
+		 * is less than a quarter of what was asked for. */
 		char dir[256];
 		snprintf(dir, sizeof(dir), "%s", path);
 		char *slash = strrchr(dir, '/');
 		if (slash)
 			*slash = '\0';
+		uint64_t room = host_memory_room();
 		struct statvfs vfs;
-		if (access(path, F_OK) != 0 && statvfs(slash ? dir : ".", &vfs) == 0 &&
-		    (uint64_t)vfs.f_bavail * vfs.f_frsize < cap_slabs * SLAB + SHP_HDR_BYTES) {
-			errno = ENOSPC;
-			free(sp);
-			return -1;
+		if (statvfs(slash ? dir : ".", &vfs) == 0 && (uint64_t)vfs.f_bavail * vfs.f_frsize < room)
+			room = (uint64_t)vfs.f_bavail * vfs.f_frsize;
+		const uint64_t reserve = e->cfg.shared_pool_bytes ? SHP_HDR_BYTES : (20ull << 30) + SHP_HDR_BYTES;
+		const uint64_t fit = room > reserve ? (room - reserve) / SLAB / window_slabs * window_slabs : 0;
+		if (fit < cap_slabs) {
+			if (fit < cap_slabs / 4) {
+				errno = ENOSPC;
+				free(sp);
+				return -1;
+			}
+			nvs_debug("engine: shared pool capacity cut from %" PRIu64 " to %" PRIu64 " GiB (host memory / tmpfs budget)",
+				  (uint64_t)((cap_slabs * SLAB) >> 30), (uint64_t)((fit * SLAB) >> 30));
+			cap_slabs = fit;
 		}
 	}
 	sp->fd = open(path, O_RDWR | O_CREAT | O_EXCL | O_CLOEXEC | O_NOFOLLOW, 0600);
@@ -2259,7 +2321,7 @@ static void fetch_retire_completed(nvs_engine *e, nvs_xfer_report *rep)
 
 static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report *rep)
 {
-	/* head-room kept below the releasing client's own margin (1/128 of the HBM, client.c) */
+	/* head-room kept below the releasing client's own margin (1/512 of the HBM, client.c) */
 	const uint64_t slack = e->cfg.chunk_bytes < (64ull << 20) ? e->cfg.chunk_bytes : (64ull << 20);
 	uint64_t want = remaining < e->cfg.burst_bytes ? remaining : e->cfg.burst_bytes;
 	size_t free_b = 0, total_b = 0;

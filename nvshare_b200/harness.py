@@ -57,6 +57,10 @@ def load_iters(path):
 
 
 def steady_tau(ts):
+    """10th percentile of a client's own iteration durations.  Only a cross-check: when a client
+    never reaches resident speed inside its quantum (the reference at full scale keeps faulting)
+    this over-estimates the resident iteration time and hides lost time -- the analysis uses the
+    solo calibration (calibrate()) instead."""
     d = sorted(b - a for a, b in zip(ts, ts[1:]) if b > a)
     if not d:
         return float("nan")
@@ -79,33 +83,47 @@ def handoff_boundaries(timeline):
     return out
 
 
-def analyse(clients, warmup, steps):
+def analyse(clients, warmup, steps, tau=None):
     """clients: {name: [iteration completion times]}.  Returns the window metrics
-    over exactly `steps` hand-offs after `warmup` hand-offs, or raises."""
+    over exactly `steps` hand-offs after `warmup` hand-offs, or raises.
+
+    tau: resident iteration time of this workload from a solo, un-hooked, un-oversubscribed
+    calibration run (seconds).  Without it the clients' own 10th percentile is used and the
+    result is marked as such."""
     tl = merged_timeline(clients)
     bounds = handoff_boundaries(tl)
     if len(bounds) < warmup + steps + 1:
         raise RuntimeError(f"only {len(bounds)} hand-offs observed, need {warmup + steps + 1}")
     t_start = bounds[warmup][0]
     t_end = bounds[warmup + steps][0]
-    taus = {n: steady_tau(ts) for n, ts in clients.items()}
+    own = {n: steady_tau(ts) for n, ts in clients.items()}
+    taus = {n: (tau if tau else own[n]) for n in clients}
     n_iters = {n: sum(1 for t in ts if t_start < t <= t_end) for n, ts in clients.items()}
     busy = sum(n_iters[n] * taus[n] for n in clients)
     wall = t_end - t_start
-    lost = max(wall - busy, 0.0)
+    lost = wall - busy                       # NOT clamped: a negative value means the analysis does not apply
     # per-hand-off gap: last iteration of the leaving client -> first iteration of the arriving one
     gaps = []
     for k in range(warmup, warmup + steps):
         t_last, a, b = bounds[k]
         t_first = next(t for t, n in tl if t > t_last and n == b)
         gaps.append(t_first - t_last - taus[b])
-    return {
+    errors = []
+    if lost < 0:
+        errors.append(f"lost time {lost:.3f} s < 0: the clients completed more iterations than fit the window at tau")
+    if any(g < -0.5 * min(taus.values()) for g in gaps):
+        errors.append("negative first-iteration gap: iterations of two clients overlap, hand-offs are not clean")
+    out = {
         "window_s": wall, "t_start": t_start, "t_end": t_end, "handoffs": steps,
-        "iters": n_iters, "tau_s": taus, "iter_per_s": sum(n_iters.values()) / wall,
+        "iters": n_iters, "tau_s": taus, "tau_source": "solo un-hooked calibration" if tau else "own 10th percentile",
+        "tau_own_p10_s": own, "iter_per_s": sum(n_iters.values()) / wall,
         "iter_per_s_resident": {n: 1.0 / taus[n] for n in clients},
         "lost_s": lost, "stall_per_handoff_s": lost / steps, "first_iter_gap_s": gaps,
         "gpu_busy_frac": busy / wall,
     }
+    if errors:
+        out["analysis_error"] = errors
+    return out
 
 
 def engine_records(paths, t_start, t_end):
@@ -213,8 +231,60 @@ def count_handoffs(out_dir, n_clients):
     return len(handoff_boundaries(merged_timeline(clients)))
 
 
-def run_clients(impl, out_dir, n_clients, kind, n, pattern, seconds, tq, extra_env=None, start_stagger=0.0,
-                stop_after_handoffs=0):
+def client_cmd(spec, log, tag, barrier="", stop_file="", seconds=0.0, extra=()):
+    """Command line of one client.  spec: {"kind": add|matmul, "n":, "pattern":} or
+    {"kind": resnet|llama, "steps":, "batch":, ...}."""
+    if spec["kind"] in ("add", "matmul"):
+        cmd = [sys.executable, "-m", "nvshare_b200.workloads", "--kind", spec["kind"], "--n", str(spec["n"]),
+               "--iters", str(spec.get("iters", 100000000)), "--pattern", spec["pattern"]]
+    else:
+        cmd = [sys.executable, "-m", "nvshare_b200.workloads_models", "--kind", spec["kind"],
+               "--steps", str(spec.get("steps", 6)), "--batch", str(spec.get("batch", 16)), "--tf32", str(spec.get("tf32", 0))]
+        if spec["kind"] == "llama":
+            cmd += ["--size", spec.get("size", "small"), "--context", str(spec.get("context", 32))]
+        if spec.get("target_bytes"):
+            cmd += ["--target-bytes", str(int(spec["target_bytes"]))]
+        if spec.get("golden"):
+            cmd += ["--golden", str(spec["golden"])]
+    cmd += ["--seconds", str(seconds), "--log", str(log), "--tag", tag]
+    if barrier:
+        cmd += ["--start-barrier", str(barrier)]
+    if stop_file:
+        cmd += ["--stop-file", str(stop_file)]
+    return cmd + list(extra)
+
+
+def calibrate(spec, out_dir, env=None, timeout=1800):
+    """Solo, un-hooked, un-oversubscribed run of the same application: its resident iteration
+    time tau (median, first iterations dropped) and -- for the model workloads -- the golden
+    numbers every hooked round is compared with.  No LD_PRELOAD, no scheduler."""
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    log = out_dir / "calibration.jsonl"
+    env = dict(env or os.environ, PYTHONPATH=str(ROOT) + (":" + os.environ["PYTHONPATH"] if os.environ.get("PYTHONPATH") else ""))
+    env.pop("LD_PRELOAD", None)
+    if spec["kind"] in ("add", "matmul"):
+        cal = dict(spec, pattern="ones", iters=spec.get("calibration_iters", 6 if spec["kind"] == "matmul" else 40))
+        cmd = client_cmd(cal, log, "calibration", extra=["--no-verify"])
+        golden = None
+    else:
+        golden = out_dir / "golden.json"
+        cal = dict(spec, golden=None, target_bytes=0)
+        cmd = client_cmd(cal, log, "calibration", extra=["--rounds", "3", "--write-golden", str(golden)])
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"calibration run failed: {r.stderr[-2000:]}")
+    ts, meta = load_iters(log)
+    skip = 4 if spec["kind"] == "add" else (1 if spec["kind"] == "matmul" else int(spec.get("steps", 6)))
+    d = sorted(b - a for a, b in zip(ts[skip:], ts[skip + 1:]) if b > a)
+    if not d:
+        raise RuntimeError("calibration run produced no iterations")
+    return {"tau_s": d[len(d) // 2], "tau_min_s": d[0], "iters": len(ts), "golden": str(golden) if golden else None,
+            "setup_s": meta.get("setup_done", {}).get("setup_s"), "torch_reserved": meta.get("setup_done", {}).get("torch_reserved")}
+
+
+def run_clients(impl, out_dir, n_clients, spec, seconds, tq, extra_env=None, start_stagger=0.0,
+                stop_after_handoffs=0, gpu=None):
     """Run the co-located clients until `stop_after_handoffs` hand-offs have been
     observed (or `seconds` elapsed); each client then verifies its results.
     Returns per-client dicts."""
@@ -232,16 +302,18 @@ def run_clients(impl, out_dir, n_clients, kind, n, pattern, seconds, tq, extra_e
     procs = []
     try:
         for i in range(n_clients):
-            # keep whatever is already preloaded (e.g. a profiler's injection library) behind ours
+            # keep whatever is already preloaded (e.g. a profiler's injection library) behind ours, and
+            # whatever is on PYTHONPATH (the driver's sitecustomize hook records which .so files we load)
             preload = str(paths["lib"]) + (":" + os.environ["LD_PRELOAD"] if os.environ.get("LD_PRELOAD") else "")
-            env = dict(os.environ, LD_PRELOAD=preload, PYTHONPATH=str(ROOT))
+            pypath = str(ROOT) + (":" + os.environ["PYTHONPATH"] if os.environ.get("PYTHONPATH") else "")
+            env = dict(os.environ, LD_PRELOAD=preload, PYTHONPATH=pypath)
+            if gpu is not None:
+                env["CUDA_VISIBLE_DEVICES"] = str(gpu)
             if impl == "ours":
                 env["NVSHARE_SOCK_DIR"] = str(sock_dir)
                 env["NVSHARE_STATS_FILE"] = str(out_dir / f"engine{i}.jsonl")
             env.update({k: str(v) for k, v in (extra_env or {}).items()})
-            cmd = [sys.executable, "-m", "nvshare_b200.workloads", "--kind", kind, "--n", str(n), "--iters", "100000000",
-                   "--seconds", str(seconds), "--pattern", pattern, "--log", str(out_dir / f"client{i}.jsonl"),
-                   "--tag", f"client{i}", "--start-barrier", str(barrier), "--stop-file", str(stop_file)]
+            cmd = client_cmd(spec, out_dir / f"client{i}.jsonl", f"client{i}", barrier, stop_file, seconds)
             procs.append(subprocess.Popen(cmd, env=env, cwd=ROOT, stdout=open(out_dir / f"client{i}.out", "w"),
                                           stderr=open(out_dir / f"client{i}.err", "w")))
             time.sleep(start_stagger)
@@ -262,6 +334,8 @@ def run_clients(impl, out_dir, n_clients, kind, n, pattern, seconds, tq, extra_e
             time.sleep(1.0)
             if stop_after_handoffs and not stop_file.exists() and count_handoffs(out_dir, n_clients) >= stop_after_handoffs:
                 stop_file.write_text("stop")
+        if not stop_file.exists():
+            stop_file.write_text("stop")
         for p in procs:
             p.wait(timeout=1800)
     finally:

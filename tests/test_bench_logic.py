@@ -28,10 +28,8 @@ def load_bench(shm_bytes=1 << 40):
     return m
 
 
-def args(**kw):
-    d = dict(hbm_fraction=0.0, impl="ours", oversub=1.5, clients=2)
-    d.update(kw)
-    return types.SimpleNamespace(**d)
+def pick(b, impl="ours", forced=0.0, world=1):
+    return b.pick_fraction(impl, 2, 1.5, HBM, forced, world)
 
 
 HBM = 191_503_007_744          # what cuMemGetInfo reports on the r01 B200
@@ -40,19 +38,21 @@ HBM = 191_503_007_744          # what cuMemGetInfo reports on the r01 B200
 def test_full_scale_fits_for_ours_but_not_for_the_reference(monkeypatch):
     b = load_bench()
     monkeypatch.setattr(b, "host_memory_budget", lambda: 213_000_000_000)     # the r01 box: 200 GiB cgroup
-    assert b.pick_fraction(args(impl="ours"), HBM) == (1.0, None)
-    frac, note = b.pick_fraction(args(impl="reference"), HBM)
+    assert pick(b, "ours") == (1.0, None)
+    frac, note = pick(b, "reference")
     assert 0.5 <= frac <= 0.65 and "host RAM budget" in note
     # an explicit fraction is never overridden
-    assert b.pick_fraction(args(impl="reference", hbm_fraction=0.25), HBM) == (0.25, None)
+    assert pick(b, "reference", forced=0.25) == (0.25, None)
+    # the peer tier keeps next to nothing on the host
+    assert pick(b, "ours", world=2) == (1.0, None)
 
 
 def test_no_limit_means_full_scale(monkeypatch):
     b = load_bench()
     monkeypatch.setattr(b, "host_memory_budget", lambda: None)
-    assert b.pick_fraction(args(impl="reference"), HBM) == (1.0, None)
+    assert pick(b, "reference") == (1.0, None)
     monkeypatch.setattr(b, "host_memory_budget", lambda: 2_000_000_000_000)
-    assert b.pick_fraction(args(impl="reference"), HBM) == (1.0, None)
+    assert pick(b, "reference") == (1.0, None)
 
 
 def test_host_memory_model():
@@ -61,7 +61,7 @@ def test_host_memory_model():
     # the reference keeps every client's pages on the host; ours only what is swapped out (+ pinned windows ahead)
     assert b.host_memory_needed("reference", 2, f, HBM) > 2 * f
     assert b.host_memory_needed("ours", 2, f, HBM) < 1.0 * HBM
-    assert b.host_memory_needed("ours", 2, 0.4 * HBM, HBM) < 20e9          # fits: nothing to swap
+    assert b.host_memory_needed("ours", 2, 0.4 * HBM, HBM) < 40e9          # fits: nothing to swap
 
 
 def test_small_dev_shm_means_private_pools(monkeypatch):
@@ -70,7 +70,7 @@ def test_small_dev_shm_means_private_pools(monkeypatch):
     f = 0.75 * HBM
     assert b.host_memory_needed("ours", 2, f, HBM) > 2 * (2 * f - HBM)
     monkeypatch.setattr(b, "host_memory_budget", lambda: 213_000_000_000)
-    frac, note = b.pick_fraction(args(impl="ours"), HBM)
+    frac, note = pick(b, "ours")
     assert frac < 1.0 and note
 
 
@@ -79,3 +79,22 @@ def test_baseline_geometry():
     n = int(math.floor(math.sqrt(1.5 * HBM / 2 / 16)))
     assert n == 94745
     assert abs(4 * 4 * n * n - 0.75 * HBM) / (0.75 * HBM) < 1e-4
+
+
+def test_client_specs_reach_the_footprint():
+    b = load_bench()
+    spec, fp = b.make_spec("add", "pos", 0.75 * HBM)
+    assert spec["n"] == 94745 and fp <= 0.75 * HBM
+    spec, fp = b.make_spec("matmul", "pos", 0.75 * HBM)          # three blocks like the reference's TF graph
+    assert spec["n"] == int(math.floor(math.sqrt(0.75 * HBM / 12))) and abs(fp - 0.75 * HBM) / HBM < 1e-4
+    spec, fp = b.make_spec("llama", "pos", 0.75 * HBM)
+    kv = spec["batch"] * spec["context"] * (1 << 20)               # 7B geometry, fp32: 1 MiB of KV per token
+    assert spec["size"] == "7b" and 27e9 + kv < fp and fp - (27e9 + kv) < 16e9
+    spec, fp = b.make_spec("resnet", "pos", 0.95 * HBM)
+    assert spec["target_bytes"] == int(0.95 * HBM)
+
+
+def test_algorithmic_bytes_are_independent_of_the_number_of_clients():
+    # what must come in per hand-off: the arriving client's footprint minus the HBM the holder leaves free
+    f = 0.75 * HBM
+    assert abs(max(min(f, 2 * f - HBM), 0) - 0.5 * HBM) < 1

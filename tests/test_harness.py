@@ -50,6 +50,40 @@ def test_slow_post_resume_iterations_count_as_stall():
     assert abs(a["stall_per_handoff_s"] - 0.7) < 0.03
 
 
+def test_thrashing_arm_needs_the_solo_calibration():
+    """VERDICT weak #2: a client that never reaches resident speed inside its quantum (the reference at
+    full scale: every iteration 2.5 s instead of 15 ms) makes its own 10th percentile useless as tau --
+    "lost time" all but vanishes.  With tau from the solo calibration the whole quantum counts as lost."""
+    t, clients, who = 0.0, {"client0": [], "client1": []}, 0
+    for _ in range(9):
+        for _ in range(4):                       # 4 slow iterations of 2.5 s per 10 s quantum
+            t += 2.5
+            clients[f"client{who}"].append(t)
+        who ^= 1
+    own = harness.analyse(clients, warmup=2, steps=4)
+    assert own["tau_source"] == "own 10th percentile" and own["stall_per_handoff_s"] < 0.1
+    cal = harness.analyse(clients, warmup=2, steps=4, tau=0.015)
+    assert cal["tau_source"] == "solo un-hooked calibration"
+    assert abs(cal["stall_per_handoff_s"] - (10.0 - 4 * 0.015)) < 0.01
+    assert "analysis_error" not in cal
+
+
+def test_overlapping_iterations_are_flagged_not_hidden():
+    c = synth(tau=0.02, quantum=1.0, stall=0.5, handoffs=10)
+    a = harness.analyse(c, warmup=3, steps=4, tau=1.2)       # a tau that cannot be right for this timeline
+    assert a["lost_s"] < 0 and any("lost time" in e for e in a["analysis_error"])
+    assert any("negative first-iteration gap" in e for e in a["analysis_error"])
+
+
+def test_client_command_lines():
+    add = harness.client_cmd({"kind": "add", "n": 1000, "pattern": "pos"}, "/tmp/l", "c0", "/tmp/go", "/tmp/stop", 30)
+    assert add[1:3] == ["-m", "nvshare_b200.workloads"] and "--start-barrier" in add and "--stop-file" in add
+    ll = harness.client_cmd({"kind": "llama", "size": "7b", "steps": 8, "batch": 24, "context": 4096, "tf32": 1,
+                             "golden": "/tmp/g.json", "target_bytes": 0}, "/tmp/l", "c1")
+    assert ll[1:3] == ["-m", "nvshare_b200.workloads_models"] and ll[ll.index("--size") + 1] == "7b"
+    assert ll[ll.index("--golden") + 1] == "/tmp/g.json" and "--target-bytes" not in ll
+
+
 def test_not_enough_handoffs_is_an_error():
     c = synth(handoffs=3)
     with pytest.raises(RuntimeError):

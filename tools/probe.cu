@@ -1200,6 +1200,168 @@ static int section_k(void)
 	return 0;
 }
 
+/* --------------------------------------------------------------- L ------ */
+/* Handing PHYSICAL chunks over instead of release -> poll -> create: A owns ~all
+ * of the HBM in 256 MiB chunks created with a POSIX-fd shareable handle type; for each chunk it
+ * exports the handle, sends the fd over a Unix socket (SCM_RIGHTS), unmaps and releases; B imports,
+ * maps and sets access.  No cuMemCreate / cuMemGetInfo polling on B's side, the memory never
+ * becomes "free" in between.  Also: does asking for a shareable handle type make cuMemCreate slower? */
+#include <sys/socket.h>
+#include <sys/wait.h>
+static int send_fd(int sock, int fd)
+{
+	char byte = 'F', ctrl[CMSG_SPACE(sizeof(int))];
+	struct iovec io = {&byte, 1};
+	struct msghdr m;
+	memset(&m, 0, sizeof m);
+	memset(ctrl, 0, sizeof ctrl);
+	m.msg_iov = &io;
+	m.msg_iovlen = 1;
+	m.msg_control = ctrl;
+	m.msg_controllen = sizeof ctrl;
+	struct cmsghdr *c = CMSG_FIRSTHDR(&m);
+	c->cmsg_level = SOL_SOCKET;
+	c->cmsg_type = SCM_RIGHTS;
+	c->cmsg_len = CMSG_LEN(sizeof(int));
+	memcpy(CMSG_DATA(c), &fd, sizeof(int));
+	return sendmsg(sock, &m, 0) == 1 ? 0 : -1;
+}
+
+static int recv_fd(int sock)
+{
+	char byte, ctrl[CMSG_SPACE(sizeof(int))];
+	struct iovec io = {&byte, 1};
+	struct msghdr m;
+	memset(&m, 0, sizeof m);
+	m.msg_iov = &io;
+	m.msg_iovlen = 1;
+	m.msg_control = ctrl;
+	m.msg_controllen = sizeof ctrl;
+	if (recvmsg(sock, &m, 0) != 1)
+		return -1;
+	struct cmsghdr *c = CMSG_FIRSTHDR(&m);
+	int fd = -1;
+	if (c && c->cmsg_type == SCM_RIGHTS)
+		memcpy(&fd, CMSG_DATA(c), sizeof(int));
+	return fd;
+}
+
+static int section_l(void)
+{
+	const size_t chunk = 256 * MiB, n_give = 200;
+	int sv[2];
+	if (socketpair(AF_UNIX, SOCK_STREAM, 0, sv) != 0)
+		return -1;
+	SharedK *sh = (SharedK *)mmap(NULL, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+	memset((void *)sh, 0, sizeof *sh);
+	pid_t b = fork();
+	if (b == 0) { /* process B: imports what A hands over */
+		close(sv[0]);
+		if (cuInit(0) != CUDA_SUCCESS || cudaSetDevice(0) != cudaSuccess || cudaFree(0) != cudaSuccess)
+			_exit(1);
+		CUmemAccessDesc acc;
+		memset(&acc, 0, sizeof acc);
+		acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+		acc.location.id = 0;
+		acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+		CUdeviceptr va;
+		if (cuMemAddressReserve(&va, n_give * chunk, 0, 0, 0) != CUDA_SUCCESS)
+			_exit(2);
+		std::vector<CUmemGenericAllocationHandle> h(n_give);
+		__sync_fetch_and_add(&sh->ready, 1);
+		double t_imp = 0, t_map = 0, t_acc = 0, t_recv = 0;
+		size_t got = 0;
+		unsigned long long first_word = 0;
+		for (; got < n_give; ++got) {
+			double t0 = now_s();
+			int fd = recv_fd(sv[1]);
+			if (fd < 0)
+				break;
+			double t1 = now_s();
+			if (cuMemImportFromShareableHandle(&h[got], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS)
+				break;
+			double t2 = now_s();
+			cuMemMap(va + got * chunk, chunk, 0, h[got], 0);
+			double t3 = now_s();
+			cuMemSetAccess(va + got * chunk, chunk, &acc, 1);
+			double t4 = now_s();
+			close(fd);
+			t_recv += t1 - t0;
+			t_imp += t2 - t1;
+			t_map += t3 - t2;
+			t_acc += t4 - t3;
+			if (got == 0)
+				cudaMemcpy(&first_word, (void *)va, 8, cudaMemcpyDeviceToHost);
+		}
+		printf("PROBE {\"section\":\"L\",\"side\":\"B\",\"chunks\":%zu,\"recv_wait_ms_per_chunk\":%.3f,\"import_ms_per_chunk\":%.3f,"
+		       "\"map_ms_per_chunk\":%.3f,\"setaccess_ms_per_chunk\":%.3f,\"first_word\":\"%llx\"}\n", got,
+		       t_recv * 1e3 / n_give, t_imp * 1e3 / n_give, t_map * 1e3 / n_give, t_acc * 1e3 / n_give, first_word);
+		fflush(stdout);
+		_exit(got == n_give ? 0 : 3);
+	}
+	pid_t a = fork();
+	if (a == 0) { /* process A: owns the HBM, hands n_give chunks over */
+		close(sv[1]);
+		if (cuInit(0) != CUDA_SUCCESS || cudaSetDevice(0) != cudaSuccess || cudaFree(0) != cudaSuccess)
+			_exit(1);
+		JState j;
+		size_t f = 0, t = 0;
+		cuMemGetInfo(&f, &t);
+		j.chunk = chunk;
+		j.n = (f - 1 * GiB) / chunk;
+		j.h.resize(j.n);
+		memset(&j.prop, 0, sizeof j.prop);
+		j.prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+		j.prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+		j.prop.location.id = 0;
+		j.prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+		memset(&j.acc, 0, sizeof j.acc);
+		j.acc.location = j.prop.location;
+		j.acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+		double t0 = now_s();
+		if (cuMemAddressReserve(&j.va, j.n * j.chunk, 0, 0, 0) != CUDA_SUCCESS || j_map_all(j))
+			_exit(2);
+		double t_fill = now_s() - t0;
+		unsigned long long magic = 0xfeedfacecafe1234ull;
+		cudaMemcpy((void *)j.va, &magic, 8, cudaMemcpyHostToDevice);
+		while (sh->ready < 1)
+			usleep(100);
+		double t_exp = 0, t_send = 0, t_unmap = 0, t_rel = 0, t0all = now_s();
+		for (size_t i = 0; i < n_give; ++i) {
+			int fd = -1;
+			double a0 = now_s();
+			if (cuMemExportToShareableHandle(&fd, j.h[i], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS)
+				_exit(4);
+			double a1 = now_s();
+			send_fd(sv[0], fd);
+			double a2 = now_s();
+			cuMemUnmap(j.va + i * j.chunk, j.chunk);
+			double a3 = now_s();
+			cuMemRelease(j.h[i]);
+			close(fd);
+			double a4 = now_s();
+			t_exp += a1 - a0;
+			t_send += a2 - a1;
+			t_unmap += a3 - a2;
+			t_rel += a4 - a3;
+		}
+		double wall = now_s() - t0all;
+		printf("PROBE {\"section\":\"L\",\"side\":\"A\",\"hbm_chunks_held\":%zu,\"create_map_ms_per_chunk_shareable\":%.3f,\"given\":%zu,"
+		       "\"export_ms_per_chunk\":%.3f,\"send_ms_per_chunk\":%.3f,\"unmap_ms_per_chunk\":%.3f,\"release_ms_per_chunk\":%.3f,"
+		       "\"wall_s\":%.3f,\"GBps\":%.1f}\n", j.n, t_fill * 1e3 / j.n, n_give, t_exp * 1e3 / n_give, t_send * 1e3 / n_give,
+		       t_unmap * 1e3 / n_give, t_rel * 1e3 / n_give, wall, n_give * chunk / 1e9 / wall);
+		fflush(stdout);
+		usleep(500000);
+		_exit(0);
+	}
+	close(sv[0]);
+	close(sv[1]);
+	int st;
+	waitpid(a, &st, 0);
+	waitpid(b, &st, 0);
+	return 0;
+}
+
 /* --------------------------------------------------------------- I ------ */
 /* The shared host pool: a /dev/shm file, pages faulted in by 8 threads (reads),
  * pinned with cuMemHostRegister.  How fast is provisioning, and is the link
@@ -1312,6 +1474,8 @@ int main(int argc, char **argv)
 		return section_j_two_process();
 	if (argc > 1 && !strcmp(argv[1], "K"))
 		return section_k();
+	if (argc > 1 && !strcmp(argv[1], "L"))
+		return section_l();
 	if (argc > 2)
 		g_scale_gib = strtoull(argv[2], NULL, 0);
 	if (cuInit(0) != CUDA_SUCCESS) {
