@@ -37,6 +37,13 @@
  *     entry has a legacy and a per-thread forwarder) and answers
  *     "cuGetProcAddress" with the v2 hook when asked by a >= 12.0 runtime.
  *   - the allocation table is thread-safe (the reference's list is not).
+ *   - the other ways of obtaining device memory are interposed too: cuMemAllocAsync,
+ *     cuMemAllocFromPoolAsync, cuMemFreeAsync (stream-ordered) and cuMemAllocPitch.  The
+ *     reference lets them through (src/hook.c:545-577 does not list them): memory obtained
+ *     there is neither charged to the per-process cap nor swappable.  Here they take the
+ *     same path as cuMemAlloc: cap check, then the swap engine (an allocation that is
+ *     available at once is a valid stream-ordered allocation; a stream-ordered free first
+ *     waits for the stream).
  *   - cuMemcpyHtoD/DtoH{,Async} on memory that is not on the GPU (swapped out or
  *     never materialised) do not wait for the lock: they are served from / into
  *     the pinned-host backing copy (host_io_bypass -> nvs_host_io, SURVEY 8f
@@ -90,6 +97,8 @@ static CUresult (*real_cuCtxSetCurrent)(CUcontext);
 static CUresult (*real_cuCtxGetCurrent)(CUcontext *);
 static CUresult (*real_cuCtxSynchronize)(void);
 static CUresult (*real_cuStreamIsCapturing)(CUstream, int *); /* optional */
+static CUresult (*real_cuStreamSynchronize[2])(CUstream);      /* optional; [legacy, per-thread default stream] */
+static CUresult (*real_cuMemFreeAsync[2])(CUdeviceptr, CUstream);
 
 static pthread_mutex_t acct_mu = PTHREAD_MUTEX_INITIALIZER;
 static size_t cap_bytes;     /* what cuMemGetInfo reports as free: the per-process cap */
@@ -166,7 +175,7 @@ enum gate_id {
 };
 static void *gate_real[G_COUNT][2];
 
-static void after_launch(void);
+static void after_launch(CUstream s);
 
 static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_device, CUstream s);
 static int touch_dst(CUdeviceptr dev, size_t n);
@@ -176,6 +185,8 @@ static int touch_dst(CUdeviceptr dev, size_t n);
  * the GPU (nvs_host_io) and must therefore neither wait for the lock nor reach
  * the driver. */
 #define GATED(name, is_launch, params, args) GATED_(name, is_launch, params, args, NO_BYPASS)
+/* is_launch: 0, or LAUNCH_ON(stream expression) for entry points that submit kernels */
+#define LAUNCH_ON(stream_expr) (1 + 0 * (uintptr_t)(launch_stream = (CUstream)(stream_expr)))
 #define GATED_(name, is_launch, params, args, bypass)                                \
 	static CUresult gate_##name##_impl(int flavour_, NVS_UNPAREN params)                \
 	{                                                                            \
@@ -190,8 +201,9 @@ static int touch_dst(CUdeviceptr dev, size_t n);
 		continue_with_lock();                                                \
 		CUresult r = real args;                                              \
 		warn_if_error(r, #name);                                             \
+		CUstream launch_stream = NULL;                                       \
 		if (is_launch)                                                       \
-			after_launch();                                              \
+			after_launch(launch_stream);                                 \
 		nvs_gate_leave();                                                    \
 		return r;                                                            \
 	}                                                                            \
@@ -203,15 +215,21 @@ static int touch_dst(CUdeviceptr dev, size_t n);
 #define NVS_PREPEND_(x, ...) (x, __VA_ARGS__)
 
 typedef unsigned int u32;
+/* the leading fields of CUlaunchConfig (cuda.h): all this library needs is the stream */
+struct nvs_launch_config_head {
+	u32 grid[3], block[3], smem;
+	CUstream stream;
+};
 
-GATED(cuLaunchKernel, 1,
+GATED(cuLaunchKernel, LAUNCH_ON(s),
       (CUfunction f, u32 gx, u32 gy, u32 gz, u32 bx, u32 by, u32 bz, u32 smem, CUstream s, void **kp, void **extra),
       (f, gx, gy, gz, bx, by, bz, smem, s, kp, extra))
-GATED(cuLaunchKernelEx, 1, (const void *config, CUfunction f, void **kp, void **extra), (config, f, kp, extra))
-GATED(cuLaunchCooperativeKernel, 1,
+GATED(cuLaunchKernelEx, LAUNCH_ON(config ? ((const struct nvs_launch_config_head *)config)->stream : NULL),
+      (const void *config, CUfunction f, void **kp, void **extra), (config, f, kp, extra))
+GATED(cuLaunchCooperativeKernel, LAUNCH_ON(s),
       (CUfunction f, u32 gx, u32 gy, u32 gz, u32 bx, u32 by, u32 bz, u32 smem, CUstream s, void **kp),
       (f, gx, gy, gz, bx, by, bz, smem, s, kp))
-GATED(cuGraphLaunch, 1, (CUgraphExec g, CUstream s), (g, s))
+GATED(cuGraphLaunch, LAUNCH_ON(s), (CUgraphExec g, CUstream s), (g, s))
 GATED(cuMemcpy, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n), (dst, src, n))
 GATED(cuMemcpyAsync, 0, (CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream s), (dst, src, n, s))
 /* host<->device copies whose device side is swapped out are host<->host copies: no GPU, no lock */
@@ -258,6 +276,11 @@ EXPORT CUresult cuGetProcAddress_v2(const char *symbol, void **pfn, int cudaVers
 EXPORT CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize);
 EXPORT CUresult cuMemFree_v2(CUdeviceptr dptr);
 EXPORT CUresult cuMemGetInfo_v2(size_t *free_b, size_t *total_b);
+EXPORT CUresult cuMemAllocPitch_v2(CUdeviceptr *dptr, size_t *pitch, size_t width_bytes, size_t height, unsigned elem);
+EXPORT CUresult cuMemAllocAsync(CUdeviceptr *dptr, size_t bytesize, CUstream s);
+EXPORT CUresult cuMemAllocFromPoolAsync(CUdeviceptr *dptr, size_t bytesize, void *pool, CUstream s);
+EXPORT CUresult cuMemFreeAsync(CUdeviceptr dptr, CUstream s);
+static CUresult hook_cuMemFreeAsync_ptsz(CUdeviceptr dptr, CUstream s);
 
 struct entry {
 	const char *base; /* name cuGetProcAddress is asked for          */
@@ -270,6 +293,7 @@ struct entry {
 
 #define E_GATE(name, elfname, ref, sfx) {#name, elfname, {(void *)gate_##name##_0, (void *)gate_##name##_1}, G_##name, ref, sfx}
 #define E_PLAIN(name, elfname, fn) {#name, elfname, {(void *)fn, (void *)fn}, -1, 1, NULL}
+#define E_PLAIN2(name, elfname, fn0, fn1) {#name, elfname, {(void *)fn0, (void *)fn1}, -1, 0, NULL}
 
 static const struct entry ENTRIES[] = {
 	E_PLAIN(cuInit, "cuInit", cuInit),
@@ -288,6 +312,10 @@ static const struct entry ENTRIES[] = {
 	E_GATE(cuMemcpyDtoD, "cuMemcpyDtoD_v2", 1, "_ptds"),
 	E_GATE(cuMemcpyDtoDAsync, "cuMemcpyDtoDAsync_v2", 1, "_ptsz"),
 	/* beyond the reference's set */
+	E_PLAIN2(cuMemAllocPitch, "cuMemAllocPitch_v2", cuMemAllocPitch_v2, cuMemAllocPitch_v2),
+	E_PLAIN2(cuMemAllocAsync, "cuMemAllocAsync", cuMemAllocAsync, cuMemAllocAsync),
+	E_PLAIN2(cuMemAllocFromPoolAsync, "cuMemAllocFromPoolAsync", cuMemAllocFromPoolAsync, cuMemAllocFromPoolAsync),
+	E_PLAIN2(cuMemFreeAsync, "cuMemFreeAsync", cuMemFreeAsync, hook_cuMemFreeAsync_ptsz),
 	E_GATE(cuLaunchKernelEx, "cuLaunchKernelEx", 0, "_ptsz"),
 	E_GATE(cuLaunchCooperativeKernel, "cuLaunchCooperativeKernel", 0, "_ptsz"),
 	E_GATE(cuGraphLaunch, "cuGraphLaunch", 0, "_ptsz"),
@@ -402,6 +430,10 @@ static void bootstrap(void)
 	real_cuCtxSynchronize = must_sym("cuCtxSynchronize");
 	/* optional: runtimes < 11.3 / < 12.0 never ask for them */
 	real_cuStreamIsCapturing = real_dlsym(cuda_lib, "cuStreamIsCapturing");
+	real_cuStreamSynchronize[0] = real_dlsym(cuda_lib, "cuStreamSynchronize");
+	real_cuStreamSynchronize[1] = real_dlsym(cuda_lib, "cuStreamSynchronize_ptsz");
+	real_cuMemFreeAsync[0] = real_dlsym(cuda_lib, "cuMemFreeAsync");
+	real_cuMemFreeAsync[1] = real_dlsym(cuda_lib, "cuMemFreeAsync_ptsz");
 	real_cuGetProcAddress = real_dlsym(cuda_lib, "cuGetProcAddress");
 	real_cuGetProcAddress_v2 = real_dlsym(cuda_lib, "cuGetProcAddress_v2");
 
@@ -620,8 +652,17 @@ static int host_io_bypass(CUdeviceptr dev, const void *host, size_t n, int to_de
 
 /* Reference src/hook.c:782-838: keep the amount of queued GPU work bounded so a
  * DROP_LOCK can be honoured quickly. */
-static void after_launch(void)
+static void after_launch(CUstream s)
 {
+	/* A launch into a capturing stream records a graph node, it queues no work -- and a
+	 * cuCtxSynchronize here would be an illegal call that invalidates the capture
+	 * (torch.cuda.graphs, cuBLAS graph capture).  The reference synchronises regardless
+	 * (src/hook.c:808): stream capture under it fails. */
+	if (s && real_cuStreamIsCapturing) {
+		int capturing = 0;
+		if (real_cuStreamIsCapturing(s, &capturing) == CUDA_SUCCESS && capturing != 0)
+			return;
+	}
 	pthread_mutex_lock(&window_mu);
 	if (++launches_since_sync >= sync_window) {
 		struct timespec a, b;
@@ -782,6 +823,68 @@ CUresult cuMemFree_v2(CUdeviceptr dptr)
 	}
 	return r;
 }
+
+/* ---- the other allocation entry points (not in the reference's set) ---- */
+
+CUresult cuMemAllocPitch_v2(CUdeviceptr *dptr, size_t *pitch, size_t width_bytes, size_t height, unsigned elem)
+{
+	if (!real_cuMemAllocManaged)
+		return CUDA_ERROR_NOT_INITIALIZED;
+	if (!dptr || !pitch || width_bytes == 0 || height == 0 || !(elem == 4 || elem == 8 || elem == 16))
+		return CUDA_ERROR_INVALID_VALUE;
+	/* what the driver does on every GPU that has VMM: rows padded to 512 bytes */
+	const size_t p = (width_bytes + 511) & ~(size_t)511;
+	CUresult r = cuMemAlloc_v2(dptr, p * height);
+	if (r == CUDA_SUCCESS)
+		*pitch = p;
+	return r;
+}
+
+/* Stream-ordered allocation: "available when the stream gets there".  Memory that is available
+ * at once satisfies that, so these are cuMemAlloc with the cap check and the swap engine behind
+ * it; the memory pool argument only says where the driver would have taken the memory from. */
+CUresult cuMemAllocAsync(CUdeviceptr *dptr, size_t bytesize, CUstream s)
+{
+	(void)s;
+	return cuMemAlloc_v2(dptr, bytesize);
+}
+
+CUresult cuMemAllocFromPoolAsync(CUdeviceptr *dptr, size_t bytesize, void *pool, CUstream s)
+{
+	(void)pool;
+	(void)s;
+	return cuMemAlloc_v2(dptr, bytesize);
+}
+
+/* Stream-ordered free: everything queued on the stream before the call may still use the memory.
+ * Ours is released on the host side, so the stream is drained first (the driver's own free of
+ * memory we did not hand out keeps its asynchronous semantics). */
+static CUresult free_async(int flavour, CUdeviceptr dptr, CUstream s)
+{
+	if (!real_cuMemFree)
+		return CUDA_ERROR_NOT_INITIALIZED;
+	nvs_engine *e = __atomic_load_n(&engine, __ATOMIC_ACQUIRE);
+	int ours = 0;
+	pthread_mutex_lock(&acct_mu);
+	for (struct uvm_alloc *a = uvm_buckets[(unsigned)((dptr >> 9) * 2654435761u) >> 24]; a && !ours; a = a->next)
+		ours = a->ptr == dptr;
+	pthread_mutex_unlock(&acct_mu);
+	if (!ours && e && nvs_touch(e, (uint64_t)dptr, 1) != NVS_E_NOT_OURS)
+		ours = 1;
+	if (!ours) {
+		if (real_cuMemFreeAsync[flavour] || real_cuMemFreeAsync[0])
+			return (real_cuMemFreeAsync[flavour] ? real_cuMemFreeAsync[flavour] : real_cuMemFreeAsync[0])(dptr, s);
+		return CUDA_ERROR_INVALID_VALUE;
+	}
+	CUresult (*sync)(CUstream) = real_cuStreamSynchronize[flavour] ? real_cuStreamSynchronize[flavour] : real_cuStreamSynchronize[0];
+	CUresult r = sync ? sync(s) : real_cuCtxSynchronize();
+	if (r != CUDA_SUCCESS)
+		return r;
+	return cuMemFree_v2(dptr);
+}
+
+CUresult cuMemFreeAsync(CUdeviceptr dptr, CUstream s) { return free_async(0, dptr, s); }
+static CUresult hook_cuMemFreeAsync_ptsz(CUdeviceptr dptr, CUstream s) { return free_async(1, dptr, s); }
 
 /* reference-exported names of the gated set: the legacy-stream forwarders */
 EXPORT CUresult cuLaunchKernel(CUfunction f, u32 gx, u32 gy, u32 gz, u32 bx, u32 by, u32 bz, u32 smem, CUstream s,

@@ -279,6 +279,36 @@ CUresult cuMemFree_v2(CUdeviceptr dptr)
 	trace("cuMemFree -> %d", r);
 	return r;
 }
+/* stream-ordered and pitched allocations: plain device memory here (streams run synchronously) */
+CUresult cuMemAllocAsync(CUdeviceptr *dptr, size_t bytes, CUstream s)
+{
+	(void)s;
+	CUresult r = plain_alloc(dptr, bytes, 1);
+	trace("cuMemAllocAsync %zu -> %d", bytes, r);
+	return r;
+}
+CUresult cuMemAllocFromPoolAsync(CUdeviceptr *dptr, size_t bytes, void *pool, CUstream s)
+{
+	(void)pool; (void)s;
+	CUresult r = plain_alloc(dptr, bytes, 1);
+	trace("cuMemAllocFromPoolAsync %zu -> %d", bytes, r);
+	return r;
+}
+CUresult cuMemFreeAsync(CUdeviceptr dptr, CUstream s)
+{
+	(void)s;
+	CUresult r = plain_free(dptr);
+	trace("cuMemFreeAsync -> %d", r);
+	return r;
+}
+CUresult cuMemAllocPitch_v2(CUdeviceptr *dptr, size_t *pitch, size_t width, size_t height, unsigned elem)
+{
+	(void)elem;
+	*pitch = (width + 511) & ~(size_t)511;
+	CUresult r = plain_alloc(dptr, *pitch * height, 1);
+	trace("cuMemAllocPitch %zu x %zu -> %d", width, height, r);
+	return r;
+}
 CUresult cuMemGetInfo_v2(size_t *free_b, size_t *total_b)
 {
 	setup_once();

@@ -256,3 +256,32 @@ def test_pool_too_small_for_three_clients_overflows_instead_of_failing(artefacts
         assert p.returncode == 0 and re.search(r"RESULT PASS iters=\d+ mismatches=0", out), out + err[-2500:]
     assert sum(err.count("pinned a private overflow arena") for _, err in outs) >= 1
     assert d.read_log().count("Sent DROP_LOCK") >= 4
+
+
+def test_stream_ordered_and_pitched_allocations_are_capped_and_swapped(artefacts, sock_dir, tmp_path):
+    """SURVEY 8f rank 2 / VERDICT r1 #8: cuMemAllocAsync, cuMemAllocFromPoolAsync, cuMemFreeAsync and
+    cuMemAllocPitch go through the cap check and the swap engine like cuMemAlloc (the reference lets
+    them through: such memory is neither charged nor swappable there)."""
+    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
+    try:
+        d.ctl("-T", "1")
+        procs = []
+        for i in (1, 2):
+            env = fake_env(total_mib=4096, ledger=tmp_path / "ledger", trace=tmp_path / f"trace{i}.txt",
+                           extra={"NVSHARE_HOST_ARENA_MIB": 64, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_SOCK_DIR": sock_dir,
+                                  "NVSHARE_POOL_GIB": 1, "NVSHARE_EVICT_POLICY": "all",
+                                  "NVSHARE_STATS_FILE": tmp_path / f"stats{i}.jsonl"})
+            env["LD_PRELOAD"] = preload("ours")
+            procs.append(subprocess.Popen([str(ORACLE / "async_app"), "16", "3.0", str(i), "3"], env=env,
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=120) for p in procs]
+    finally:
+        d.stop()
+    import json
+    for i, (p, (out, err)) in enumerate(zip(procs, outs), 1):
+        assert p.returncode == 0 and "RESULT PASS" in out, out + err[-2000:]
+        assert "CAP rc=2" in out                       # 3 GiB > 4096 - 1536 MiB: CUDA_ERROR_OUT_OF_MEMORY, like cuMemAlloc
+        trace = (tmp_path / f"trace{i}.txt").read_text()
+        assert "cuMemAllocAsync" not in trace and "cuMemAllocPitch" not in trace and "cuMemCreate" in trace
+        ops = [json.loads(l)["op"] for l in (tmp_path / f"stats{i}.jsonl").read_text().splitlines()]
+        assert "evict" in ops and "fetch" in ops       # and it is swapped like any other memory

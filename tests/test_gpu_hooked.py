@@ -182,3 +182,60 @@ def test_loading_client_does_not_take_the_gpu(artefacts, tmp_path):
     err = b.stderr
     assert err.count("served from the backing copy") >= 4
     assert err.index("served from the backing copy") < err.index("Sent REQ_LOCK")   # the lock was asked for afterwards
+
+
+def _pair_of(tmp_path, argv_of, tq=1, extra_env=None, timeout=600):
+    sock_dir = tmp_path / "nvs"
+    sock_dir.mkdir(exist_ok=True)
+    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
+    try:
+        d.ctl("-T", str(tq))
+        procs = []
+        for i in (1, 2):
+            env = dict(os.environ, LD_PRELOAD=preload("ours"), NVSHARE_SOCK_DIR=str(sock_dir), PYTHONPATH=str(ROOT),
+                       NVSHARE_EVICT_POLICY="all", NVSHARE_STATS_FILE=str(tmp_path / f"stats{i}.jsonl"))
+            env.update(extra_env or {})
+            procs.append(subprocess.Popen(argv_of(i), env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=timeout) for p in procs]
+        return d.read_log(), [(p.returncode, o, e) for p, (o, e) in zip(procs, outs)]
+    finally:
+        d.stop()
+
+
+def _assert_swapped(tmp_path, log, res):
+    for rc, out, err in res:
+        assert rc == 0 and "RESULT PASS" in out, out + err[-3000:]
+    assert log.count("Sent DROP_LOCK") >= 2
+    for i in (1, 2):
+        ops = [r["op"] for r in stats(tmp_path, i)]
+        assert "evict" in ops and "fetch" in ops
+
+
+def test_cuda_graph_replays_through_forced_swaps(artefacts, tmp_path):
+    """cuGraphLaunch is gated (the reference lets it through), the capture itself is
+    not disturbed by the launch hook's synchronisation window, and the memory the graph's nodes
+    point at is unmapped and re-mapped under it between replays."""
+    log, res = _pair_of(tmp_path, lambda i: [sys.executable, str(ROOT / "tests" / "apps" / "graph_app.py"), "4096", "8"])
+    _assert_swapped(tmp_path, log, res)
+
+
+def test_cooperative_launches_through_forced_swaps(artefacts, tmp_path):
+    """cuLaunchCooperativeKernel (grid-wide sync) is gated too; runtime-API application, exact 64-bit check."""
+    from nvs_testlib import ORACLE
+    app = ORACLE / "coop_app"
+    if not app.exists():
+        pytest.skip("oracle/_ref/coop_app not built (needs nvcc at build time)")
+    log, res = _pair_of(tmp_path, lambda i: [str(app), "512", "8", str(i)])
+    _assert_swapped(tmp_path, log, res)
+
+
+def test_stream_ordered_allocator_backend_is_capped_and_swapped(artefacts, tmp_path):
+    """PyTorch with backend:cudaMallocAsync: every tensor comes from cuMemAllocAsync / cuMemFreeAsync, which
+    the reference neither charges to the cap nor makes swappable.  Here they go through the swap engine."""
+    log, res = run_pair(tmp_path, "add", 12000, 8, "pos", tq=2,
+                        extra_env={"NVSHARE_EVICT_POLICY": "all", "PYTORCH_CUDA_ALLOC_CONF": "backend:cudaMallocAsync"})
+    for rc, out, err in res:
+        assert rc == 0 and out.startswith("PASS"), out + err[-3000:]
+    for i in (1, 2):
+        recs = stats(tmp_path, i)
+        assert sum(r["bytes"] + r.get("clean_bytes", 0) for r in recs if r["op"] == "evict") >= 3 * 12000 * 12000 * 4
