@@ -108,8 +108,9 @@ typedef struct nvs_engine_config {
 	/* 1 = scan slabs before eviction and do not move same-filled ones (all 64-bit
 	 * words equal): they are re-created on the device at fetch (nvs_slab_splat) */
 	uint32_t elide_constant;
-	/* fetch maps HBM in bursts of this many bytes once that much is free, instead of
-	 * chunk by chunk as it trickles in from the evicting process (8 GiB; probe K, calls 11-12) */
+	/* a fetch that needs HBM somebody else is still releasing waits while the free HBM keeps
+	 * growing and starts mapping when it has stood still for a few ms, or when this many bytes
+	 * (64 GiB) are free: release and create calls of two processes must not interleave (probe K) */
 	uint64_t burst_bytes;
 	/* 1 = keep the backing copy of a chunk after it has been fetched (as long as the pool has
 	 * room: retained units are the first to be reclaimed), record a 128-bit hash per slab when a

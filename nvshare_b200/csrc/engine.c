@@ -479,7 +479,7 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->chunk_bytes = env_u64("NVSHARE_CHUNK_MIB", 256) << 20;
 	cfg->small_alloc_bytes = env_u64("NVSHARE_SMALL_ALLOC_KIB", 1024) << 10;
 	cfg->batch_bytes = env_u64("NVSHARE_BATCH_MIB", 1024) << 20;
-	cfg->burst_bytes = env_u64("NVSHARE_BURST_MIB", 8192) << 20;
+	cfg->burst_bytes = env_u64("NVSHARE_BURST_MIB", 65536) << 20;
 	cfg->host_arena_bytes = env_u64("NVSHARE_HOST_ARENA_MIB", 1024) << 20;
 	/* Pinned-host tier (PCIe Gen5 x16), B200 probes D and G: the copy engines move 55.4 (out) /
 	 * 55.2 (in) GB/s alone and 50.2 + 48.7 with both directions busy in two processes; the
@@ -493,7 +493,12 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->evict_variant = parse_variant(getenv("NVSHARE_EVICT_VARIANT"), parse_variant(all, NVS_COPY_CE));
 	cfg->fetch_variant = parse_variant(getenv("NVSHARE_FETCH_VARIANT"), parse_variant(all, NVS_COPY_CE));
 	cfg->peer_evict_variant = parse_variant(getenv("NVSHARE_PEER_EVICT_VARIANT"), parse_variant(all, NVS_COPY_TMA));
-	cfg->peer_fetch_variant = parse_variant(getenv("NVSHARE_PEER_FETCH_VARIANT"), parse_variant(all, NVS_COPY_TMA));
+	/* ... except that a FETCH usually runs while the previous holder's eviction kernel is still going
+	 * in another process, and the GPU time-slices kernels of different processes (probe G: 22 + 22
+	 * GB/s kernel + kernel against 49 + 44 kernel + copy engine): eviction kernel + fetch on the copy
+	 * engines overlap, two kernels take turns.  NVSHARE_PEER_FETCH_VARIANT=tma for a fetch that has
+	 * the GPU to itself. */
+	cfg->peer_fetch_variant = parse_variant(getenv("NVSHARE_PEER_FETCH_VARIANT"), parse_variant(all, NVS_COPY_CE));
 	cfg->retain = (uint32_t)env_u64("NVSHARE_RETAIN", 1);
 	/* B200 probe: 2 CTAs already saturate PCIe Gen5 x16 in one direction
 	 * (52.7 GB/s); 8 leaves head-room when SMs are shared; the peer tier
@@ -2295,16 +2300,22 @@ out:
 /*
  * Burst gating.  While another process is still handing its HBM back, do NOT map
  * each chunk the moment it fits: with HBM full, one process releasing and another
- * creating chunk by chunk slow every VMM call from ~0.3 ms to ~5 ms (B200, probe K:
- * 41 GB/s of "hand-over bandwidth", less than the PCIe copy it is supposed to feed).
- * Waiting until a burst is free and then mapping it back to back restores ~0.2 ms
- * per call (511 GB/s in the same probe with 8 GiB bursts).  The burst also delays
- * the start of the fetch by burst / eviction rate (0.17 s for 8 GiB over PCIe).
- * 8 GiB is the measured compromise on the BASELINE configuration: 16 GiB costs
- * latency (stall 3.40 s vs 2.93-3.02 s), 2 GiB brings the contention back (three
- * runs: 2.59, 3.16, 4.21 s, eviction down to 35 GB/s; all-ones data 1.10 s vs
- * 0.30 s) -- profiles/r01_call11_burst_sweep_summary.txt, r01_call12_*.
+ * creating chunk by chunk slow every VMM call from ~0.2 ms to ~5 ms (B200, probe K:
+ * 41 GB/s of "hand-over bandwidth", less than the PCIe copy it is supposed to feed);
+ * one process at a time runs at ~0.2 ms per call (511 GB/s with 8 GiB bursts, 1.2 TB/s
+ * for a releaser left alone).  Round 1 therefore mapped in fixed 8 GiB bursts.
+ *
+ * Round 2: since unchanged slabs are no longer copied, most of an eviction is a bare
+ * release that takes ~0.1 s for 70 GB -- if nobody interferes.  So the gate now follows
+ * the releaser instead of a byte count: wait while the free HBM is still GROWING, go as
+ * soon as it has stood still for NVS_SETTLE_MS with room for a batch (the releaser is
+ * done, or is busy copying the next dirty batch: a chunk every ~5 ms over PCIe, and then
+ * its few VMM calls hardly collide with ours), or as soon as `burst_bytes` (now a cap:
+ * 64 GiB) or everything still missing is free.  Measured on the BASELINE configuration
+ * (r2 calls 1 -> 2): fetch wall 2.21 s with fixed 8 GiB bursts (copy 1.81 s + 0.40 s of
+ * stalls), see DESIGN.md section 7 for the adaptive gate.
  */
+#define NVS_SETTLE_MS 3.0
 static int fetch_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep);
 
 /* While a fetch waits for HBM: hand back the backing units of batches that have already
@@ -2323,33 +2334,39 @@ static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report
 {
 	/* head-room kept below the releasing client's own margin (1/512 of the HBM, client.c) */
 	const uint64_t slack = e->cfg.chunk_bytes < (64ull << 20) ? e->cfg.chunk_bytes : (64ull << 20);
-	uint64_t want = remaining < e->cfg.burst_bytes ? remaining : e->cfg.burst_bytes;
+	const uint64_t one_batch = e->cfg.batch_bytes + e->cfg.chunk_bytes + slack;
+	const uint64_t cap = remaining < e->cfg.burst_bytes ? remaining : e->cfg.burst_bytes;
 	size_t free_b = 0, total_b = 0;
-	if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= e->cfg.batch_bytes + e->cfg.chunk_bytes + slack ||
-	    free_b >= remaining + slack)
-		return 0; /* room for at least this batch: carry on with the current burst */
-	double t0 = now_ms(), next_pressure = 0, last_progress = t0;
+	if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= remaining + slack)
+		return 0; /* everything that is still missing fits: nobody has to release anything for us */
+	double t0 = now_ms(), next_pressure = 0, last_growth = t0;
 	size_t last_free = free_b;
+	int polls = 0;
 	for (;;) {
-		if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= want + slack)
-			break;
 		const double now = now_ms(), waited = now - t0;
 		if (free_b > last_free)
-			last_progress = now; /* the previous holder is still handing HBM back: no need to press it */
+			last_growth = now; /* the previous holder is handing HBM back right now */
 		last_free = free_b;
+		if (free_b >= cap + slack)
+			break;
+		if (free_b >= one_batch && polls > 0 && now - last_growth >= NVS_SETTLE_MS)
+			break; /* room for a batch and the releaser has paused: our calls will not collide with its */
 		if (waited > e->cfg.oom_wait_ms) {
 			nvs_warn("engine: HBM still exhausted after %.0f ms", waited);
 			rep->wait_ms += waited;
 			return NVS_E_TIMEOUT;
 		}
-		if (e->cfg.pressure_cb && now - last_progress >= PRESSURE_AFTER_MS && waited >= next_pressure) {
+		if (e->cfg.pressure_cb && now - last_growth >= PRESSURE_AFTER_MS && waited >= next_pressure) {
 			e->cfg.pressure_cb(e->cfg.pressure_user, remaining);
 			next_pressure = waited + 1000;
 		}
 		fetch_retire_completed(e, rep);
 		pthread_mutex_unlock(&e->mu);
-		usleep(2000);
+		usleep(polls < 200 ? 500 : 2000);
 		pthread_mutex_lock(&e->mu);
+		++polls;
+		if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS)
+			break;
 	}
 	rep->wait_ms += now_ms() - t0;
 	return 0;

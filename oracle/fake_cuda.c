@@ -338,6 +338,8 @@ struct phys {
 	int fd;
 	size_t bytes;
 	int live;
+	int exported; /* a shareable handle (fd) of it has left this process: the bytes stay charged to the
+	               * ledger when we release our reference, whoever imports the fd releases them */
 };
 #define MAX_PHYS 65536
 static struct phys g_phys[MAX_PHYS];
@@ -419,11 +421,64 @@ CUresult cuMemRelease(CUmemGenericAllocationHandle h)
 	pthread_mutex_lock(&g_mu);
 	close(g_phys[h].fd);
 	size_t bytes = g_phys[h].bytes;
+	int exported = g_phys[h].exported;
 	g_phys[h].live = 0;
+	g_phys[h].exported = 0;
 	g_my_phys -= bytes;
 	pthread_mutex_unlock(&g_mu);
-	phys_give(bytes);
+	if (!exported)
+		phys_give(bytes);
 	trace("cuMemRelease %zu", bytes);
+	return OK;
+}
+
+/* Shareable handles (POSIX fd): the memfd itself.  Physical memory follows the fd: the exporter's
+ * release does not return the bytes to the ledger, the importer's does. */
+CUresult cuMemExportToShareableHandle(void *out, CUmemGenericAllocationHandle h, int type, unsigned long long flags)
+{
+	(void)flags;
+	if (type != 1 || h == 0 || h >= MAX_PHYS || !g_phys[h].live)
+		return E_INVALID;
+	int fd = dup(g_phys[h].fd);
+	if (fd < 0)
+		return E_OOM;
+	g_phys[h].exported = 1;
+	*(int *)out = fd;
+	trace("cuMemExportToShareableHandle %zu", g_phys[h].bytes);
+	return OK;
+}
+
+CUresult cuMemImportFromShareableHandle(CUmemGenericAllocationHandle *h, void *os_handle, int type)
+{
+	setup_once();
+	int fd = (int)(intptr_t)os_handle;
+	struct stat st;
+	if (type != 1 || fstat(fd, &st) != 0 || st.st_size == 0)
+		return E_INVALID;
+	int mine = dup(fd);
+	if (mine < 0)
+		return E_OOM;
+	pthread_mutex_lock(&g_mu);
+	int slot = -1;
+	for (int i = 1; i < MAX_PHYS; ++i)
+		if (!g_phys[i].live) {
+			slot = i;
+			break;
+		}
+	if (slot > 0) {
+		g_phys[slot].fd = mine;
+		g_phys[slot].bytes = (size_t)st.st_size;
+		g_phys[slot].live = 1;
+		g_phys[slot].exported = 0;
+		g_my_phys += (size_t)st.st_size;
+	}
+	pthread_mutex_unlock(&g_mu);
+	if (slot < 0) {
+		close(mine);
+		return E_OOM;
+	}
+	*h = (CUmemGenericAllocationHandle)slot;
+	trace("cuMemImportFromShareableHandle %zu", (size_t)st.st_size);
 	return OK;
 }
 

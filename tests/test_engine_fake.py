@@ -67,7 +67,7 @@ def test_version_and_default_config(fake):
     assert cfg.chunk_bytes == 256 * MiB and cfg.host_arena_bytes == 1024 * MiB
     # pinned-host tier on the copy engines (256-byte TLPs), peer tier on the sm_100a kernel: engine.c, probes D/G
     assert cfg.evict_variant == E.COPY_CE and cfg.fetch_variant == E.COPY_CE
-    assert cfg.peer_evict_variant == E.COPY_TMA and cfg.peer_fetch_variant == E.COPY_TMA and cfg.retain == 1
+    assert cfg.peer_evict_variant == E.COPY_TMA and cfg.peer_fetch_variant == E.COPY_CE and cfg.retain == 1
     assert cfg.tma_stages == 6 and cfg.tma_tile_bytes == 32768 and cfg.tma_warps == 1
 
 
