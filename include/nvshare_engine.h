@@ -120,6 +120,10 @@ typedef struct nvs_engine_config {
 	 * the pinned-host tier (PCIe), where the copy engines beat any SM kernel by the TLP size */
 	uint32_t peer_evict_variant;
 	uint32_t peer_fetch_variant;
+	/* 1 = while the owner holds the GPU lock, write resident chunks that have no backing copy back
+	 * in the background (fused copy + hash kernel, lowest-priority stream): the link is idle then,
+	 * and whatever has not changed again by the hand-off does not have to be copied on it */
+	uint32_t preclean;
 } nvs_engine_config;
 
 typedef struct nvs_xfer_report {
@@ -162,6 +166,7 @@ typedef struct nvs_stats {
 	uint64_t clean_skipped_bytes_total; /* eviction bytes that did not have to be copied       */
 	uint64_t stolen_slabs_total;    /* retained units this engine took over from other chunks  */
 	uint64_t ce_calls_total;        /* cuMemcpyAsync calls issued by evict / fetch             */
+	uint64_t precleaned_bytes_total; /* written back in the background during the owner's quantum */
 } nvs_stats;
 
 /* Fill *cfg with defaults, then apply NVSHARE_* environment overrides

@@ -96,6 +96,8 @@ struct drv {
 	CUresult (*MemcpyAsync)(CUdeviceptr, CUdeviceptr, size_t, CUstream);
 	CUresult (*MemsetD32Async)(CUdeviceptr, unsigned, size_t, CUstream);
 	CUresult (*StreamCreate)(CUstream *, unsigned);
+	CUresult (*StreamCreateWithPriority)(CUstream *, unsigned, int);        /* optional */
+	CUresult (*CtxGetStreamPriorityRange)(int *, int *);                    /* optional */
 	CUresult (*StreamDestroy)(CUstream);
 	CUresult (*StreamSynchronize)(CUstream);
 	CUresult (*EventCreate)(CUevent *, unsigned);
@@ -194,6 +196,7 @@ struct chunk {
 	uint8_t scanned;    /* this eviction has already scanned it: cpmask / nh / cmask valid */
 	uint8_t had_backing; /* ... and it went into the scan with a valid backing copy        */
 	uint8_t volatile_skips; /* fetches since a volatile chunk's backing was last retained  */
+	uint64_t pre_epoch;  /* engine epoch in which the pre-cleaner last looked at this chunk  */
 	uint32_t btag;      /* tag written next to our units in the pool: proves they are still ours */
 	uint64_t touch;     /* engine touch clock of the last host-side write (nvs_touch)      */
 	uint64_t est_copy;  /* bytes this eviction would have to copy (from the scan)          */
@@ -331,6 +334,17 @@ struct nvs_engine {
 	uint32_t scan_counter_next;
 	uint64_t touch_clock;
 	uint32_t tag_next;
+	/* background pre-cleaning (preclean_main) */
+	pthread_t pre_thread;
+	int pre_thread_started;
+	pthread_cond_t pre_cv;
+	CUstream pre_stream; /* lowest priority: never in the way of the application's kernels */
+	CUevent pre_done;
+	nvs_copy_desc *pre_descs;
+	uint64_t pre_descs_dev;
+	struct scan_result *pre_out;
+	uint64_t pre_out_dev;
+	CUdeviceptr pre_counter;
 	CUevent ev_begin, ev_end;
 	CUdeviceptr counters; /* u32[N_COUNTERS], device memory */
 	uint32_t counter_next;
@@ -500,6 +514,7 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	 * the GPU to itself. */
 	cfg->peer_fetch_variant = parse_variant(getenv("NVSHARE_PEER_FETCH_VARIANT"), parse_variant(all, NVS_COPY_CE));
 	cfg->retain = (uint32_t)env_u64("NVSHARE_RETAIN", 1);
+	cfg->preclean = (uint32_t)env_u64("NVSHARE_PRECLEAN", 1);
 	/* B200 probe: 2 CTAs already saturate PCIe Gen5 x16 in one direction
 	 * (52.7 GB/s); 8 leaves head-room when SMs are shared; the peer tier
 	 * (NVLink 5) wants ~74. */
@@ -2530,6 +2545,148 @@ out:
 	return rc;
 }
 
+/* ---------------------------------------------------------- pre-clean ---- */
+
+/*
+ * SURVEY 8f rank 3, first half: while the owner of the lock computes, the link to the backing
+ * tier is idle.  This thread uses it: one resident chunk at a time that has no (complete)
+ * backing copy is written back by the FUSED copy + hash kernel (nvs_slab_scan with a
+ * destination) on a lowest-priority stream with a handful of CTAs.  Every lane hashes exactly
+ * the vectors it stores, so the recorded hashes describe the bytes in the backing copy whatever
+ * the application's kernels were doing to the source meanwhile; at the hand-off the eviction
+ * scan compares them with the hashes of the then-current contents and copies only what differs.
+ * A chunk that keeps turning out dirty is left alone (ST_VOLATILE, re-probed now and then); only
+ * FREE pool units are used, and the copies are the first thing anybody short of units takes
+ * over (RS_PLAIN).  The reference has no counterpart: UVM pages stay put until somebody faults.
+ */
+static struct chunk *preclean_pick(nvs_engine *e)
+{
+	for (struct alloc *a = e->head; a; a = a->next) {
+		if (a->passthrough)
+			continue;
+		for (uint32_t i = 0; i < a->n_chunks; ++i) {
+			struct chunk *c = &a->chunks[i];
+			if (c->state != CH_RESIDENT || c->backing || c->scanned)
+				continue;
+			if (c->stable == ST_VOLATILE) { /* was dirty against its copy last time: mostly not worth it */
+				if (c->volatile_skips < VOLATILE_REPROBE)
+					continue;
+			}
+			if (c->pre_epoch == e->epoch + 1)
+				continue; /* already tried during this residency */
+			return c;
+		}
+	}
+	return NULL;
+}
+
+static void *preclean_main(void *arg)
+{
+	nvs_engine *e = arg;
+	sigset_t all; /* this thread lives inside an arbitrary application */
+	sigfillset(&all);
+	pthread_sigmask(SIG_SETMASK, &all, NULL);
+	if (ctx_enter(e) != 0)
+		return NULL;
+	uint64_t pass_bytes = 0;
+	pthread_mutex_lock(&e->mu);
+	while (!e->stopping) {
+		if (!e->resident_mode) {
+			pthread_cond_wait(&e->pre_cv, &e->mu);
+			continue;
+		}
+		pthread_mutex_unlock(&e->mu);
+		/* api_mu keeps evict / fetch / free away from the chunk while its copy is in flight */
+		pthread_mutex_lock(&e->api_mu);
+		pthread_mutex_lock(&e->mu);
+		struct chunk *c = (e->resident_mode && !e->stopping) ? preclean_pick(e) : NULL;
+		int launched = 0;
+		if (c) {
+			c->pre_epoch = e->epoch + 1;
+			const uint32_t n = (uint32_t)(c->bytes / SLAB);
+			const uint32_t tag = ++e->tag_next ? e->tag_next : ++e->tag_next;
+			/* free units only: never take over anybody's kept copy, never wait, never pin inline */
+			if (pool_take(e, &e->host_pool, n, &c->backing, 0, tag) == 0) {
+				c->tier = TIER_HOST;
+				c->btag = tag;
+				e->st.host_pool_used = e->host_pool.used;
+				for (uint32_t k = 0; k < n; ++k) {
+					e->pre_descs[k].src = c->va + (uint64_t)k * SLAB;
+					e->pre_descs[k].dst = c->backing + (uint64_t)k * SLAB;
+					e->pre_descs[k].bytes = SLAB;
+					e->pre_descs[k].tag = 0;
+				}
+				uint32_t nn = n, want_hash = 1;
+				unsigned grid = n < 8 ? n : 8;
+				void *params[] = {&e->pre_descs_dev, &nn, &e->pre_counter, &e->pre_out_dev, &want_hash};
+				if (e->d.MemsetD32Async(e->pre_counter, 0, 1, e->pre_stream) == CUDA_SUCCESS &&
+				    e->d.LaunchKernel(e->fn_scan, grid, 1, 1, 256, 1, 1, 0, e->pre_stream, params, NULL) == CUDA_SUCCESS &&
+				    e->d.EventRecord(e->pre_done, e->pre_stream) == CUDA_SUCCESS) {
+					launched = 1;
+					e->st.kernel_launches_total++;
+				} else {
+					pool_give(e, &e->host_pool, c->backing, n, c->btag);
+					c->backing = 0;
+					c->tier = TIER_NONE;
+				}
+			} else if (e->shp && e->cfg.prepin && e->host_pool.bytes < (uint64_t)e->shp->n_windows * e->cfg.host_arena_bytes) {
+				/* let the pinning thread bring the next window in; try again on the next round */
+				c->pre_epoch = 0;
+				e->pin_target = e->host_pool.bytes + e->cfg.host_arena_bytes;
+				pthread_cond_signal(&e->pin_cv);
+			}
+		}
+		if (launched) {
+			pthread_mutex_unlock(&e->mu);
+			CUresult r = e->d.EventSynchronize(e->pre_done);
+			pthread_mutex_lock(&e->mu);
+			const uint32_t n = (uint32_t)(c->bytes / SLAB);
+			if (r == CUDA_SUCCESS && (c->hash || (c->hash = malloc(MAX_CHUNK_SLABS * sizeof(struct slab_hash))))) {
+				for (uint32_t k = 0; k < n; ++k) {
+					c->hash[k].h0 = e->pre_out[k].h0;
+					c->hash[k].h1 = e->pre_out[k].h1;
+				}
+				mask_fill(c->bvalid, n); /* the copy holds bytes for every slab, same-filled or not */
+				backing_mark_retained(e, c);
+				e->st.precleaned_bytes_total += c->bytes;
+				pass_bytes += c->bytes;
+			} else {
+				pool_give(e, &e->host_pool, c->backing, n, c->btag);
+				c->backing = 0;
+				c->tier = TIER_NONE;
+			}
+			e->st.host_pool_used = e->host_pool.used;
+		}
+		const int more = c != NULL;
+		if (!more && pass_bytes) {
+			if (e->stats_file) {
+				fprintf(e->stats_file, "{\"op\":\"preclean\",\"t\":%.6f,\"pid\":%d,\"bytes\":%" PRIu64 ",\"retained_bytes\":%" PRIu64
+					",\"pool_used\":%" PRIu64 "}\n", wall_s(), (int)getpid(), pass_bytes, e->st.retained_bytes, e->host_pool.used);
+				fflush(e->stats_file);
+			}
+			nvs_debug("engine: pre-cleaned %" PRIu64 " MiB in the background", pass_bytes >> 20);
+			pass_bytes = 0;
+		}
+		pthread_mutex_unlock(&e->mu);
+		pthread_mutex_unlock(&e->api_mu);
+		if (more) {
+			usleep(1000); /* leave the entry points room between two chunks */
+			pthread_mutex_lock(&e->mu);
+		} else {
+			/* nothing to do right now: sleep until the next lock grant (or for a while: new allocations) */
+			struct timespec until;
+			clock_gettime(CLOCK_REALTIME, &until);
+			until.tv_sec += 1;
+			pthread_mutex_lock(&e->mu);
+			if (!e->stopping)
+				pthread_cond_timedwait(&e->pre_cv, &e->mu, &until);
+		}
+	}
+	pthread_mutex_unlock(&e->mu);
+	ctx_leave(e);
+	return NULL;
+}
+
 /* ------------------------------------------------------ alloc / free ---- */
 
 void nvs_set_resident_mode(nvs_engine *e, int holds_lock)
@@ -2538,6 +2695,8 @@ void nvs_set_resident_mode(nvs_engine *e, int holds_lock)
 		return;
 	pthread_mutex_lock(&e->mu);
 	e->resident_mode = holds_lock != 0;
+	if (e->resident_mode && e->pre_thread_started)
+		pthread_cond_signal(&e->pre_cv);
 	pthread_mutex_unlock(&e->mu);
 }
 
@@ -3137,8 +3296,12 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 		}
 		memcpy((char *)&e->d + DRV_SYMS[i].off, &p, sizeof(p));
 	}
+	/* optional entry points (older drivers / the test double do without) */
+	*(void **)&e->d.StreamCreateWithPriority = resolve("cuStreamCreateWithPriority");
+	*(void **)&e->d.CtxGetStreamPriorityRange = resolve("cuCtxGetStreamPriorityRange");
 	pthread_mutex_init(&e->api_mu, NULL);
 	pthread_mutex_init(&e->mu, NULL);
+	pthread_cond_init(&e->pre_cv, NULL);
 	pthread_cond_init(&e->pin_cv, NULL);
 	pthread_cond_init(&e->grow_cv, NULL);
 
@@ -3250,6 +3413,25 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 		if (pthread_create(&e->pin_thread, NULL, pin_thread_main, e) == 0)
 			e->pin_thread_started = 1;
 	}
+	if (e->cfg.preclean && e->cfg.retain && e->cfg.n_peers == 0) {
+		int lo = 0, hi = 0;
+		CUdeviceptr dp = 0;
+		if (!(e->d.StreamCreateWithPriority && e->d.CtxGetStreamPriorityRange &&
+		      e->d.CtxGetStreamPriorityRange(&lo, &hi) == CUDA_SUCCESS &&
+		      e->d.StreamCreateWithPriority(&e->pre_stream, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS))
+			CK(e, e->d.StreamCreate(&e->pre_stream, CU_STREAM_NON_BLOCKING));
+		CK(e, e->d.EventCreate(&e->pre_done, CU_EVENT_DISABLE_TIMING));
+		CK(e, e->d.MemHostAlloc((void **)&e->pre_descs, MAX_CHUNK_SLABS * (sizeof(nvs_copy_desc) + sizeof(struct scan_result)),
+					CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+		if (e->d.MemHostGetDevicePointer(&dp, e->pre_descs, 0) != CUDA_SUCCESS)
+			dp = (CUdeviceptr)(uintptr_t)e->pre_descs;
+		e->pre_descs_dev = dp;
+		e->pre_out = (struct scan_result *)(e->pre_descs + MAX_CHUNK_SLABS);
+		e->pre_out_dev = dp + MAX_CHUNK_SLABS * sizeof(nvs_copy_desc);
+		e->pre_counter = e->scratch + 32;
+		if (pthread_create(&e->pre_thread, NULL, preclean_main, e) == 0)
+			e->pre_thread_started = 1;
+	}
 	nvs_debug("engine: ready on device %d (%d SMs): chunk %" PRIu64 " MiB, evict=%u fetch=%u, peers=%d",
 		  e->device, e->n_sms, e->cfg.chunk_bytes >> 20, e->cfg.evict_variant, e->cfg.fetch_variant,
 		  e->cfg.n_peers);
@@ -3268,12 +3450,16 @@ void nvs_engine_destroy(nvs_engine *e)
 {
 	if (!e)
 		return;
-	if (e->pin_thread_started) {
+	if (e->pin_thread_started || e->pre_thread_started) {
 		pthread_mutex_lock(&e->mu);
 		e->stopping = 1;
 		pthread_cond_broadcast(&e->pin_cv);
+		pthread_cond_broadcast(&e->pre_cv);
 		pthread_mutex_unlock(&e->mu);
-		pthread_join(e->pin_thread, NULL);
+		if (e->pin_thread_started)
+			pthread_join(e->pin_thread, NULL);
+		if (e->pre_thread_started)
+			pthread_join(e->pre_thread, NULL);
 	}
 	int have_ctx = e->ctx && e->d.CtxPushCurrent && ctx_enter(e) == 0;
 	if (have_ctx) {
@@ -3319,6 +3505,12 @@ void nvs_engine_destroy(nvs_engine *e)
 			e->d.EventDestroy(e->scan_done);
 		if (e->scan_begin)
 			e->d.EventDestroy(e->scan_begin);
+		if (e->pre_done)
+			e->d.EventDestroy(e->pre_done);
+		if (e->pre_stream)
+			e->d.StreamDestroy(e->pre_stream);
+		if (e->pre_descs)
+			e->d.MemFreeHost(e->pre_descs);
 		if (e->module)
 			e->d.ModuleUnload(e->module);
 		ctx_leave(e);
@@ -3329,6 +3521,7 @@ void nvs_engine_destroy(nvs_engine *e)
 	pthread_mutex_destroy(&e->api_mu);
 	pthread_cond_destroy(&e->pin_cv);
 	pthread_cond_destroy(&e->grow_cv);
+	pthread_cond_destroy(&e->pre_cv);
 	free(e->by_va);
 	free(e);
 }

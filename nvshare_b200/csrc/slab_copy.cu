@@ -254,7 +254,13 @@ nvs_slab_copy_ldg(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uin
  *   nvs_slab_scan    one CTA (256 threads) per slab: out[i] = {word 0, all words
  *                    equal?, h0, h1}.  want_hash == 0: leaves the slab at the first
  *                    32 KiB tile that differs (h0 = h1 = 0).  want_hash != 0: reads
- *                    every byte.
+ *                    every byte.  A descriptor with dst != 0 is a FUSED copy + hash:
+ *                    every 16-byte vector a lane loads is hashed and stored to dst by
+ *                    that same lane, so the hash describes exactly the bytes that
+ *                    landed in dst even while other kernels are writing the source
+ *                    (background pre-cleaning: the engine writes resident chunks back
+ *                    during their owner's quantum, when the link is idle, and no
+ *                    second pass over the copy is needed to know what it holds).
  *   nvs_slab_splat   the inverse of same-filled: fill dst with the 64-bit value
  *
  * The hash (restated in C by oracle/nvshare_oracle.c: oracle_slab_hash, and checked
@@ -312,6 +318,7 @@ nvs_slab_scan(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uint32_
 		if (idx >= n_descs)
 			return;
 		const uint4 *__restrict__ p = reinterpret_cast<const uint4 *>(descs[idx].src);
+		uint4 *__restrict__ q = reinterpret_cast<uint4 *>(descs[idx].dst); /* NULL: scan only */
 		const uint64_t n16 = descs[idx].bytes >> 4;
 		const unsigned long long v0 = reinterpret_cast<const unsigned long long *>(descs[idx].src)[0];
 		const uint32_t v0lo = (uint32_t)v0, v0hi = (uint32_t)(v0 >> 32);
@@ -333,6 +340,8 @@ nvs_slab_scan(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uint32_
 			for (int u = 0; u < NVS_SCAN_UNROLL; ++u) {
 				d |= (v[u].x != v0lo) | (v[u].y != v0hi) | (v[u].z != v0lo) | (v[u].w != v0hi);
 				if (live[u]) {
+					if (q)
+						__stcs(q + base + (uint64_t)u * NVS_SCAN_THREADS + t, v[u]);
 					NVS_H_ROUND(a0, v[u].x);
 					NVS_H_ROUND(a1, v[u].y);
 					NVS_H_ROUND(a2, v[u].z);
@@ -340,7 +349,7 @@ nvs_slab_scan(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uint32_
 				}
 			}
 			differs |= d;
-			if (!want_hash && __syncthreads_or(d)) {
+			if (!want_hash && !q && __syncthreads_or(d)) {
 				differs = 1;
 				break;
 			}
@@ -370,8 +379,8 @@ nvs_slab_scan(const nvs_copy_desc *__restrict__ descs, uint32_t n_descs, uint32_
 			}
 			out[idx].value = v0;
 			out[idx].is_const = !any_differs && (descs[idx].bytes & 15ull) == 0;
-			out[idx].h0 = want_hash ? s0 : 0ull;
-			out[idx].h1 = want_hash ? s1 : 0ull;
+			out[idx].h0 = (want_hash || q) ? s0 : 0ull;
+			out[idx].h1 = (want_hash || q) ? s1 : 0ull;
 		}
 	}
 }

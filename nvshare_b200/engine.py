@@ -37,7 +37,7 @@ class EngineConfig(C.Structure):
         ("pressure_cb", C.c_void_p), ("pressure_user", C.c_void_p),
         ("shared_pool_path", C.c_char_p), ("shared_pool_bytes", C.c_uint64), ("elide_constant", C.c_uint32),
         ("burst_bytes", C.c_uint64), ("retain", C.c_uint32), ("peer_evict_variant", C.c_uint32),
-        ("peer_fetch_variant", C.c_uint32),
+        ("peer_fetch_variant", C.c_uint32), ("preclean", C.c_uint32),
     ]
 
 
@@ -58,7 +58,7 @@ class Stats(C.Structure):
         "n_allocs", "requested_bytes", "va_bytes", "resident_bytes", "swapped_bytes", "unbacked_bytes",
         "passthrough_bytes", "host_pool_bytes", "host_pool_used", "peer_pool_bytes", "peer_pool_used",
         "n_evicts", "n_fetches", "evicted_bytes_total", "fetched_bytes_total", "kernel_launches_total",
-        "host_io_bytes_total", "retained_bytes", "clean_skipped_bytes_total", "stolen_slabs_total", "ce_calls_total")]
+        "host_io_bytes_total", "retained_bytes", "clean_skipped_bytes_total", "stolen_slabs_total", "ce_calls_total", "precleaned_bytes_total")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

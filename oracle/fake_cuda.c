@@ -639,11 +639,18 @@ CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, uns
 		for (uint32_t i = 0; i < n; ++i) {
 			const uint64_t *p = (const uint64_t *)(uintptr_t)d[i].src;
 			uint64_t words = d[i].bytes / 8, k = 1, h[2] = {0, 0};
+			if (d[i].dst) {
+				/* fused copy + hash: in the real kernel every lane hashes the very vector it stores, so the
+				 * result describes what LANDED in dst even if the source is being written meanwhile
+				 * (application threads, here) -- emulated by looking at the copy, not at the source again */
+				memcpy((void *)(uintptr_t)d[i].dst, p, d[i].bytes & ~15ull);
+				p = (const uint64_t *)(uintptr_t)d[i].dst;
+			}
 			while (k < words && p[k] == p[0])
 				++k;
 			out[i].value = p[0];
 			out[i].is_const = (k == words) && (d[i].bytes & 15) == 0;
-			if (want_hash)
+			if (want_hash || d[i].dst)
 				slab_hash_ref(p, d[i].bytes, h);
 			out[i].h0 = h[0];
 			out[i].h1 = h[1];

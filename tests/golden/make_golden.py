@@ -98,7 +98,9 @@ def run_trace_app(lib_impl, sched_dir, tmp, alloc_mib=100 * 1024, total_mib=192 
         env["NVSHARE_SOCK_DIR"] = str(sched_dir)
     r = subprocess.run([str(ORACLE / "trace_app"), str(alloc_mib), "3"], env=env, capture_output=True, text=True,
                        timeout=120)
-    names = [ln.split()[0] for ln in trace.read_text().splitlines() if ln.split()]
+    # the engine's own kernels (background pre-cleaning, scans) are not the application's calls
+    names = [ln.split()[0] for ln in trace.read_text().splitlines()
+             if ln.split() and not (len(ln.split()) > 1 and ln.split()[1].startswith("nvs_slab"))]
     # The real cuMemFree (what the reference's hook calls) synchronises INSIDE the driver, where no trace
     # sees it; our engine frees VMM memory with cuMemUnmap, which does not, so it drains the context
     # itself first.  That explicit call stands for the implicit one and is not part of the comparison.
