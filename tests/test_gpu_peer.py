@@ -22,12 +22,15 @@ def torch2():
     return torch
 
 
-def test_evict_to_peer_hbm_and_back(torch2, artefacts):
+@pytest.mark.parametrize("fetch_v", ["tma", "ce"])
+def test_evict_to_peer_hbm_and_back(torch2, artefacts, fetch_v):
+    """Eviction always on the sm_100a TMA kernel; the fetch on the kernel (a fetch that has the GPU to itself)
+    and on the copy engines (the default: it overlaps the previous holder's eviction kernel)."""
     torch = torch2
     from nvshare_b200 import engine as E
     size = 6 * GiB
     free1_before, _ = torch.cuda.mem_get_info(1)
-    with E.Engine(peers=[1], peer_capacity_bytes=16 * GiB, fetch_variant="tma", elide_constant=0) as e:
+    with E.Engine(peers=[1], peer_capacity_bytes=16 * GiB, peer_fetch_variant=fetch_v, elide_constant=0) as e:
         p = e.alloc(size)
         e.fetch_all()
         e.pattern_fill(p, size // 8, seed=21)
@@ -40,7 +43,10 @@ def test_evict_to_peer_hbm_and_back(torch2, artefacts):
         assert e.pattern_verify(p, size // 8, seed=21) == 0
         evict_gbps = ev["bytes"] / 1e6 / ev["copy_ms"]
         fetch_gbps = fe["bytes"] / 1e6 / fe["copy_ms"]
-        print(f"peer tier: evict {evict_gbps:.0f} GB/s, fetch {fetch_gbps:.0f} GB/s")
+        print(f"peer tier: evict (tma) {evict_gbps:.0f} GB/s, fetch ({fetch_v}) {fetch_gbps:.0f} GB/s, "
+              f"kernel launches {ev['launches']}+{fe['launches']}, copy-engine calls {ev['ce_calls']}+{fe['ce_calls']}")
+        assert ev["launches"] >= 1 and ev["ce_calls"] == 0
+        assert (fe["launches"] >= 1 and fe["ce_calls"] == 0) if fetch_v == "tma" else fe["ce_calls"] >= 1
         assert evict_gbps > 150 and fetch_gbps > 150             # far above PCIe Gen5 x16 (~55 GB/s): NVLink
         e.free(p)
 
