@@ -25,6 +25,9 @@
  *                    pages in; here it runs after cuda_sync_context() on
  *                    DROP_LOCK (src/client.c:308-317) and on early release
  *                    (src/client.c:472-476)
+ *   nvs_evict_announce
+ *                    no counterpart: tells the next holder's fetch (through the shared pool
+ *                    header) that HBM is about to be released for it
  *   nvs_evict_best_effort
  *                    no counterpart: eviction as a favour to the client that is
  *                    mapping (memory-pressure hint on the wire); never waits for
@@ -207,6 +210,11 @@ int nvs_evict(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep);
  * repeats the whole copy on the GPU path, which makes that harmless.
  */
 int nvs_host_io(nvs_engine *e, uint64_t dptr, void *host, uint64_t bytes, int to_device);
+
+/* Say that an eviction for the next holder is about to start (call it BEFORE the lock is given
+ * away, nvs_evict after): the next holder's fetch then follows this engine's release progress
+ * through the shared pool instead of polling the driver.  No-op without a shared pool. */
+void nvs_evict_announce(nvs_engine *e);
 
 /* Like nvs_evict, but never waits for room in the backing tier: it evicts what the
  * tier can take right now and returns 0 (possibly having moved less than asked).

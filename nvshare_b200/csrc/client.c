@@ -191,6 +191,8 @@ static void release_lock_and_evict(int have_hint, unsigned waiters, uint64_t nee
 	close_gate_and_drain();
 	sync_app_context();
 	uint64_t mib = eviction_amount_mib(have_hint, waiters, need_mib);
+	if (mib != 0 && dp.evict_announce)
+		dp.evict_announce(); /* before the next holder is told to go: its fetch then follows our progress */
 	if (early_release)
 		send_msg(NVS_LOCK_RELEASED, NULL);
 	do_evict(mib);

@@ -35,6 +35,7 @@ struct nvs_client_datapath {
 	uint64_t (*free_hbm_mib)(void);         /* what the driver reports free right now    */
 	uint64_t (*total_hbm_mib)(void);
 	int (*evict_best_effort)(uint64_t min_bytes); /* same, but never waits for backing space */
+	void (*evict_announce)(void);           /* an eviction for the next holder is about to start */
 };
 
 void nvs_client_start(const struct nvs_client_driver *drv, const struct nvs_client_datapath *dp);

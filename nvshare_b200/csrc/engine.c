@@ -270,6 +270,14 @@ struct shp_hdr {
 	int32_t owners[SHP_MAX_SLABS];
 	uint8_t rstate[SHP_MAX_SLABS]; /* RS_*: the unit holds a copy its owner can do without */
 	uint32_t ctag[SHP_MAX_SLABS];
+	/* Hand-over progress, written by the client that is evicting for the next holder and read by
+	 * the one that is fetching: how much HBM the eviction announced by `releaser_pid` has given
+	 * back so far.  The fetching side waits on these words instead of polling cuMemGetInfo every
+	 * millisecond -- driver calls of two processes at the moment one of them runs hundreds of
+	 * cuMemUnmap / cuMemRelease back to back are exactly what made the release slow (probe K). */
+	volatile int32_t releaser_pid;       /* 0: nobody is releasing                           */
+	volatile uint32_t release_seq;       /* bumped at every announcement                     */
+	volatile uint64_t released_bytes;    /* since the announcement                           */
 };
 enum { RS_NONE = 0, RS_PLAIN = 1, RS_STABLE = 2 }; /* reclaim order: free, then PLAIN, then STABLE */
 _Static_assert(sizeof(struct shp_hdr) <= SHP_HDR_BYTES, "shared pool header too large");
@@ -1166,7 +1174,10 @@ static int backing_assign(nvs_engine *e, struct chunk *c, int nowait)
 		if (!e->shp || nowait || now_ms() - t0 > e->cfg.oom_wait_ms)
 			return rc;
 		/* the shared pool is full and entirely pinned here: another client is about
-		 * to hand units back (its fetch releases them batch by batch) -- unless it died */
+		 * to hand units back (its fetch releases them batch by batch) -- unless it died.
+		 * Whoever follows our release progress must not wait for us while we wait for it. */
+		if (e->shp->hdr->releaser_pid == (int32_t)getpid())
+			__atomic_store_n(&e->shp->hdr->releaser_pid, 0, __ATOMIC_RELEASE);
 		if (now_ms() >= next_reap) {
 			next_reap = now_ms() + 500;
 			if (shp_reap_dead(e->shp))
@@ -2077,10 +2088,35 @@ static int evict_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
 		rep->chunks++;
 	}
 	rep->map_ms += now_ms() - t0;
+	if (e->shp && e->shp->hdr->releaser_pid == (int32_t)getpid()) {
+		uint64_t freed = 0;
+		for (uint32_t i = 0; i < s->n_chunks; ++i)
+			freed += s->chunks[i]->bytes;
+		__atomic_fetch_add(&e->shp->hdr->released_bytes, freed, __ATOMIC_RELEASE);
+	}
 out:
 	s->busy = 0;
 	slot_reset(s);
 	return rc;
+}
+
+/* The owner is about to give the lock away and will then evict: said BEFORE the next holder is
+ * told to go, so that its fetch knows somebody is releasing HBM for it and follows the progress
+ * words in the shared pool header instead of polling the driver. */
+void nvs_evict_announce(nvs_engine *e)
+{
+	if (!e || !e->shp)
+		return;
+	struct shp_hdr *h = e->shp->hdr;
+	h->released_bytes = 0;
+	__atomic_fetch_add(&h->release_seq, 1, __ATOMIC_RELEASE);
+	__atomic_store_n(&h->releaser_pid, (int32_t)getpid(), __ATOMIC_RELEASE);
+}
+
+static void evict_announce_done(nvs_engine *e)
+{
+	if (e->shp && e->shp->hdr->releaser_pid == (int32_t)getpid())
+		__atomic_store_n(&e->shp->hdr->releaser_pid, 0, __ATOMIC_RELEASE);
 }
 
 static int evict_impl(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep_out, int best_effort);
@@ -2288,6 +2324,7 @@ out:
 		e->slots[k].busy = 0;
 		slot_reset(&e->slots[k]);
 	}
+	evict_announce_done(e);
 	/* chunks this call looked at but did not put out (it stopped early, or failed) */
 	for (size_t j = 0; victims && j < n_all; ++j) {
 		struct chunk *c = victims[j];
@@ -2357,6 +2394,34 @@ static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report
 	double t0 = now_ms(), next_pressure = 0, last_growth = t0;
 	size_t last_free = free_b;
 	int polls = 0;
+	/* Somebody has announced that it is releasing for us (same scheduler, shared pool): follow
+	 * its progress words, without a single driver call, until it is done or `cap` has come back. */
+	if (e->shp) {
+		struct shp_hdr *h = e->shp->hdr;
+		int32_t who = __atomic_load_n(&h->releaser_pid, __ATOMIC_ACQUIRE);
+		const uint32_t seq = __atomic_load_n(&h->release_seq, __ATOMIC_ACQUIRE);
+		if (who != 0 && who != (int32_t)getpid()) {
+			for (;;) {
+				who = __atomic_load_n(&h->releaser_pid, __ATOMIC_ACQUIRE);
+				if (who == 0 || __atomic_load_n(&h->release_seq, __ATOMIC_ACQUIRE) != seq ||
+				    __atomic_load_n(&h->released_bytes, __ATOMIC_ACQUIRE) >= cap + slack)
+					break;
+				if (now_ms() - t0 > 2000.0 || (kill(who, 0) != 0 && errno == ESRCH))
+					break; /* stuck or gone: fall back to asking the driver */
+				fetch_retire_completed(e, rep); /* the releaser may be waiting for the units of what has landed here */
+				pthread_mutex_unlock(&e->mu);
+				usleep(200);
+				pthread_mutex_lock(&e->mu);
+			}
+			fetch_retire_completed(e, rep);
+			if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= one_batch) {
+				rep->wait_ms += now_ms() - t0;
+				return 0;
+			}
+			last_free = free_b;
+			last_growth = now_ms();
+		}
+	}
 	for (;;) {
 		const double now = now_ms(), waited = now - t0;
 		if (free_b > last_free)
@@ -2377,7 +2442,7 @@ static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report
 		}
 		fetch_retire_completed(e, rep);
 		pthread_mutex_unlock(&e->mu);
-		usleep(polls < 200 ? 500 : 2000);
+		usleep(polls < 100 ? 1000 : 2000);
 		pthread_mutex_lock(&e->mu);
 		++polls;
 		if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS)

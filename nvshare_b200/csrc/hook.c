@@ -499,6 +499,17 @@ static int dp_evict_impl(uint64_t min_bytes, int best_effort)
 	return rc;
 }
 
+static void dp_evict_announce(void)
+{
+	if (nvs_process_exiting)
+		return;
+	pthread_mutex_lock(&engine_mu);
+	nvs_engine *e = engine;
+	pthread_mutex_unlock(&engine_mu);
+	if (e)
+		nvs_evict_announce(e);
+}
+
 static uint64_t dp_nonresident_mib(void)
 {
 	pthread_mutex_lock(&engine_mu);
@@ -551,7 +562,7 @@ static void reset_sync_window(void)
 static void start_client(void)
 {
 	static const struct nvs_client_datapath dp = {dp_fetch_all, dp_evict, dp_nonresident_mib, dp_lock_state,
-						       dp_free_hbm_mib, dp_total_hbm_mib, dp_evict_best_effort};
+						       dp_free_hbm_mib, dp_total_hbm_mib, dp_evict_best_effort, dp_evict_announce};
 	nvs_client_on_context_sync = reset_sync_window;
 	nvs_client_start(&client_drv, uvm_mode ? NULL : &dp);
 }
