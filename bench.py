@@ -445,7 +445,8 @@ def run_experiment(impl, kind, pattern, clients, oversub, tq, warmup, steps, tot
             "host_bytes": {"out": sum(r["host_bytes"] for r in ev), "in": sum(r["host_bytes"] for r in fe)},
             "peer_bytes": {"out": sum(r["peer_bytes"] for r in ev), "in": sum(r["peer_bytes"] for r in fe)},
             "copy_ms": {"evict": sum(r["copy_ms"] for r in ev), "fetch": sum(r["copy_ms"] for r in fe)},
-            "scan_ms": sum(r.get("scan_ms", 0) for r in ev),
+            "scan_ms": sum(r.get("scan_ms", 0) for r in ev), "scan_launches": sum(r.get("scan_launches", 0) for r in ev),
+            "copy_kernel_launches": sum(r["launches"] - r.get("scan_launches", 0) for r in ev) + sum(1 for r in fe if r["peer_bytes"] and r["launches"]),
             "kernel_launches": sum(r["launches"] for r in ev + fe), "ce_calls": sum(r.get("ce_calls", 0) for r in ev + fe),
             "evicts": len(ev), "fetches": len(fe),
             "map_ms_mean": statistics_mean([r["map_ms"] for r in ev + fe]),
@@ -480,8 +481,12 @@ def roofline_objects(exp, probe, world):
             "note": "bytes the scan/hash launches of the timed evictions read / their CUDA-event time; alone on an idle GPU: "
                     "see roofline_kernels.scan_hash"}
     t = traffic.get("nvs_slab_scan")
-    scan["traffic"] = t["dram_per_algorithmic_byte"] if t else None
-    scan["traffic_unit"] = "DRAM bytes (read + write, ncu --set full) per algorithmic byte" if t else None
+    per_launch = d["bytes_scanned"] / d["scan_launches"] if d.get("scan_launches") else None
+    scan["algorithmic_bytes_per_launch"] = per_launch
+    scan["launches"] = d.get("scan_launches")
+    scan["traffic"] = per_launch * t["dram_per_algorithmic_byte"] if t and per_launch else None
+    scan["traffic_source"] = (f"DRAM read + write bytes per launch = algorithmic bytes per launch x {t['dram_per_algorithmic_byte']:.4f} "
+                              f"({t['source']})") if t else None
     if world == 1:
         out["roofline"] = scan
         out["roofline_link"] = {
@@ -507,8 +512,12 @@ def roofline_objects(exp, probe, world):
                                      "frac": d["fetch_GBps"] / pk_in if d.get("fetch_GBps") and pk_in else None},
                            "peak_source": "cuMemcpyPeer GPU0<->GPU1 measured in this run" if pk_out else
                                           "770 GB/s (B200_PROFILING.md fallback)",
-                           "traffic": t["dram_per_algorithmic_byte"] if t else None,
-                           "traffic_unit": "local DRAM bytes per algorithmic byte (ncu --set full)" if t else None}
+                           "algorithmic_bytes_per_launch": ((d["peer_bytes"]["out"] + d["peer_bytes"]["in"]) / d["copy_kernel_launches"]
+                                                            if d.get("copy_kernel_launches") else None),
+                           "traffic": ((d["peer_bytes"]["out"] + d["peer_bytes"]["in"]) / d["copy_kernel_launches"] * t["dram_per_algorithmic_byte"]
+                                       if t and d.get("copy_kernel_launches") else None),
+                           "traffic_source": (f"local DRAM bytes per launch = algorithmic bytes per launch x {t['dram_per_algorithmic_byte']:.4f} "
+                                              f"({t['source']})") if t else None}
         out["roofline_scan"] = scan
     out["roofline_kernels"] = probe.get("kernels")
     return out

@@ -147,6 +147,7 @@ typedef struct nvs_xfer_report {
 	                          sm_100a kernel launches only                            */
 	uint64_t scanned_bytes; /* bytes the scan/hash kernel read from HBM                */
 	double   scan_ms;      /* CUDA-event time of the scan/hash launches               */
+	uint64_t scan_launches; /* how many of `launches` were scan/hash launches          */
 } nvs_xfer_report;
 
 typedef struct nvs_stats {

@@ -1943,6 +1943,7 @@ static int scan_slot(nvs_engine *e, struct slot *s, nvs_xfer_report *rep)
 		if (e->d.EventElapsedTime(&ms, e->scan_begin, e->scan_done) == CUDA_SUCCESS)
 			rep->scan_ms += ms;
 		rep->launches++;
+		rep->scan_launches++;
 		/* the early-exit scan reads one 32 KiB tile of a slab that is not same-filled */
 		rep->scanned_bytes += want_hash ? bytes : 0;
 	}
@@ -2021,10 +2022,10 @@ static void report_emit(nvs_engine *e, const char *what, const nvs_xfer_report *
 		",\"chunks\":%" PRIu64 ",\"launches\":%" PRIu64 ",\"ce_calls\":%" PRIu64 ",\"wall_ms\":%.3f,\"copy_ms\":%.3f,"
 		"\"map_ms\":%.3f,\"wait_ms\":%.3f,\"scan_ms\":%.3f,\"host_bytes\":%" PRIu64 ",\"peer_bytes\":%" PRIu64
 		",\"elided_bytes\":%" PRIu64 ",\"clean_bytes\":%" PRIu64 ",\"scanned_bytes\":%" PRIu64
-		",\"retained_bytes\":%" PRIu64 ",\"pool_used\":%" PRIu64 "}\n",
+		",\"scan_launches\":%" PRIu64 ",\"retained_bytes\":%" PRIu64 ",\"pool_used\":%" PRIu64 "}\n",
 		what, wall_s(), (int)getpid(), r->bytes, r->slabs, r->chunks, r->launches, r->ce_calls, r->wall_ms, r->copy_ms,
 		r->map_ms, r->wait_ms, r->scan_ms, r->host_bytes, r->peer_bytes, r->elided_bytes, r->clean_bytes,
-		r->scanned_bytes, e->st.retained_bytes, e->host_pool.used);
+		r->scanned_bytes, r->scan_launches, e->st.retained_bytes, e->host_pool.used);
 	fflush(e->stats_file);
 }
 

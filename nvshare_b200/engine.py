@@ -47,6 +47,7 @@ class XferReport(C.Structure):
         ("wall_ms", C.c_double), ("copy_ms", C.c_double), ("map_ms", C.c_double), ("wait_ms", C.c_double),
         ("host_bytes", C.c_uint64), ("peer_bytes", C.c_uint64), ("elided_bytes", C.c_uint64),
         ("clean_bytes", C.c_uint64), ("ce_calls", C.c_uint64), ("scanned_bytes", C.c_uint64), ("scan_ms", C.c_double),
+        ("scan_launches", C.c_uint64),
     ]
 
     def as_dict(self):

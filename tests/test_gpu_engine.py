@@ -43,7 +43,10 @@ def oracle(artefacts):
 @pytest.fixture()
 def engine(torch_cuda, artefacts):
     from nvshare_b200 import engine as E
-    e = E.Engine()                          # production defaults: 256 MiB chunks, host tier on the copy engines, clean-slab skip
+    # production defaults (256 MiB chunks, host tier on the copy engines, clean-slab skip) except background
+    # pre-cleaning: it would write chunks back while a test is still filling them and make the byte counts
+    # asserted below depend on timing (it has its own test)
+    e = E.Engine(preclean=0)
     yield e
     e.close()
 
@@ -286,6 +289,44 @@ def test_clean_slabs_are_not_copied_again_and_one_changed_word_is(torch_cuda, en
     assert engine.pattern_verify(p, word, first_index=11, seed=5) == 0       # everything before it still the pattern
     del t
     engine.free(p)
+
+
+def test_background_precleaning_with_the_fused_copy_hash_kernel(torch_cuda, artefacts):
+    """nvs_slab_scan with a destination (copy + hash in one pass) on the GPU: while the "owner" holds the lock and a
+    kernel keeps rewriting one allocation, the pre-cleaner writes everything back; the eviction then copies only
+    what the recorded hashes do not vouch for, and every byte survives the round trip."""
+    import time
+    torch = torch_cuda
+    from nvshare_b200 import engine as E
+    with E.Engine() as e:
+        size = 1 * GiB
+        quiet, busy = e.alloc(size), e.alloc(size)
+        e.fetch_all()
+        e.pattern_fill(quiet, size // 8, first_index=3, seed=8)
+
+        class Raw:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+        t = torch.as_tensor(Raw(busy, size // 8), device="cuda")
+        t.zero_()
+        e.set_resident_mode(True)
+        deadline = time.time() + 20
+        while e.stats()["precleaned_bytes_total"] < 2 * size and time.time() < deadline:
+            t.add_(1)                                        # the application keeps writing while its memory is being copied
+            torch.cuda.synchronize()
+        assert e.stats()["precleaned_bytes_total"] >= 2 * size
+        t.add_(1)
+        torch.cuda.synchronize()
+        expect = int(t[0].item())
+        r = e.evict(0)
+        assert r["clean_bytes"] >= size and r["bytes"] + r["clean_bytes"] + r["elided_bytes"] == 2 * size   # `quiet` was not copied again
+        assert r["bytes"] > 0                                                                            # `busy` had changed
+        e.fetch_all()
+        assert e.pattern_verify(quiet, size // 8, first_index=3, seed=8) == 0
+        assert bool((t == expect).all().item())
+        del t
+        e.free(quiet); e.free(busy)
 
 
 @pytest.mark.parametrize("warps,stages,tile_kib", [(1, 2, 16), (1, 6, 32), (4, 3, 16), (8, 3, 8), (2, 4, 24), (1, 3, 64)])

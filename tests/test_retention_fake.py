@@ -45,7 +45,8 @@ def view(ptr, nbytes):
 
 def mk(**kw):
     from nvshare_b200 import engine as E
-    args = dict(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, batch_bytes=24 * MiB, oom_wait_ms=300, prepin=0)
+    # background pre-cleaning is tested on its own below: with it the byte counts asserted here depend on timing
+    args = dict(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, batch_bytes=24 * MiB, oom_wait_ms=300, prepin=0, preclean=0)
     args.update(kw)
     return E.Engine(**args)
 
@@ -242,6 +243,34 @@ def test_scan_slabs_matches_the_oracle_hash(fake, oracle):
         e.close()
 
 
+def test_background_precleaning_through_the_c_abi(fake):
+    """The owner holds the lock (resident mode) and leaves its data alone: the pre-cleaner writes every resident
+    chunk back with the fused copy + hash kernel; the eviction that follows copies nothing."""
+    import time
+    e = mk(preclean=1, prepin=1)                         # the pre-cleaner only takes units that are already pinned
+    try:
+        p = e.alloc(32 * MiB)
+        e.fetch_all()
+        e.pattern_fill(p, 32 * MiB // 8, seed=77)
+        e.set_resident_mode(True)                            # what libnvshare.so says when LOCK_OK has been handled
+        deadline = time.time() + 10
+        while e.stats()["precleaned_bytes_total"] < 32 * MiB and time.time() < deadline:
+            time.sleep(0.02)
+        st = e.stats()
+        assert st["precleaned_bytes_total"] >= 32 * MiB and st["retained_bytes"] == 32 * MiB
+        view(p + 5 * MiB, 8)[:] = 1                          # ... then one slab changes after all
+        r = e.evict(0)
+        assert r["bytes"] == SLAB and r["clean_bytes"] == 32 * MiB - SLAB
+        e.fetch_all()
+        want = np.empty(32 * MiB // 8, dtype=np.uint64)
+        C.CDLL(str(ORACLE / "liboracle.so")).oracle_pattern_fill(C.c_void_p(want.ctypes.data), C.c_uint64(want.size), C.c_uint64(0), C.c_uint64(77))
+        want.view(np.uint8)[5 * MiB:5 * MiB + 8] = 1
+        assert np.array_equal(view(p, 32 * MiB).view(np.uint64), want)
+        e.free(p)
+    finally:
+        e.close()
+
+
 def test_shared_pool_other_client_takes_over_kept_copies(artefacts, tmp_path):
     """Two clients, one shared pool that cannot hold what both would like to keep: the second
     takes over the first one's kept (reclaimable) units; the first notices at its next eviction
@@ -255,7 +284,7 @@ def test_shared_pool_other_client_takes_over_kept_copies(artefacts, tmp_path):
         from nvshare_b200 import engine as E
         MiB = 1 << 20
         e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=32 * MiB, shared_pool_path={str(pool)!r},
-                     shared_pool_bytes=64 * MiB, prepin=0, oom_wait_ms=2000)
+                     shared_pool_bytes=64 * MiB, prepin=0, oom_wait_ms=2000, preclean=0)
         step = {str(tmp_path)!r} + "/step"
         def wait(n):
             while not os.path.exists(step + str(n)): time.sleep(0.01)
