@@ -72,7 +72,7 @@ def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--tq", type=int, default=0, help="scheduler time quantum in seconds (reference default: 30); "
                     "0 = 10 for add (the reference's README: \"don't set TQ < 10\"), 30 for matmul, 5 for the model configs")
@@ -688,7 +688,9 @@ def extras(args, line, probe, world, total_b, frac, out_dir):
         ref_frac, _ = pick_fraction("reference", args.clients, args.oversub, total_b, 0.0, 1)
         if ref_frac < frac - 0.01:
             try:
-                exp = run_experiment("ours", "add", args.pattern, args.clients, args.oversub, args.tq, min(args.warmup, 4),
+                # (five hand-offs of warm-up like the headline: each client has to evict twice before the
+                # engine knows which of its chunks are worth keeping copies of)
+                exp = run_experiment("ours", "add", args.pattern, args.clients, args.oversub, args.tq, min(max(args.warmup, 5), 6),
                                      min(args.steps, 6), total_b, ref_frac, 1, out_dir / "same_scale")
                 line["same_scale"] = brief(exp)
                 line["same_scale"]["why"] = ("the reference arm cannot hold 2 x footprint in this box's host RAM and runs at "
