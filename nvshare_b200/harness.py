@@ -146,7 +146,9 @@ def engine_records(paths, t_start, t_end):
 # ------------------------------------------------------------------ running --
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  Once a second:
+    every sample is a round of NVML queries that take driver locks the hand-off's cuMemUnmap /
+    cuMemCreate calls also need (r2 call 5: the same 373 unmaps took 150 ms or 1.4 s)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -159,7 +161,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                       "--format=csv,noheader,nounits", "-lms", "1000"],
                                       stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except FileNotFoundError:
             self.p = None
