@@ -65,6 +65,7 @@ from nvshare_b200 import harness  # noqa: E402
 
 GiB = 1 << 30
 MiB = 1 << 20
+T_START = time.time()          # of this process: the driver's clock around the run starts about here
 METRIC = "swap_GBps_at_1.5x_hbm_oversub_2_clients"
 
 
@@ -347,7 +348,7 @@ def statistics_mean(xs):
 
 
 def run_experiment(impl, kind, pattern, clients, oversub, tq, warmup, steps, total_b, hbm_fraction, world, out_dir,
-                   peer_capacity_frac=0.92):
+                   peer_capacity_frac=0.92, time_limit_s=None):
     """One co-located run: calibration (solo, un-hooked), the clients under the chosen library + scheduler,
     analysis.  Returns a dict; never raises for a failed run (reports it)."""
     out_dir = Path(out_dir)
@@ -390,12 +391,20 @@ def run_experiment(impl, kind, pattern, clients, oversub, tq, warmup, steps, tot
         # the clients stop as soon as warmup + steps + 2 hand-offs have been seen; this is only the safety limit
         per_handoff = tq + (12 if impl == "ours" else 60) + (0 if kind in ("add",) else 20)
         seconds = (warmup + steps + 3) * per_handoff + 60
+        setup_timeout = 1800
+        if time_limit_s:             # a sub-run inside somebody else's time limit: never overrun it
+            left = time_limit_s - (time.time() - t0)
+            setup_timeout = max(30.0, 0.6 * left)
+            seconds = min(seconds, max(20.0, left - setup_timeout - 20))
         sampler = harness.ClockSampler(out_dir / "clocks.csv")
         sampler.start()
         t0 = time.time()
         try:
             runs = harness.run_clients(impl, out_dir, clients, spec, seconds, tq, extra_env=extra,
-                                       stop_after_handoffs=warmup + steps + 2)
+                                       stop_after_handoffs=warmup + steps + 2, setup_timeout=setup_timeout)
+        except RuntimeError as ex:
+            res.update({"error": str(ex), "verified": False})
+            return res
         finally:
             res["clocks"] = sampler.stop()
         res["wall_s"] = time.time() - t0
@@ -644,7 +653,7 @@ def run_rank0(args, world):
         if cpu:
             line["cpu_baseline"] = cpu
         if not args.no_extras:
-            extras(args, line, probe, world, total_b, frac, out_dir)
+            extras(args, line, probe, world, total_b, frac, out_dir, T_START)
     else:
         line["value"] = e2e
         line["gpu_launches"] = 0
@@ -679,19 +688,29 @@ def brief(exp):
     return out
 
 
-def extras(args, line, probe, world, total_b, frac, out_dir):
+# The driver gives every `bench.py --gpus N` run 870 s (SCALE_r01.json per_n_timeout_s); the sub-runs only get
+# what the headline has left of a budget well inside that, and say so when they had to be skipped or cut.
+TOTAL_BUDGET_S = 780.0
+
+
+def extras(args, line, probe, world, total_b, frac, out_dir, t_bench_start):
     """Sub-runs that make the other BASELINE configurations and a same-configuration pair driver-visible.
     Each is independent: a failure is reported inside its own record and never costs the headline."""
     if args.kind != "add":
         return
+
+    def left():
+        return TOTAL_BUDGET_S - (time.time() - t_bench_start)
     if world == 1:
         ref_frac, _ = pick_fraction("reference", args.clients, args.oversub, total_b, 0.0, 1)
-        if ref_frac < frac - 0.01:
+        if ref_frac < frac - 0.01 and left() < 170:
+            line["same_scale"] = {"skipped": f"only {left():.0f} s of the run's time budget left"}
+        elif ref_frac < frac - 0.01:
             try:
                 # (five hand-offs of warm-up like the headline: each client has to evict twice before the
                 # engine knows which of its chunks are worth keeping copies of)
                 exp = run_experiment("ours", "add", args.pattern, args.clients, args.oversub, args.tq, min(max(args.warmup, 5), 6),
-                                     min(args.steps, 6), total_b, ref_frac, 1, out_dir / "same_scale")
+                                     min(args.steps, 6), total_b, ref_frac, 1, out_dir / "same_scale", time_limit_s=left())
                 line["same_scale"] = brief(exp)
                 line["same_scale"]["why"] = ("the reference arm cannot hold 2 x footprint in this box's host RAM and runs at "
                                              "this fraction of the HBM; this is our arm in that very configuration")
@@ -705,9 +724,12 @@ def extras(args, line, probe, world, total_b, frac, out_dir):
         plan.append(("config5_llama7b_decode_x4_3xHBM_peer_tier", "llama"))
     for name, kind in plan:
         clients, oversub, tq, _ = KIND_DEFAULTS[kind]
+        if left() < 240:
+            line["configs"][name] = {"skipped": f"only {left():.0f} s of the run's time budget left", "verified": None}
+            continue
         try:
             exp = run_experiment("ours", kind, "pos", clients, oversub, tq, 2, 4, total_b, 1.0, world, out_dir / name,
-                                 peer_capacity_frac=0.97)
+                                 peer_capacity_frac=0.97, time_limit_s=left())
             line["configs"][name] = brief(exp)
         except Exception as ex:
             line["configs"][name] = {"error": repr(ex), "verified": False}

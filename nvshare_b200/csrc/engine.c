@@ -1648,8 +1648,20 @@ static void state_account(nvs_engine *e, struct chunk *c, int new_state)
 	c->state = (uint8_t)new_state;
 }
 
-/* Give a chunk physical HBM.  Retries while another process is still releasing. */
+#define NVS_I_LOCK_LOST (-100) /* internal: chunk_map gave up because its owner no longer holds the GPU lock */
+
+/* Give a chunk physical HBM.  Retries while another process is still releasing.
+ * while_holding_lock: the caller is an allocation made by the lock HOLDER (mapped at once);
+ * if the lock goes away while it waits for HBM, waiting on makes no sense -- nobody will be
+ * asked to make room for a client that is not running -- so it returns NVS_I_LOCK_LOST and
+ * the rest of the allocation stays virtual until the next fetch. */
+static int chunk_map_ex(nvs_engine *e, struct chunk *c, double *wait_ms, int while_holding_lock);
 static int chunk_map(nvs_engine *e, struct chunk *c, double *wait_ms)
+{
+	return chunk_map_ex(e, c, wait_ms, 0);
+}
+
+static int chunk_map_ex(nvs_engine *e, struct chunk *c, double *wait_ms, int while_holding_lock)
 {
 	CUmemAllocationProp prop;
 	memset(&prop, 0, sizeof(prop));
@@ -1682,6 +1694,8 @@ static int chunk_map(nvs_engine *e, struct chunk *c, double *wait_ms)
 			nvs_debug("engine: waiting for HBM to be released by another client");
 			warned = 1;
 		}
+		if (while_holding_lock && !e->resident_mode)
+			return NVS_I_LOCK_LOST;
 		if (e->cfg.pressure_cb && now_ms() - last_progress >= PRESSURE_AFTER_MS && waited >= next_pressure) {
 			/* nobody is (any longer) freeing memory for us: say how much we still miss */
 			e->cfg.pressure_cb(e->cfg.pressure_user, e->st.swapped_bytes + e->st.unbacked_bytes);
@@ -2828,7 +2842,13 @@ int nvs_alloc(nvs_engine *e, uint64_t *dptr, uint64_t bytes)
 	if (e->resident_mode) {
 		for (uint32_t i = 0; i < a->n_chunks; ++i) {
 			struct chunk *c = &a->chunks[i];
-			if ((rc = chunk_map(e, c, NULL)) != 0) {
+			if ((rc = chunk_map_ex(e, c, NULL, 1)) == NVS_I_LOCK_LOST) {
+				/* the quantum ended while we were waiting for HBM: what is mapped stays, the rest of
+				 * the allocation is virtual until this client is granted the lock again (nvs_fetch_all) */
+				rc = 0;
+				break;
+			}
+			if (rc != 0) {
 				for (uint32_t k = 0; k < i; ++k) {
 					chunk_unmap(e, &a->chunks[k]);
 					state_account(e, &a->chunks[k], CH_UNBACKED);

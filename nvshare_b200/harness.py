@@ -286,7 +286,7 @@ def calibrate(spec, out_dir, env=None, timeout=1800):
 
 
 def run_clients(impl, out_dir, n_clients, spec, seconds, tq, extra_env=None, start_stagger=0.0,
-                stop_after_handoffs=0, gpu=None):
+                stop_after_handoffs=0, gpu=None, setup_timeout=1800):
     """Run the co-located clients until `stop_after_handoffs` hand-offs have been
     observed (or `seconds` elapsed); each client then verifies its results.
     Returns per-client dicts."""
@@ -320,7 +320,8 @@ def run_clients(impl, out_dir, n_clients, spec, seconds, tq, extra_env=None, sta
                                           stderr=open(out_dir / f"client{i}.err", "w")))
             time.sleep(start_stagger)
         # release the clients together once each has built its inputs
-        deadline = time.time() + 1800
+        deadline = time.time() + setup_timeout
+        ready = 0
         while time.time() < deadline:
             ready = 0
             for i in range(n_clients):
@@ -330,6 +331,8 @@ def run_clients(impl, out_dir, n_clients, spec, seconds, tq, extra_env=None, sta
             if ready == n_clients or any(p.poll() is not None for p in procs):
                 break
             time.sleep(0.2)
+        if ready < n_clients and all(p.poll() is None for p in procs):
+            raise RuntimeError(f"only {ready} of {n_clients} clients had built their inputs after {setup_timeout} s")
         barrier.write_text("go")
         t_go = time.time()
         while any(p.poll() is None for p in procs) and time.time() - t_go < seconds + 60:

@@ -477,3 +477,47 @@ def test_best_effort_eviction_never_waits_for_backing_space(fake, tmp_path):
         e.free(p)
     finally:
         e.close()
+
+
+def test_allocation_by_the_lock_holder_stops_waiting_when_the_lock_goes(fake, tmp_path):
+    """r2 call 5: the quantum ended while the holder's cuMemAlloc was waiting for HBM the other client still
+    had; the allocation kept the engine's entry lock for oom_wait_ms (120 s), the hand-off's eviction queued
+    behind it, and the daemon rightly ignored pressure from a client that no longer held the lock.  Now the
+    wait ends with the lock: what is mapped stays, the rest is virtual until the next fetch."""
+    ledger = tmp_path / "ledger"
+    code = textwrap.dedent(f"""
+        import ctypes as C, sys, threading, time
+        sys.path.insert(0, {str(ROOT)!r})
+        fake = C.CDLL({str(FAKE_DIR / 'libcuda.so.1')!r}, mode=C.RTLD_GLOBAL)
+        fake.cuInit(0); ctx = C.c_void_p(); fake.cuDevicePrimaryCtxRetain(C.byref(ctx), 0); fake.cuCtxSetCurrent(ctx)
+        from nvshare_b200 import engine as E
+        MiB = 1 << 20
+        e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, oom_wait_ms=60000, prepin=0, preclean=0)
+        hog = C.c_uint64()
+        assert fake.cuMemAlloc_v2(C.byref(hog), C.c_size_t(40 * MiB)) == 0      # "the other client": 40 of 64 MiB
+        e.set_resident_mode(True)                                              # we hold the lock
+        out = {{}}
+        def alloc():
+            fake.cuCtxSetCurrent(ctx)
+            t0 = time.time(); out["p"] = e.alloc(48 * MiB); out["s"] = time.time() - t0
+        th = threading.Thread(target=alloc); th.start()
+        time.sleep(0.5)
+        assert th.is_alive()                                                   # waiting for HBM
+        t0 = time.time()
+        e.set_resident_mode(False)                                             # DROP_LOCK: the quantum is over
+        th.join(10)
+        assert not th.is_alive() and time.time() - t0 < 2.0, "the allocation kept waiting without the lock"
+        st = e.stats()
+        print("RESIDENT", st["resident_bytes"] // MiB, "UNBACKED", st["unbacked_bytes"] // MiB, flush=True)
+        t0 = time.time(); e.evict(0); print("EVICT_S %.2f" % (time.time() - t0), flush=True)   # the hand-off's eviction is not stuck
+        assert fake.cuMemFree_v2(hog) == 0
+        e.fetch_all(); e.pattern_fill(out["p"], 48 * MiB // 8, seed=1)
+        print("BAD", e.pattern_verify(out["p"], 48 * MiB // 8, seed=1), flush=True)
+        e.free(out["p"]); e.close()
+    """)
+    env = dict(__import__("os").environ, FAKE_CUDA_TOTAL_MIB="64", FAKE_CUDA_LEDGER=str(ledger))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "BAD 0" in r.stdout, r.stdout + r.stderr
+    res, unb = (int(x) for x in r.stdout.split("RESIDENT")[1].split()[0:3:2])
+    assert res + unb == 48 and 0 < res <= 24 and unb >= 24, r.stdout          # part mapped, the rest virtual
+    assert float(r.stdout.split("EVICT_S")[1].split()[0]) < 2.0
