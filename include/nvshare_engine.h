@@ -226,6 +226,11 @@ int nvs_evict_best_effort(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *re
 
 int nvs_get_stats(nvs_engine *e, nvs_stats *out);
 
+/* Is dptr the start of an allocation this engine handed out (small pass-through ones included)?
+ * 0 = yes (and *req_bytes = the size that was asked for), NVS_E_NOT_OURS = no.  For callers that must
+ * decide who frees a pointer before they do anything else with it (cuMemFreeAsync). */
+int nvs_lookup(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes);
+
 /* The application is about to write [dptr, dptr+bytes) from the host side of the API (a
  * cuMemcpy* / cuMemset* destination seen by the hook).  Only a hint: chunks touched recently
  * are the last to be chosen by a partial eviction (they are the ones most likely to differ

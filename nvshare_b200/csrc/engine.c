@@ -3144,6 +3144,18 @@ out:
 	return rc;
 }
 
+int nvs_lookup(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes)
+{
+	if (!e)
+		return NVS_E_BAD_ARG;
+	pthread_mutex_lock(&e->mu);
+	struct alloc *a = table_find(e, dptr);
+	if (a && req_bytes)
+		*req_bytes = a->req_bytes;
+	pthread_mutex_unlock(&e->mu);
+	return a ? 0 : NVS_E_NOT_OURS;
+}
+
 int nvs_touch(nvs_engine *e, uint64_t dptr, uint64_t bytes)
 {
 	if (!e || bytes == 0)

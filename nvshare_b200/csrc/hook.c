@@ -880,7 +880,7 @@ static CUresult free_async(int flavour, CUdeviceptr dptr, CUstream s)
 	for (struct uvm_alloc *a = uvm_buckets[(unsigned)((dptr >> 9) * 2654435761u) >> 24]; a && !ours; a = a->next)
 		ours = a->ptr == dptr;
 	pthread_mutex_unlock(&acct_mu);
-	if (!ours && e && nvs_touch(e, (uint64_t)dptr, 1) != NVS_E_NOT_OURS)
+	if (!ours && e && nvs_lookup(e, (uint64_t)dptr, NULL) == 0)
 		ours = 1;
 	if (!ours) {
 		if (real_cuMemFreeAsync[flavour] || real_cuMemFreeAsync[0])
