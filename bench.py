@@ -488,7 +488,8 @@ def roofline_objects(exp, probe, world):
             "frac": d["scan_GBps"] / hbm_pk if d.get("scan_GBps") else None, "peak_source": hbm_src,
             "algorithmic_bytes_total": d.get("bytes_scanned"),
             "note": "bytes the scan/hash launches of the timed evictions read / their CUDA-event time; alone on an idle GPU: "
-                    "see roofline_kernels.scan_hash"}
+                    "see roofline_kernels.scan_hash.  The peak is the measured COPY figure (read + write traffic of b.copy_(a)); "
+                    "a read-only pass has no write turn-arounds and can exceed it (frac > 1)"}
     t = traffic.get("nvs_slab_scan")
     per_launch = d["bytes_scanned"] / d["scan_launches"] if d.get("scan_launches") else None
     scan["algorithmic_bytes_per_launch"] = per_launch

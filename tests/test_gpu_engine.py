@@ -309,7 +309,7 @@ def test_background_precleaning_with_the_fused_copy_hash_kernel(torch_cuda, arte
                 self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
 
         t = torch.as_tensor(Raw(busy, size // 8), device="cuda")
-        t.zero_()
+        t.copy_(torch.arange(size // 8, device="cuda", dtype=torch.int64))      # position-dependent: nothing same-filled
         e.set_resident_mode(True)
         deadline = time.time() + 20
         while e.stats()["precleaned_bytes_total"] < 2 * size and time.time() < deadline:
@@ -318,13 +318,13 @@ def test_background_precleaning_with_the_fused_copy_hash_kernel(torch_cuda, arte
         assert e.stats()["precleaned_bytes_total"] >= 2 * size
         t.add_(1)
         torch.cuda.synchronize()
-        expect = int(t[0].item())
+        added = int(t[0].item())
         r = e.evict(0)
         assert r["clean_bytes"] >= size and r["bytes"] + r["clean_bytes"] + r["elided_bytes"] == 2 * size   # `quiet` was not copied again
         assert r["bytes"] > 0                                                                            # `busy` had changed
         e.fetch_all()
         assert e.pattern_verify(quiet, size // 8, first_index=3, seed=8) == 0
-        assert bool((t == expect).all().item())
+        assert bool((t == torch.arange(size // 8, device="cuda", dtype=torch.int64) + added).all().item())
         del t
         e.free(quiet); e.free(busy)
 
