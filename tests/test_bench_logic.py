@@ -5,6 +5,7 @@ from __future__ import annotations
 import importlib.util
 import math
 import types
+from pathlib import Path
 
 from nvs_testlib import ROOT
 
@@ -98,3 +99,32 @@ def test_algorithmic_bytes_are_independent_of_the_number_of_clients():
     # what must come in per hand-off: the arriving client's footprint minus the HBM the holder leaves free
     f = 0.75 * HBM
     assert abs(max(min(f, 2 * f - HBM), 0) - 0.5 * HBM) < 1
+
+
+def test_sub_runs_live_inside_the_time_budget(monkeypatch):
+    """The driver gives every `bench.py --gpus N` run a fixed time; the sub-runs (same-scale pair, configs #4/#5)
+    only get what the headline left, and say so when they were skipped."""
+    b = load_bench()
+    calls = []
+
+    def fake_run(impl, kind, *a, **kw):
+        calls.append((kind, kw.get("time_limit_s")))
+        return {"kind": kind, "impl": impl, "verified": True, "spec": {}}
+    monkeypatch.setattr(b, "run_experiment", fake_run)
+    monkeypatch.setattr(b, "pick_fraction", lambda impl, *a, **k: (0.6, "note") if impl == "reference" else (1.0, None))
+    a = types.SimpleNamespace(kind="add", pattern="pos", clients=2, oversub=1.5, tq=10, warmup=5, steps=20)
+    # plenty of time: N=1 runs the same-scale pair, N=2 config #4, N=8 config #5, N=4 nothing
+    for world, want in ((1, ["add"]), (2, ["resnet"]), (8, ["llama"]), (4, [])):
+        calls.clear()
+        line = {}
+        b.extras(a, line, {}, world, HBM, 1.0, Path("/tmp/x"), b.time.time())
+        assert [k for k, _ in calls] == want
+        assert all(0 < lim <= b.TOTAL_BUDGET_S for _, lim in calls)
+    # the headline used the budget up: nothing is started, and the line says why
+    calls.clear()
+    line = {}
+    b.extras(a, line, {}, 2, HBM, 1.0, Path("/tmp/x"), b.time.time() - (b.TOTAL_BUDGET_S - 100))
+    assert calls == [] and "skipped" in line["configs"]["config4_resnet50_train_x2_2xHBM_peer_tier"]
+    line = {}
+    b.extras(a, line, {}, 1, HBM, 1.0, Path("/tmp/x"), b.time.time() - (b.TOTAL_BUDGET_S - 100))
+    assert calls == [] and "skipped" in line["same_scale"]
