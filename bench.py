@@ -188,17 +188,20 @@ def probe_main():
     free_b, total_b = torch.cuda.mem_get_info()
     out = {"hbm_free": free_b, "hbm_total": total_b, "n_gpus_visible": torch.cuda.device_count(),
            "link": measure_link_peak(torch), "peer": measure_peer_peak(torch)}
-    try:
-        out["kernels"] = measure_kernels(torch)
-    except Exception as ex:          # no engine library: report it, the bench itself will fail loudly later
-        out["kernels_error"] = repr(ex)
+    if os.environ.get("NVS_BENCH_PROBE_KERNELS", "1") == "1":
+        try:
+            out["kernels"] = measure_kernels(torch)
+        except Exception as ex:      # no engine library: report it, the bench itself will fail loudly later
+            out["kernels_error"] = repr(ex)
     print("PROBE " + json.dumps(out), flush=True)
     return 0
 
 
-def run_probes():
-    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--probe"], capture_output=True, text=True, timeout=900,
-                       env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+def run_probes(kernels=True):
+    """kernels=False for the reference arm: nothing of ours is loaded anywhere in that arm, probes included."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["NVS_BENCH_PROBE_KERNELS"] = "1" if kernels else "0"
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--probe"], capture_output=True, text=True, timeout=900, env=env)
     for line in r.stdout.splitlines():
         if line.startswith("PROBE "):
             return json.loads(line[6:])
@@ -585,7 +588,7 @@ def run_rank0(args, world):
                 "the reference arm runs the reference's own two workloads (add, matmul)"}, 0.0
 
     ncpu = os.cpu_count()
-    probe = run_probes()
+    probe = run_probes(kernels=args.impl == "ours")
     total_b = probe["hbm_total"]
     cpu = cpu_baseline() if (args.impl == "ours" and world == 1) or args.impl == "reference" else None
 
