@@ -3363,7 +3363,7 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 		{ free(e); return NVS_E_BAD_ARG; }
 	else
 		nvs_engine_default_config(&e->cfg);
-	if (getenv("NVSHARE_DEBUG"))
+	if (getenv("NVSHARE_DEBUG") && !nvs_debug_enabled) /* (inside the interposer hook.c has set it already: no store under the other threads' reads) */
 		nvs_debug_enabled = 1;
 
 	/* sanity of geometry */

@@ -380,7 +380,7 @@ static struct nvs_client_driver client_drv;
 
 static void mark_exiting(void)
 {
-	nvs_process_exiting = 1;
+	__atomic_store_n(&nvs_process_exiting, 1, __ATOMIC_RELAXED);
 }
 
 static void bootstrap(void)
@@ -461,7 +461,7 @@ static void bootstrap(void)
 
 static int dp_fetch_all(void)
 {
-	if (nvs_process_exiting)
+	if (NVS_EXITING())
 		return 0;
 	pthread_mutex_lock(&engine_mu);
 	nvs_engine *e = engine;
@@ -470,7 +470,7 @@ static int dp_fetch_all(void)
 		return 0;
 	nvs_xfer_report rep;
 	int rc = nvs_fetch_all(e, &rep);
-	if (rc == NVS_E_SHUTDOWN || nvs_process_exiting)
+	if (rc == NVS_E_SHUTDOWN || NVS_EXITING())
 		return 0; /* the application is exiting: nothing left to keep consistent */
 	if (rc != 0)
 		nvs_warn("fetch failed: %s", nvs_strerror(rc));
@@ -483,7 +483,7 @@ static int dp_evict_best_effort(uint64_t min_bytes) { return dp_evict_impl(min_b
 
 static int dp_evict_impl(uint64_t min_bytes, int best_effort)
 {
-	if (nvs_process_exiting)
+	if (NVS_EXITING())
 		return 0;
 	pthread_mutex_lock(&engine_mu);
 	nvs_engine *e = engine;
@@ -492,7 +492,7 @@ static int dp_evict_impl(uint64_t min_bytes, int best_effort)
 		return 0;
 	nvs_xfer_report rep;
 	int rc = best_effort ? nvs_evict_best_effort(e, min_bytes, &rep) : nvs_evict(e, min_bytes, &rep);
-	if (rc == NVS_E_SHUTDOWN || nvs_process_exiting)
+	if (rc == NVS_E_SHUTDOWN || NVS_EXITING())
 		return 0;
 	if (rc != 0)
 		nvs_warn("evict failed: %s", nvs_strerror(rc));
@@ -501,7 +501,7 @@ static int dp_evict_impl(uint64_t min_bytes, int best_effort)
 
 static void dp_evict_announce(void)
 {
-	if (nvs_process_exiting)
+	if (NVS_EXITING())
 		return;
 	pthread_mutex_lock(&engine_mu);
 	nvs_engine *e = engine;
@@ -546,7 +546,7 @@ static void on_engine_pressure(void *user, uint64_t bytes)
 static void dp_lock_state(int v)
 {
 	pthread_mutex_lock(&engine_mu);
-	holds_lock = v;
+	__atomic_store_n(&holds_lock, v, __ATOMIC_RELAXED); /* host_io_bypass() reads it without the mutex */
 	if (engine)
 		nvs_set_resident_mode(engine, v);
 	pthread_mutex_unlock(&engine_mu);
@@ -1002,5 +1002,7 @@ EXPORT void *nvs_dlsym_234(void *handle, const char *symbol)
 	return hooked_dlsym(1, handle, symbol);
 }
 
+#ifndef NVS_NO_DLSYM_EXPORT /* ThreadSanitizer builds (tools/sanitize.sh tsan): its start-up cannot live with an interposed dlsym */
 __asm__(".symver nvs_dlsym_225, dlsym@@GLIBC_2.2.5");
 __asm__(".symver nvs_dlsym_234, dlsym@GLIBC_2.34");
+#endif

@@ -17,6 +17,7 @@
 extern int nvs_debug_enabled __attribute__((visibility("hidden")));
 /* set once the host process has entered exit(): library threads must not call exit() again */
 extern volatile int nvs_process_exiting __attribute__((visibility("hidden")));
+#define NVS_EXITING() __atomic_load_n(&nvs_process_exiting, __ATOMIC_RELAXED)
 
 #define nvs_log_at(level, ...)                               \
 	do {                                                 \
@@ -35,7 +36,7 @@ extern volatile int nvs_process_exiting __attribute__((visibility("hidden")));
 #define nvs_fatal(...)                                       \
 	do {                                                 \
 		nvs_log_at("FATAL", __VA_ARGS__);            \
-		if (nvs_process_exiting)                     \
+		if (NVS_EXITING())                           \
 			_exit(1);                            \
 		exit(1);                                     \
 	} while (0)
