@@ -6,6 +6,7 @@ driver's "HBM" is host-addressable while mapped)."""
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 import pytest
@@ -44,6 +45,7 @@ ops = st.lists(
         st.tuples(st.just("cold"), st.integers(1, 9), st.integers(0, 255)),     # allocate + load without the GPU
         st.tuples(st.just("hio_w"), st.integers(0, 7), st.integers(0, 10**6)),  # host -> swapped-out range
         st.tuples(st.just("hio_r"), st.integers(0, 7), st.integers(0, 10**6)),  # swapped-out range -> host
+        st.tuples(st.just("idle"), st.integers(1, 6), st.just(0)),              # the owner computes: the pre-cleaner gets a few ms
     ),
     min_size=4, max_size=28)
 
@@ -135,6 +137,10 @@ def _run_model(fake, script, elide, chunk_slabs, **engine_kw):
                 assert rc in (0, -9)
                 if resident:
                     assert rc == -9                                     # never served while the data is in HBM
+            elif op == "idle":
+                if resident:
+                    e.set_resident_mode(True)                           # what a lock grant does: wakes the pre-cleaner
+                time.sleep(a * 1e-3)                                    # (the next op may well find it in mid-copy)
             elif op == "free" and order:
                 p = order.pop(a % len(order))
                 e.free(p)
