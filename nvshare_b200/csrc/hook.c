@@ -764,7 +764,8 @@ CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize)
 		warn_if_error(r, "cuMemGetInfo_v2");
 		cap_known = 1;
 	}
-	if (sum_allocated + bytesize > cap_bytes) {
+	/* (the reference's `sum_allocated + bytesize > cap`, src/hook.c:662, without the wrap-around of a huge request) */
+	if (sum_allocated > cap_bytes || bytesize > cap_bytes - sum_allocated) {
 		if (!single_oversub) {
 			pthread_mutex_unlock(&acct_mu);
 			return CUDA_ERROR_OUT_OF_MEMORY;
@@ -772,6 +773,7 @@ CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize)
 		nvs_warn("Memory allocations exceeded physical GPU memory capacity. This can cause extreme"
 			 " performance degradation!");
 	}
+	sum_allocated += bytesize; /* reserved at the check: two threads cannot both pass it on the same room */
 	pthread_mutex_unlock(&acct_mu);
 
 	nvs_debug("cuMemAlloc requested %zu bytes", bytesize);
@@ -795,14 +797,15 @@ CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize)
 		if (r == CUDA_SUCCESS)
 			nvs_warn("allocation made without a current context is not swappable");
 	}
+	pthread_mutex_lock(&acct_mu);
 	if (r == CUDA_SUCCESS) {
-		pthread_mutex_lock(&acct_mu);
-		sum_allocated += bytesize;
 		if (uvm_mode || !e)
 			uvm_insert(*dptr, bytesize);
 		nvs_debug("Total allocated memory on GPU is %.2f MiB", sum_allocated / 1048576.0);
-		pthread_mutex_unlock(&acct_mu);
+	} else {
+		sum_allocated -= bytesize;
 	}
+	pthread_mutex_unlock(&acct_mu);
 	return r;
 }
 
@@ -886,6 +889,16 @@ static CUresult free_async(int flavour, CUdeviceptr dptr, CUstream s)
 		if (real_cuMemFreeAsync[flavour] || real_cuMemFreeAsync[0])
 			return (real_cuMemFreeAsync[flavour] ? real_cuMemFreeAsync[flavour] : real_cuMemFreeAsync[0])(dptr, s);
 		return CUDA_ERROR_INVALID_VALUE;
+	}
+	if (s && real_cuStreamIsCapturing) {
+		/* Inside a capture the driver would record a free NODE; memory of ours cannot be released by a
+		 * graph, and synchronising the stream would invalidate the capture.  Refuse, loudly, and leave
+		 * the capture intact: the memory stays allocated until cuMemFree. */
+		int capturing = 0;
+		if (real_cuStreamIsCapturing(s, &capturing) == CUDA_SUCCESS && capturing != 0) {
+			nvs_warn("cuMemFreeAsync inside a stream capture is not supported for swappable memory; free it outside the capture");
+			return CUDA_ERROR_NOT_SUPPORTED;
+		}
 	}
 	CUresult (*sync)(CUstream) = real_cuStreamSynchronize[flavour] ? real_cuStreamSynchronize[flavour] : real_cuStreamSynchronize[0];
 	CUresult r = sync ? sync(s) : real_cuCtxSynchronize();

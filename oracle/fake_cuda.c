@@ -196,7 +196,15 @@ CUresult cuCtxPopCurrent_v2(CUcontext *ctx)
 	return OK;
 }
 CUresult cuCtxGetDevice(CUdevice *d) { *d = 0; return OK; }
-CUresult cuCtxSynchronize(void) { trace("cuCtxSynchronize"); return OK; }
+static CUresult sync_during_capture(const char *what);
+CUresult cuCtxSynchronize(void)
+{
+	CUresult r = sync_during_capture("cuCtxSynchronize");
+	if (r)
+		return r;
+	trace("cuCtxSynchronize");
+	return OK;
+}
 CUresult cuGetErrorString(CUresult e, const char **s) { *s = e == 0 ? "no error" : e == 2 ? "out of memory" : "fake error"; return OK; }
 CUresult cuGetErrorName(CUresult e, const char **s) { *s = e == 0 ? "CUDA_SUCCESS" : e == 2 ? "CUDA_ERROR_OUT_OF_MEMORY" : "CUDA_ERROR_FAKE"; return OK; }
 
@@ -546,9 +554,56 @@ CUresult cuMemsetD32_v2(CUdeviceptr p, unsigned v, size_t n) { trace("cuMemsetD3
 
 /* ------------------------------------------------- streams / events ------ */
 
-CUresult cuStreamCreate(CUstream *s, unsigned f) { (void)f; *s = malloc(8); return OK; }
-CUresult cuStreamDestroy_v2(CUstream s) { free(s); return OK; }
-CUresult cuStreamSynchronize(CUstream s) { (void)s; return OK; }
+/* Stream capture, as far as an interposer can tell: a capturing stream records nodes instead of doing
+ * work, and a synchronisation while a capture is active is an illegal call that invalidates the capture
+ * (CUDA_ERROR_STREAM_CAPTURE_UNSUPPORTED now, ..._INVALIDATED when the capture is ended). */
+struct fake_stream { int capture; /* 0 none, 1 active, 2 invalidated */ int pad; };
+static struct fake_stream *g_capturing; /* one capture at a time is all the tests need */
+CUresult cuStreamCreate(CUstream *s, unsigned f) { (void)f; *s = calloc(1, sizeof(struct fake_stream)); return OK; }
+CUresult cuStreamDestroy_v2(CUstream s) { if ((struct fake_stream *)s == g_capturing) g_capturing = NULL; free(s); return OK; }
+CUresult cuStreamBeginCapture_v2(CUstream s, int mode)
+{
+	(void)mode;
+	if (!s || g_capturing)
+		return E_INVALID;
+	g_capturing = s;
+	g_capturing->capture = 1;
+	trace("cuStreamBeginCapture");
+	return OK;
+}
+CUresult cuStreamIsCapturing(CUstream s, int *status)
+{
+	*status = s ? ((struct fake_stream *)s)->capture : 0;
+	return OK;
+}
+CUresult cuStreamEndCapture(CUstream s, void **graph)
+{
+	struct fake_stream *fs = s;
+	if (!fs || fs != g_capturing)
+		return E_INVALID;
+	const int was = fs->capture;
+	fs->capture = 0;
+	g_capturing = NULL;
+	if (graph)
+		*graph = was == 1 ? (void *)fs : NULL;
+	trace("cuStreamEndCapture -> %d", was == 1 ? 0 : 901);
+	return was == 1 ? OK : 901;
+}
+static CUresult sync_during_capture(const char *what)
+{
+	if (!g_capturing || g_capturing->capture == 0)
+		return OK;
+	g_capturing->capture = 2;
+	trace("%s during capture -> 900", what);
+	return 900;
+}
+CUresult cuStreamSynchronize(CUstream s)
+{
+	struct fake_stream *fs = s;
+	if (fs && fs->capture)
+		return sync_during_capture("cuStreamSynchronize");
+	return OK;
+}
 struct fake_event { struct timespec ts; };
 CUresult cuEventCreate(CUevent *e, unsigned f) { (void)f; *e = calloc(1, sizeof(struct fake_event)); return OK; }
 CUresult cuEventDestroy_v2(CUevent e) { free(e); return OK; }

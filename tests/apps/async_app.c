@@ -4,7 +4,7 @@
  * (cuMemAllocPitch).  CPU test-suite (fake driver) and real GPU alike; knows nothing about nvshare.
  *
  * usage: async_app <MiB per buffer> <seconds> <seed> [cap-probe GiB]
- * Prints "CAP rc=<r>" for an allocation of <cap-probe GiB> (0 = skip) and
+ * Prints "CAP rc=<r>" for an allocation of <cap-probe GiB> (0 = skip), "WRAP rc=<r>" for one of 2^64 - 1 MiB, and
  * "RESULT PASS|FAIL iters=<n> mismatches=<m>".
  */
 #include <stdint.h>
@@ -61,6 +61,11 @@ int main(int argc, char **argv)
 		CUdeviceptr big = 0;
 		CUresult r = cuMemAllocAsync(&big, cap_gib << 30, st);
 		printf("CAP rc=%d\n", r);
+		if (r == 0)
+			cuMemFreeAsync(big, st);
+		/* a request so large that "allocated so far + request" wraps around must not slip under the cap */
+		r = cuMemAllocAsync(&big, (size_t)0 - ((size_t)1 << 20), st);
+		printf("WRAP rc=%d\n", r);
 		if (r == 0)
 			cuMemFreeAsync(big, st);
 	}

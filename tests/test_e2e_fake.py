@@ -285,7 +285,41 @@ def test_stream_ordered_and_pitched_allocations_are_capped_and_swapped(artefacts
     for i, (p, (out, err)) in enumerate(zip(procs, outs), 1):
         assert p.returncode == 0 and "RESULT PASS" in out, out + err[-2000:]
         assert "CAP rc=2" in out                       # 3 GiB > 4096 - 1536 MiB: CUDA_ERROR_OUT_OF_MEMORY, like cuMemAlloc
+        assert "WRAP rc=2" in out                      # sum + request wraps around 2^64: still refused
         trace = (tmp_path / f"trace{i}.txt").read_text()
         assert "cuMemAllocAsync" not in trace and "cuMemAllocPitch" not in trace and "cuMemCreate" in trace
         ops = [json.loads(l)["op"] for l in (tmp_path / f"stats{i}.jsonl").read_text().splitlines()]
         assert "evict" in ops and "fetch" in ops       # and it is swapped like any other memory
+
+
+def _capture_run(impl, sd, tmp_path):
+    d = Daemon(impl, sd)
+    try:
+        env = fake_env(total_mib=4096, trace=tmp_path / f"trace_{impl}.txt",
+                       extra={"NVSHARE_HOST_ARENA_MIB": 64, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_SOCK_DIR": sd})
+        env["LD_PRELOAD"] = preload(impl)
+        r = subprocess.run([str(ORACLE / "capture_app"), "5000"], env=env, capture_output=True, text=True, timeout=120)
+        return r.returncode, r.stdout, r.stderr, (tmp_path / f"trace_{impl}.txt").read_text()
+    finally:
+        d.stop()
+
+
+def test_stream_capture_survives_the_sync_window(artefacts, sock_dir, tmp_path):
+    """SURVEY 8f rank 2 / DESIGN 8: a launch into a capturing stream records a graph node; synchronising then is an
+    illegal call that invalidates the capture.  5000 captured launches (more than any sync window) leave the capture
+    intact, and a stream-ordered free of swappable memory inside it is refused (801) without harming it."""
+    rc, out, err, trace = _capture_run("ours", sock_dir, tmp_path)
+    assert rc == 0 and "RESULT PASS" in out, out + err[-2000:]
+    assert "FREE_IN_CAPTURE rc=801" in out and "END_CAPTURE rc=0" in out and "FREE_AFTER rc=0" in out
+    assert "during capture" not in trace
+
+
+@pytest.mark.reference
+def test_stream_capture_breaks_under_the_reference_library(artefacts, default_sock_lock, tmp_path):
+    """The documented difference: the reference synchronises every `window` launches regardless of capture
+    (src/hook.c:808), which invalidates the capture of the same application."""
+    rc, out, err, trace = _capture_run("reference", default_sock_lock, tmp_path)
+    # its cuLaunchKernel hook hands the failed synchronisation back to the application (or, had the application
+    # ignored that, the capture would have ended as invalidated)
+    assert rc != 0 and ("cuLaunchKernel" in out and "-> 900" in out or "END_CAPTURE rc=901" in out), out + err[-2000:]
+    assert "cuCtxSynchronize during capture" in trace
