@@ -468,10 +468,11 @@ def run_experiment(impl, kind, pattern, clients, oversub, tq, warmup, steps, tot
             "retained_bytes_last": max([r.get("retained_bytes", 0) for r in recs] or [0]),
             "pool_used_max": max([r.get("pool_used", 0) for r in recs] or [0]),
         }
-        if algo_bytes_dir > 0 and steps:
+        if algo_bytes_dir > 0 and fe and ev:
+            # per transfer that completed inside the window (the window may hold one more of them than timed steps)
             res["device"]["link_bytes_over_algorithmic"] = {
-                "in": res["device"]["bytes_fetched"] / steps / algo_bytes_dir,
-                "out": res["device"]["bytes_evicted"] / steps / algo_bytes_dir}
+                "in": res["device"]["bytes_fetched"] / len(fe) / algo_bytes_dir,
+                "out": res["device"]["bytes_evicted"] / len(ev) / algo_bytes_dir}
         pins = [r for r in harness.engine_records(paths, 0, 1e18) if r["op"] == "pin"]
         if pins:        # where the pinned pool's pages ended up (engine.c numa_init): the last report covers the whole pool
             last = max(pins, key=lambda r: r["t"])
