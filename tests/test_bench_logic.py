@@ -128,3 +128,26 @@ def test_sub_runs_live_inside_the_time_budget(monkeypatch):
     line = {}
     b.extras(a, line, {}, 1, HBM, 1.0, Path("/tmp/x"), b.time.time() - (b.TOTAL_BUDGET_S - 100))
     assert calls == [] and "skipped" in line["same_scale"]
+
+
+def test_reference_arm_probes_load_nothing_of_ours(monkeypatch):
+    """`bench.py --impl reference` must not touch our kernels or engine anywhere, its probe child included."""
+    b = load_bench()
+    seen = {}
+
+    def fake_run(cmd, **kw):
+        seen["env"] = kw["env"]
+        return types.SimpleNamespace(returncode=0, stdout='PROBE {"hbm_total": 1, "link": {"h2d": 1, "d2h": 1}}\n', stderr="")
+    monkeypatch.setattr(b.subprocess, "run", fake_run)
+    try:
+        b.run_probes(kernels=False)
+    except Exception:
+        pass                      # the reply format is not what is being tested
+    assert seen["env"]["NVS_BENCH_PROBE_KERNELS"] == "0"
+    try:
+        b.run_probes()
+    except Exception:
+        pass
+    assert seen["env"]["NVS_BENCH_PROBE_KERNELS"] == "1"
+    src = (ROOT / "bench.py").read_text()
+    assert 'run_probes(kernels=args.impl == "ours")' in src
