@@ -257,7 +257,7 @@ struct arena {
 #define SHP_MAGIC 0x6e767368504f4f4cull /* "nvshPOOL" */
 #define SHP_HDR_BYTES (8ull << 20)
 #define SHP_MAX_SLABS (1u << 19) /* 1 TiB */
-#define SHP_VERSION 2
+#define SHP_VERSION 3
 
 struct shp_hdr {
 	volatile uint64_t magic;
@@ -278,6 +278,10 @@ struct shp_hdr {
 	volatile int32_t releaser_pid;       /* 0: nobody is releasing                           */
 	volatile uint32_t release_seq;       /* bumped at every announcement                     */
 	volatile uint64_t released_bytes;    /* since the announcement                           */
+	/* Owners are identified by pid and their liveness is checked with kill(pid, 0): that only means
+	 * something inside ONE pid namespace.  Clients of another one (containers that share /dev/shm
+	 * but not the pid namespace) must not attach -- they would reap the units of live owners. */
+	uint64_t pid_ns;                     /* inode of the creator's /proc/self/ns/pid, 0 = unknown */
 };
 enum { RS_NONE = 0, RS_PLAIN = 1, RS_STABLE = 2 }; /* reclaim order: free, then PLAIN, then STABLE */
 _Static_assert(sizeof(struct shp_hdr) <= SHP_HDR_BYTES, "shared pool header too large");
@@ -1399,6 +1403,12 @@ static uint64_t host_memory_room(void)
 	return room;
 }
 
+static uint64_t my_pid_ns(void)
+{
+	struct stat st;
+	return stat("/proc/self/ns/pid", &st) == 0 ? (uint64_t)st.st_ino : 0;
+}
+
 /* Open (or create) the pool file.  Returns 0, or -1 to fall back to a private pool. */
 static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
 {
@@ -1494,6 +1504,7 @@ static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
 		sp->hdr->version = SHP_VERSION;
 		sp->hdr->window_slabs = window_slabs;
 		sp->hdr->capacity_slabs = cap_slabs;
+		sp->hdr->pid_ns = my_pid_ns();
 		__atomic_store_n(&sp->hdr->magic, SHP_MAGIC, __ATOMIC_RELEASE);
 	} else {
 		for (int i = 0; i < 5000 && __atomic_load_n(&sp->hdr->magic, __ATOMIC_ACQUIRE) != SHP_MAGIC; ++i)
@@ -1503,6 +1514,13 @@ static int shp_open(nvs_engine *e, const char *path, uint64_t capacity_bytes)
 		    cap_slabs > SHP_MAX_SLABS || sp->hdr->window_slabs == 0 || cap_slabs % sp->hdr->window_slabs != 0 ||
 		    sp->hdr->used_slabs > cap_slabs || (uint64_t)sp->hdr->window_slabs * SLAB < e->cfg.chunk_bytes) {
 			nvs_warn("engine: shared pool %s is not usable by this client (geometry/version)", path);
+			munmap(m, SHP_HDR_BYTES + cap_slabs * SLAB);
+			sp->hdr = NULL;
+			goto fail;
+		}
+		if (sp->hdr->pid_ns != my_pid_ns()) {
+			nvs_warn("engine: shared pool %s belongs to another pid namespace (its owners' liveness cannot be "
+				 "checked from here): using a private pool", path);
 			munmap(m, SHP_HDR_BYTES + cap_slabs * SLAB);
 			sp->hdr = NULL;
 			goto fail;

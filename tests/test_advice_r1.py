@@ -89,6 +89,46 @@ def test_pool_file_that_is_not_ours_is_refused(artefacts, tmp_path, how):
         assert pool.stat().st_size == 4096                                     # untouched, not unlinked
 
 
+def test_pool_of_another_pid_namespace_is_not_attached(artefacts, tmp_path):
+    """Units are owned by pid and dead owners' units are reaped with kill(pid, 0): that means nothing across pid
+    namespaces (containers sharing /dev/shm), where every live owner would look dead.  Such a client must fall
+    back to a private pool and leave the owner's units alone."""
+    import shutil
+    if not shutil.which("unshare") or subprocess.run(["unshare", "--pid", "--fork", "true"], capture_output=True).returncode != 0:
+        pytest.skip("cannot create a pid namespace here")
+    pool = tmp_path / "pool"
+    owner_code = PRELUDE + textwrap.dedent(f"""
+        e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, shared_pool_path={str(pool)!r},
+                     shared_pool_bytes=256 * MiB, prepin=0, retain=0)
+        p = e.alloc(32 * MiB); e.fetch_all(); e.pattern_fill(p, 32 * MiB // 8, seed=5); e.evict(0)   # 32 MiB live in the pool
+        print("READY", flush=True); sys.stdin.readline()
+        e.fetch_all(); print("BAD", e.pattern_verify(p, 32 * MiB // 8, seed=5), flush=True)
+        e.free(p); e.close()
+    """)
+    guest_code = PRELUDE + textwrap.dedent(f"""
+        e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, shared_pool_path={str(pool)!r},
+                     shared_pool_bytes=256 * MiB, prepin=0, retain=0)
+        p = e.alloc(64 * MiB); e.fetch_all(); e.pattern_fill(p, 64 * MiB // 8, seed=6); e.evict(0)
+        e.fetch_all(); print("BAD", e.pattern_verify(p, 64 * MiB // 8, seed=6))
+        e.free(p); e.close()
+    """)
+    owner = subprocess.Popen([sys.executable, "-c", owner_code], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, text=True)
+    try:
+        assert "READY" in owner.stdout.readline()
+        g = subprocess.run(["unshare", "--pid", "--fork", sys.executable, "-c", guest_code], capture_output=True, text=True, timeout=120)
+        assert g.returncode == 0 and "BAD 0" in g.stdout, g.stdout + g.stderr
+        assert "another pid namespace" in g.stderr and "private pinned pool" in g.stderr
+        # the same program inside the owner's namespace does attach
+        g2 = subprocess.run([sys.executable, "-c", guest_code], capture_output=True, text=True, timeout=120)
+        assert g2.returncode == 0 and "BAD 0" in g2.stdout and "another pid namespace" not in g2.stderr, g2.stdout + g2.stderr
+        out, err = owner.communicate("go\n", timeout=60)
+        assert "BAD 0" in out, out + err                     # the owner's units were not reaped under it
+    finally:
+        if owner.poll() is None:
+            owner.kill()
+
+
 class ScriptedDaemon:
     """Just enough of nvshare-scheduler to drive one real client library by hand."""
 
