@@ -70,7 +70,7 @@ def test_pool_file_that_is_not_ours_is_refused(artefacts, tmp_path, how):
         os.symlink(victim, pool)
     else:
         # right owner and mode, but a header whose geometry does not match the file
-        hdr = struct.pack("<QIIQQ", 0x6e767368504f4f4c, 2, 0, 1 << 40, 0)
+        hdr = struct.pack("<QIIQQ", 0x6e767368504f4f4c, 3, 0, 1 << 40, 0)
         pool.write_bytes(hdr + b"\0" * ((8 << 20) + (64 << 20) - len(hdr)))
         os.chmod(pool, 0o600)
     code = PRELUDE + textwrap.dedent(f"""

@@ -149,7 +149,7 @@ def test_shared_pool_lifecycle(artefacts, sock_dir, tmp_path):
         assert len(mine) == 1                                          # ONE backing file for both clients
         hdr = mine.copy().pop().open("rb").read(32)
         magic, version, window_slabs, capacity, used = struct.unpack("<QIIQQ", hdr)
-        assert magic == 0x6e767368504f4f4c and version == 2 and window_slabs == 32 and capacity == 512
+        assert magic == 0x6e767368504f4f4c and version == 3 and window_slabs == 32 and capacity == 512
         finish(procs)
         res_used = struct.unpack("<QIIQQ", mine.copy().pop().open("rb").read(32))[4]
         assert res_used == 0                                           # everything handed back
