@@ -703,20 +703,25 @@ struct uvm_alloc {
 };
 static struct uvm_alloc *uvm_buckets[256];
 
+static inline unsigned uvm_hash(CUdeviceptr p)
+{
+	return (unsigned)((p >> 9) * 2654435761u) >> 24;
+}
+
 static void uvm_insert(CUdeviceptr p, size_t n)
 {
 	struct uvm_alloc *a = malloc(sizeof(*a));
 	nvs_must(a != NULL);
 	a->ptr = p;
 	a->size = n;
-	unsigned h = (unsigned)((p >> 9) * 2654435761u) >> 24;
+	unsigned h = uvm_hash(p);
 	a->next = uvm_buckets[h];
 	uvm_buckets[h] = a;
 }
 
 static size_t uvm_remove(CUdeviceptr p)
 {
-	unsigned h = (unsigned)((p >> 9) * 2654435761u) >> 24;
+	unsigned h = uvm_hash(p);
 	for (struct uvm_alloc **pp = &uvm_buckets[h]; *pp; pp = &(*pp)->next)
 		if ((*pp)->ptr == p) {
 			struct uvm_alloc *a = *pp;
@@ -880,7 +885,7 @@ static CUresult free_async(int flavour, CUdeviceptr dptr, CUstream s)
 	nvs_engine *e = __atomic_load_n(&engine, __ATOMIC_ACQUIRE);
 	int ours = 0;
 	pthread_mutex_lock(&acct_mu);
-	for (struct uvm_alloc *a = uvm_buckets[(unsigned)((dptr >> 9) * 2654435761u) >> 24]; a && !ours; a = a->next)
+	for (struct uvm_alloc *a = uvm_buckets[uvm_hash(dptr)]; a && !ours; a = a->next)
 		ours = a->ptr == dptr;
 	pthread_mutex_unlock(&acct_mu);
 	if (!ours && e && nvs_lookup(e, (uint64_t)dptr, NULL) == 0)
