@@ -626,7 +626,16 @@ static struct fake_fn g_fns[32];
 static int g_nfns;
 static unsigned long g_launches;
 
-CUresult cuModuleLoadData(CUmodule *m, const void *image) { *m = (void *)image; trace("cuModuleLoadData"); return image ? OK : E_INVALID; }
+CUresult cuModuleLoadData(CUmodule *m, const void *image)
+{
+	if (getenv("FAKE_CUDA_NO_BINARY")) { /* "this GPU is not sm_100a": CUDA_ERROR_NO_BINARY_FOR_GPU */
+		trace("cuModuleLoadData -> 209");
+		return 209;
+	}
+	*m = (void *)image;
+	trace("cuModuleLoadData");
+	return image ? OK : E_INVALID;
+}
 CUresult cuModuleUnload(CUmodule m) { (void)m; return OK; }
 CUresult cuModuleGetFunction(CUfunction *f, CUmodule m, const char *name)
 {

@@ -75,6 +75,15 @@ def test_uvm_mode_two_clients(artefacts, sock_dir, tmp_path):
     assert all("engine:" not in err for _, _, err in results)
 
 
+def test_gpu_without_our_kernel_image_runs_on_managed_memory(artefacts, sock_dir, tmp_path):
+    """only the sm_100a image is embedded; on any other GPU the drop-in must still work.  The engine
+    fails to load its kernels, the library says so and runs the process on the reference's mechanism."""
+    log, results = run_clients("ours", "ours", sock_dir, tmp_path, seconds=3.0, extra={"FAKE_CUDA_NO_BINARY": 1})
+    check(results)
+    for _, _, err in results:
+        assert "swap engine unavailable on this GPU/driver" in err and "managed-memory mechanism" in err
+
+
 @pytest.mark.reference
 def test_our_library_under_reference_daemon(artefacts, default_sock_lock, tmp_path):
     log, results = run_clients("reference", "ours", default_sock_lock, tmp_path, seconds=3.0)
