@@ -397,7 +397,10 @@ def run_experiment(impl, kind, pattern, clients, oversub, tq, warmup, steps, tot
         setup_timeout = 1800
         if time_limit_s:             # a sub-run inside somebody else's time limit: never overrun it
             left = time_limit_s - (time.time() - t0)
-            setup_timeout = max(30.0, 0.6 * left)
+            # the timed part gets what its hand-offs need first (stall allowance: 4 s for add, 7 s for the models),
+            # the clients' setup whatever is left of the limit
+            need = (warmup + steps + 2) * (tq + (4 if kind == "add" else 7)) + 10
+            setup_timeout = max(45.0, left - need - 20)
             seconds = min(seconds, max(20.0, left - setup_timeout - 20))
         sampler = harness.ClockSampler(out_dir / "clocks.csv")
         sampler.start()
@@ -708,7 +711,7 @@ def extras(args, line, probe, world, total_b, frac, out_dir, t_bench_start):
         return TOTAL_BUDGET_S - (time.time() - t_bench_start)
     if world == 1:
         ref_frac, _ = pick_fraction("reference", args.clients, args.oversub, total_b, 0.0, 1)
-        if ref_frac < frac - 0.01 and left() < 170:
+        if ref_frac < frac - 0.01 and left() < 240:
             line["same_scale"] = {"skipped": f"only {left():.0f} s of the run's time budget left"}
         elif ref_frac < frac - 0.01:
             try:
