@@ -125,8 +125,8 @@ static void set_own_lock(int v)
 void nvs_client_pressure(uint64_t mib)
 {
 	char hint[NVS_MSG_DATA_LEN];
-	if (sock_fd < 0)
-		return;
+	if (sock_fd < 0 || !sched_v2)
+		return; /* the reference daemon would take it for a plain lock request (and nobody is lazily resident under it) */
 	snprintf(hint, sizeof(hint), "%c%" PRIu64, NVS_HINT_PRESSURE_PREFIX, mib);
 	send_msg(NVS_REQ_LOCK, hint);
 }

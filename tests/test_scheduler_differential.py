@@ -40,7 +40,7 @@ def run_script(d, seed, n_clients=4, n_ops=60):
 
     next_id = 0
     for step in range(n_ops):
-        op = rng.choice(["connect", "req", "req", "rel", "rel", "close", "off", "on", "tq", "garbage", "unknown",
+        op = rng.choice(["connect", "req", "req", "req_hint", "rel", "rel", "close", "off", "on", "tq", "garbage", "unknown",
                          "req_unreg"])
         if op == "connect" or not clients:
             if len(clients) < n_clients:
@@ -60,6 +60,15 @@ def run_script(d, seed, n_clients=4, n_ops=60):
         c = clients[name]
         if op == "req":
             c.send(REQ_LOCK)
+        elif op == "req_hint":
+            # the `data` bytes of a REQ_LOCK are ours to use (the reference never reads them): whatever they hold
+            # -- a need hint, an absurd one, junk -- the lock protocol itself must not change.  ('p' is excluded: a
+            # pressure message is an extension that is deliberately not a lock request.)
+            junk = rng.choice([b"n123", b"n0", b"n99999999999999999999", b"nabc", b"n-5", b"w3n7", b"x", b"\xff" * 19,
+                               bytes(rng.randrange(1, 256) for _ in range(19))])
+            if junk[:1] in (b"p", b"e"):
+                junk = b"n" + junk[1:]
+            c.send(REQ_LOCK, data=junk)
         elif op == "rel":
             c.send(LOCK_RELEASED)
         elif op == "close":
