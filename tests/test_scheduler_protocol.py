@@ -248,3 +248,76 @@ def test_drop_lock_carries_waiter_hint_ours_only(artefacts, tmp_path):
         assert b.expect(DROP_LOCK, timeout=3)["data"] == b"w0n0"        # nobody waits: the holder may stay resident
     finally:
         d.stop()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_mutual_exclusion_under_random_traffic_with_hints(artefacts, tmp_path, seed):
+    """Our daemon only (the extension frames have no counterpart): random register / request (with need hints) /
+    pressure / release / disconnect traffic with a 1 s quantum running underneath.  Whatever arrives, a LOCK_OK is
+    only ever sent while nobody else has been told it holds the lock, pressure never grants anything, and the daemon
+    survives."""
+    import random
+    rng = random.Random(1000 + seed)
+    sock_dir = tmp_path / "nvs"; sock_dir.mkdir()
+    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
+    clients, holder, grants = {}, None, 0
+    try:
+        d.ctl("-T", "1")
+
+        def drain():
+            nonlocal holder, grants
+            time.sleep(0.02)
+            for name, c in list(clients.items()):
+                while True:
+                    m = c.recv(0.005)
+                    if m is None:
+                        break
+                    if m == b"":
+                        c.close(); del clients[name]
+                        if holder == name:
+                            holder = None
+                        break
+                    if m["type"] == LOCK_OK:
+                        assert holder is None, f"LOCK_OK to {name} while {holder} holds the lock"
+                        holder = name
+                        grants += 1
+                    elif m["type"] == DROP_LOCK and m["data"][:1] != b"e" and holder == name and rng.random() < 0.8:
+                        c.send(LOCK_RELEASED)              # a well-behaved holder gives way at the end of its quantum
+                        holder = None
+
+        for step in range(150):
+            op = rng.choice(["connect", "req", "req", "req", "press", "rel", "close", "wait"])
+            if op == "connect" or not clients:
+                if len(clients) < 5:
+                    name = f"c{step}"
+                    c = MockClient(d.sock_path, name)
+                    c.register()
+                    clients[name] = c
+                drain()
+                continue
+            name = rng.choice(sorted(clients))
+            c = clients[name]
+            if op == "req":
+                c.send(REQ_LOCK, data=b"n%d" % rng.randrange(0, 200000))
+            elif op == "press":
+                c.send(REQ_LOCK, data=b"p%d" % rng.randrange(0, 200000))
+            elif op == "rel":
+                c.send(LOCK_RELEASED)                      # from anybody: only the holder's counts
+                if holder == name:
+                    holder = None
+            elif op == "close":
+                c.close(); del clients[name]
+                if holder == name:
+                    holder = None
+            elif op == "wait":
+                time.sleep(0.15)
+            drain()
+        assert grants >= 5
+        # still alive and sane: a fresh client gets the lock once everybody else is gone
+        for c in clients.values():
+            c.close()
+        time.sleep(0.1)
+        z = MockClient(d.sock_path, "z"); z.register(); z.send(REQ_LOCK, data=b"n1"); z.expect(LOCK_OK, timeout=3)
+        z.close()
+    finally:
+        d.stop()
