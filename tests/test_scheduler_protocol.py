@@ -261,6 +261,7 @@ def test_mutual_exclusion_under_random_traffic_with_hints(artefacts, tmp_path, s
     sock_dir = tmp_path / "nvs"; sock_dir.mkdir()
     d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
     clients, holder, grants = {}, None, 0
+    pending = set()          # clients with a request the daemon may still answer
     try:
         d.ctl("-T", "1")
 
@@ -281,6 +282,7 @@ def test_mutual_exclusion_under_random_traffic_with_hints(artefacts, tmp_path, s
                         assert holder is None, f"LOCK_OK to {name} while {holder} holds the lock"
                         holder = name
                         grants += 1
+                        pending.discard(name)
                     elif m["type"] == DROP_LOCK and m["data"][:1] != b"e" and holder == name and rng.random() < 0.8:
                         c.send(LOCK_RELEASED)              # a well-behaved holder gives way at the end of its quantum
                         holder = None
@@ -299,14 +301,21 @@ def test_mutual_exclusion_under_random_traffic_with_hints(artefacts, tmp_path, s
             c = clients[name]
             if op == "req":
                 c.send(REQ_LOCK, data=b"n%d" % rng.randrange(0, 200000))
+                pending.add(name)
             elif op == "press":
                 c.send(REQ_LOCK, data=b"p%d" % rng.randrange(0, 200000))
             elif op == "rel":
-                c.send(LOCK_RELEASED)                      # from anybody: only the holder's counts
+                # from the holder, or from somebody who is not even asking (ignored by the daemon).  Not from a
+                # waiter: its release could cross a LOCK_OK that is already on its way and give that lock back,
+                # which is legal and which this model could not tell from a violation.
+                if holder != name and name in pending:
+                    continue
+                c.send(LOCK_RELEASED)
                 if holder == name:
                     holder = None
             elif op == "close":
                 c.close(); del clients[name]
+                pending.discard(name)
                 if holder == name:
                     holder = None
             elif op == "wait":
