@@ -558,7 +558,8 @@ def main():
         import torch
         import torch.distributed as dist
         import datetime
-        torch.cuda.set_device(local)
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world,
                                 timeout=datetime.timedelta(minutes=60))
         # create the communicator now, while GPU 0 is still empty; the data-path work then runs on rank 0

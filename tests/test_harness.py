@@ -119,3 +119,32 @@ def test_world_size_2_gloo_reduction(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1 and '"max_s": 3.5' in lines[0] and '"n_gpus": 2' in lines[0]
+
+
+@pytest.mark.parametrize("impl", ["ours", "reference"])
+def test_bench_main_under_torchrun_world_size_2(tmp_path, impl):
+    """The real bench.py main() as the driver launches it for N = 2 (gloo here, no GPU): rank 0 alone does the
+    data-path work and prints ONE line, rank 1 takes part in the barriers and the MAX reduction (our arm) or exits
+    at once (reference arm: no process group at all), both exit 0."""
+    code = textwrap.dedent(f"""
+        import importlib.util, os, sys
+        spec = importlib.util.spec_from_file_location("bench_module", {str(ROOT / "bench.py")!r})
+        b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+        def fake_rank0(args, world):
+            assert int(os.environ["RANK"]) == 0, "only rank 0 may do data-path work"
+            return {{"impl": args.impl, "n_gpus": world, "steps": args.steps, "verified": True, "value": 1.0}}, 2.5
+        b.run_rank0 = fake_rank0
+        sys.argv = ["bench.py", "--gpus", "2", "--steps", "3", "--warmup", "3", "--impl", {impl!r}]
+        rc = b.main()
+        print("RANK", os.environ["RANK"], "rc", rc, flush=True)
+        sys.exit(rc)
+    """)
+    script = tmp_path / "w2bench.py"
+    script.write_text(code)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617" if impl == "ours" else "29619", str(script)],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and '"n_gpus": 2' in lines[0] and f'"impl": "{impl}"' in lines[0]
+    assert "RANK 0 rc 0" in r.stdout and "RANK 1 rc 0" in r.stdout
