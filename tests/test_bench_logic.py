@@ -151,3 +151,59 @@ def test_reference_arm_probes_load_nothing_of_ours(monkeypatch):
     assert seen["env"]["NVS_BENCH_PROBE_KERNELS"] == "1"
     src = (ROOT / "bench.py").read_text()
     assert 'run_probes(kernels=args.impl == "ours")' in src
+
+
+def test_run_experiment_post_processing_on_synthetic_records(tmp_path, monkeypatch):
+    """Everything bench.py does around a run -- the time-limit split of a sub-run, the analysis, the `device` record
+    from the engines' stats lines, the roofline objects -- executed on CPU over synthetic client timelines and
+    engine records (the clients themselves need a GPU)."""
+    import json
+    b = load_bench()
+    tq, stall, tau = 1.0, 0.4, 0.02
+    t, who, iters, recs = 1000.0, 0, {0: [], 1: []}, {0: [], 1: []}
+    for _ in range(12):                                    # 12 quanta = 11 hand-offs
+        t += stall
+        recs[who].append({"op": "fetch", "t": t, "bytes": 50 << 30, "copy_ms": 900.0, "host_bytes": 50 << 30, "peer_bytes": 0,
+                          "launches": 0, "ce_calls": 200, "map_ms": 60.0, "wait_ms": 150.0, "wall_ms": 1100.0, "elided_bytes": 0,
+                          "retained_bytes": 40 << 30, "pool_used": 90 << 30})
+        end = t + tq
+        while t < end:
+            t += tau
+            iters[who].append(t)
+        recs[who].append({"op": "evict", "t": t + 0.3, "bytes": 5 << 30, "copy_ms": 100.0, "host_bytes": 5 << 30, "peer_bytes": 0,
+                          "launches": 3, "scan_launches": 2, "ce_calls": 20, "map_ms": 90.0, "wait_ms": 0.0, "wall_ms": 400.0,
+                          "scanned_bytes": 140 << 30, "scan_ms": 24.0, "clean_bytes": 45 << 30, "elided_bytes": 0,
+                          "retained_bytes": 40 << 30, "pool_used": 90 << 30})
+        who ^= 1
+    seen = {}
+
+    def fake_run_clients(impl, out_dir, n, spec, seconds, tq_, extra_env=None, stop_after_handoffs=0, setup_timeout=0, **kw):
+        seen.update(seconds=seconds, setup_timeout=setup_timeout, stop_after=stop_after_handoffs)
+        for i in (0, 1):
+            (Path(out_dir) / f"engine{i}.jsonl").write_text("".join(json.dumps(r) + "\n" for r in recs[i]))
+        return [{"rc": 0, "iters": iters[i], "meta": {"summary": {"result": "PASS"}}, "out": "", "err_tail": ""} for i in (0, 1)]
+
+    class Sampler:
+        def __init__(self, *a, **k): pass
+        def start(self): pass
+        def stop(self, *a, **k): return {"sm_mhz": 1800.0, "sm_max_mhz": 1965.0, "reasons": []}
+    monkeypatch.setattr(b.harness, "calibrate", lambda spec, out, env=None: {"tau_s": tau, "iters": 100})
+    monkeypatch.setattr(b.harness, "run_clients", fake_run_clients)
+    monkeypatch.setattr(b.harness, "ClockSampler", Sampler)
+    exp = b.run_experiment("ours", "add", "pos", 2, 1.5, tq, 2, 4, HBM, 1.0, 1, tmp_path / "x", time_limit_s=300)
+    assert "error" not in exp, exp
+    # the timed part got what (2 + 4 + 2) hand-offs need, the setup the rest, and together they stay inside the limit
+    assert seen["stop_after"] == 8 and seen["seconds"] >= 8 * (tq + 4) and seen["setup_timeout"] + seen["seconds"] + 20 <= 300 + 1e-6
+    assert exp["verified"] and abs(exp["stall_ms_per_handoff"] - 1e3 * stall) < 60
+    dev = exp["device"]
+    assert dev["fetches"] >= 4 and dev["evicts"] >= 4 and dev["scan_GBps"] > 1000
+    ratio = dev["link_bytes_over_algorithmic"]            # per transfer, not per timed step
+    assert abs(ratio["in"] - (50 << 30) / exp["algorithmic_bytes_per_handoff_per_direction"]) < 1e-9
+    assert abs(ratio["out"] - (5 << 30) / exp["algorithmic_bytes_per_handoff_per_direction"]) < 1e-9
+    roof = b.roofline_objects(exp, {"link": {"h2d": 55.0, "d2h": 52.0}}, 1)
+    assert roof["roofline"]["kernel"] == "nvs_slab_scan" and roof["roofline"]["frac"] > 0
+    assert roof["roofline_link"]["fetch"]["frac"] > 0 and roof["roofline_link"]["evict"]["peak"] == 52.0
+    brief = b.brief(exp)
+    assert brief["verified"] and "stall_ms_per_handoff" in brief
+    roof2 = b.roofline_objects(exp, {"link": {"h2d": 55.0, "d2h": 52.0}, "peer": {"out": 781.0, "in": 780.0}}, 2)
+    assert roof2["roofline"]["bound"] == "nvlink" and roof2["roofline"]["peak"] == 780.5 and "roofline_scan" in roof2
