@@ -207,3 +207,63 @@ def test_run_experiment_post_processing_on_synthetic_records(tmp_path, monkeypat
     assert brief["verified"] and "stall_ms_per_handoff" in brief
     roof2 = b.roofline_objects(exp, {"link": {"h2d": 55.0, "d2h": 52.0}, "peer": {"out": 781.0, "in": 780.0}}, 2)
     assert roof2["roofline"]["bound"] == "nvlink" and roof2["roofline"]["peak"] == 780.5 and "roofline_scan" in roof2
+
+
+def test_the_json_line_of_both_arms_is_assembled_on_cpu(tmp_path, monkeypatch):
+    """run_rank0 from probes to the finished line, with the GPU-bound pieces replaced: every key of the bench contract
+    is there for our arm, and the reference arm carries its own cpu_baseline / e2e and launches nothing of ours."""
+    import json
+    b = load_bench()
+    tq, stall, tau = 1.0, 0.4, 0.02
+    t, who, iters, recs = 1000.0, 0, {0: [], 1: []}, {0: [], 1: []}
+    for _ in range(12):
+        t += stall
+        recs[who].append({"op": "fetch", "t": t, "bytes": 50 << 30, "copy_ms": 900.0, "host_bytes": 50 << 30, "peer_bytes": 0,
+                          "launches": 0, "ce_calls": 200, "map_ms": 60.0, "wait_ms": 150.0, "wall_ms": 1100.0, "elided_bytes": 0})
+        end = t + tq
+        while t < end:
+            t += tau
+            iters[who].append(t)
+        recs[who].append({"op": "evict", "t": t + 0.3, "bytes": 5 << 30, "copy_ms": 100.0, "host_bytes": 5 << 30, "peer_bytes": 0,
+                          "launches": 3, "scan_launches": 2, "ce_calls": 20, "map_ms": 90.0, "wait_ms": 0.0, "wall_ms": 400.0,
+                          "scanned_bytes": 140 << 30, "scan_ms": 24.0, "clean_bytes": 45 << 30, "elided_bytes": 0})
+        who ^= 1
+
+    def fake_run_clients(impl, out_dir, n, spec, seconds, tq_, **kw):
+        if impl == "ours":
+            for i in (0, 1):
+                (Path(out_dir) / f"engine{i}.jsonl").write_text("".join(json.dumps(r) + "\n" for r in recs[i]))
+        return [{"rc": 0, "iters": iters[i], "meta": {"summary": {"result": "PASS"}}, "out": "", "err_tail": ""} for i in (0, 1)]
+
+    class Sampler:
+        def __init__(self, *a, **k): pass
+        def start(self): pass
+        def stop(self, *a, **k): return {"sm_mhz": 1800.0, "sm_max_mhz": 1965.0, "reasons": []}
+    probes = []
+    monkeypatch.setattr(b.harness, "calibrate", lambda spec, out, env=None: {"tau_s": tau, "iters": 100})
+    monkeypatch.setattr(b.harness, "run_clients", fake_run_clients)
+    monkeypatch.setattr(b.harness, "ClockSampler", Sampler)
+    monkeypatch.setattr(b, "run_probes", lambda kernels=True: probes.append(kernels) or
+                        {"hbm_total": HBM, "link": {"h2d": 55.0, "d2h": 52.0}, "kernels": {"scan_hash": {}} if kernels else None})
+    monkeypatch.setattr(b, "cpu_baseline", lambda: {"value": 8.9, "unit": "GB/s", "cores": 1, "kind": "port", "sample": "x"})
+    monkeypatch.setattr(b, "host_memory_budget", lambda: None)
+    monkeypatch.setattr(b.subprocess, "Popen", None)       # nothing may be started behind the stubs' back
+    for impl in ("ours", "reference"):
+        if impl == "reference" and not b.harness.impl_paths("reference")["lib"].exists():
+            continue
+        args = types.SimpleNamespace(impl=impl, kind="add", pattern="pos", clients=2, oversub=1.5, tq=tq, warmup=2, steps=4,
+                                     hbm_fraction=1.0, keep=str(tmp_path / impl), no_extras=True, gpus=1)
+        line, wall = b.run_rank0(args, 1)
+        json.dumps(line)                                   # serialisable
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "cpu_baseline", "verified"):
+            assert k in line, (impl, k)
+        assert line["impl"] == impl and line["verified"] and line["config"]["workload"]
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+        if impl == "ours":
+            assert line["gpu_launches"] > 0 and line["roofline"]["kernel"] == "nvs_slab_scan" and line["cpu_baseline"]["kind"] == "port"
+            assert line["e2e"]["h2d_bytes_per_step"] > 0
+        else:
+            assert line["gpu_launches"] == 0 and line["cpu_baseline"]["kind"] == "reference" and "roofline" not in line
+            assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert probes[0] is True and (len(probes) == 1 or probes[1] is False)
