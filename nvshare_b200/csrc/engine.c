@@ -2732,6 +2732,9 @@ static void *preclean_main(void *arg)
 				c->pre_epoch = 0;
 				e->pin_target = e->host_pool.bytes + e->cfg.host_arena_bytes;
 				pthread_cond_signal(&e->pin_cv);
+			} else if (!e->shp && e->cfg.prepin && e->host_pool.bytes < e->pin_target) {
+				/* private pool: the pinning thread is still on its way to the footprint; same */
+				c->pre_epoch = 0;
 			}
 		}
 		if (launched) {

@@ -14,6 +14,13 @@ from nvshare_b200 import harness
 from nvs_testlib import ROOT
 
 
+def free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def synth(tau=0.02, quantum=1.0, stall=0.5, handoffs=8, slow_first=0.0):
     """Two clients alternating; every hand-off costs `stall` seconds before the arriving
     client's first iteration (plus `slow_first` spread over its first iteration)."""
@@ -114,7 +121,7 @@ def test_world_size_2_gloo_reduction(tmp_path):
     script = tmp_path / "w2.py"
     script.write_text(code)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(script)],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -136,15 +143,15 @@ def test_bench_main_under_torchrun_world_size_2(tmp_path, impl):
         b.run_rank0 = fake_rank0
         sys.argv = ["bench.py", "--gpus", "2", "--steps", "3", "--warmup", "3", "--impl", {impl!r}]
         rc = b.main()
-        print("RANK", os.environ["RANK"], "rc", rc, flush=True)
+        print("RANK", os.environ["RANK"], "rc", rc, file=sys.stderr, flush=True)    # (stdout belongs to rank 0's one line)
         sys.exit(rc)
     """)
     script = tmp_path / "w2bench.py"
     script.write_text(code)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29617" if impl == "ours" else "29619", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(script)],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1 and '"n_gpus": 2' in lines[0] and f'"impl": "{impl}"' in lines[0]
-    assert "RANK 0 rc 0" in r.stdout and "RANK 1 rc 0" in r.stdout
+    assert "RANK 0 rc 0" in r.stderr and "RANK 1 rc 0" in r.stderr
