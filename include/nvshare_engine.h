@@ -38,6 +38,9 @@
  *                    copy is host memory -> pinned host backing and needs
  *                    neither the GPU nor its lock
  *   nvs_get_stats    no counterpart (the reference has no counters)
+ *   nvs_gpu_account_query / nvs_gpu_lent_bytes
+ *                    src/hook.c:77-78, 662 (sum_allocated and the cap check), extended from
+ *                    "this process, device 0" to "every process, per GPU" 
  *   nvs_touch        no counterpart (recency hint from the hooked cuMemcpy / cuMemset calls)
  *   nvs_copy_slabs / nvs_scan_slabs / nvs_pattern_fill / nvs_pattern_verify
  *                    no counterpart: raw access to the sm_100a kernels for the
@@ -225,6 +228,31 @@ void nvs_evict_announce(nvs_engine *e);
 int nvs_evict_best_effort(nvs_engine *e, uint64_t min_bytes, nvs_xfer_report *rep);
 
 int nvs_get_stats(nvs_engine *e, nvs_stats *out);
+
+/*
+ * Per-GPU accounting across processes and schedulers ("peers' HBM used as backing
+ * must be accounted in those GPUs' caps").  The reference counts per process and knows one GPU
+ * (sum_allocated, src/hook.c:77-78, 662; device 0, src/client.c:386).  Here every engine records,
+ * in one small ledger file per user and machine, the backing arenas it creates on peer GPUs
+ * ("lent") and the swappable memory its owner has allocated on the GPU it computes on ("own");
+ * a peer arena is only created while  lent + arena <= total - reserve - largest own  on that GPU,
+ * and the hook shrinks the cuMemGetInfo / cuMemAlloc cap of a client by what its GPU has lent.
+ *   which = -1: the GPU this engine computes on;  which = i >= 0: peer i of the configuration.
+ */
+typedef struct nvs_gpu_account {
+	int32_t  tracked;       /* 1: this GPU is in the ledger (0: no ledger / driver without UUIDs)   */
+	int32_t  device;        /* CUDA ordinal as this process numbers the GPUs                        */
+	uint64_t total_bytes;   /* cuDeviceTotalMem (own GPU only; 0 for peers)                         */
+	uint64_t reserve_bytes; /* slice nobody may claim (NVSHARE_GPU_RESERVE_MIB, default 1536 MiB)   */
+	uint64_t lent_bytes;    /* backing arenas held on it by processes that compute elsewhere        */
+	uint64_t max_own_bytes; /* largest swappable footprint among the processes computing on it      */
+	uint64_t my_lent_bytes;
+	uint64_t my_own_bytes;
+	uint64_t refusals;      /* peer arenas this engine did not create because the GPU had no room   */
+} nvs_gpu_account;
+int nvs_gpu_account_query(nvs_engine *e, int which, nvs_gpu_account *out);
+/* What the GPU this engine computes on has lent to clients of other GPUs (for the hook's cap). */
+uint64_t nvs_gpu_lent_bytes(nvs_engine *e);
 
 /* Is dptr the start of an allocation this engine handed out (small pass-through ones included)?
  * 0 = yes (and *req_bytes = the size that was asked for), NVS_E_NOT_OURS = no.  For callers that must

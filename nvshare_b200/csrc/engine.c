@@ -56,6 +56,7 @@
 #include "../../include/nvshare_engine.h"
 #include "cuda_min.h"
 #include "nvs_log.h"
+#include "gpu_ledger.h"
 #include "slab_copy_cubin.h" /* generated: nvs_slab_copy_cubin[], nvs_slab_copy_cubin_len */
 
 #define SLAB NVS_SLAB_BYTES
@@ -98,6 +99,8 @@ struct drv {
 	CUresult (*StreamCreate)(CUstream *, unsigned);
 	CUresult (*StreamCreateWithPriority)(CUstream *, unsigned, int);        /* optional */
 	CUresult (*CtxGetStreamPriorityRange)(int *, int *);                    /* optional */
+	CUresult (*DeviceGetUuid)(uint8_t uuid[16], CUdevice);                  /* optional (gpu ledger) */
+	CUresult (*DeviceTotalMem)(size_t *, CUdevice);                         /* optional (gpu ledger) */
 	CUresult (*StreamDestroy)(CUstream);
 	CUresult (*StreamSynchronize)(CUstream);
 	CUresult (*EventCreate)(CUevent *, unsigned);
@@ -300,6 +303,8 @@ struct pool {
 	uint64_t bytes, used;
 	uint64_t capacity; /* 0 = unlimited */
 	int device;        /* peer ordinal, -1 for the host tier */
+	int gl_dev;        /* that GPU's index in the cross-process ledger (gpu_ledger.h), -1 = not tracked */
+	uint64_t gl_refusals; /* arenas not created because the ledger said that GPU has no room to lend */
 };
 
 struct scan_result;
@@ -373,6 +378,9 @@ struct nvs_engine {
 	struct shpool *shp; /* non-NULL: host_pool's arenas are windows of the shared pool */
 	struct pool peer_pools[NVS_MAX_PEERS];
 	uint32_t peer_rr;
+	int gl_dev;          /* the GPU we compute on, in the cross-process ledger (-1 = not tracked) */
+	uint64_t gl_reserve; /* bytes of every GPU that are nobody's to claim (contexts, libraries)  */
+	uint64_t gl_total;   /* cuDeviceTotalMem of the GPU we compute on                            */
 	uint64_t epoch;
 	int resident_mode;
 	nvs_stats st;
@@ -1087,6 +1095,51 @@ static int host_pool_overflow(nvs_engine *e)
 	return 0;
 }
 
+/* Put GPU `ordinal` (as this process numbers them) into the cross-process ledger: by UUID, because
+ * CUDA_VISIBLE_DEVICES renumbers the GPUs per process.  -1: not tracked (no ledger, or a driver
+ * without the two queries). */
+static int gl_register(nvs_engine *e, int ordinal, uint64_t *total_out)
+{
+	uint8_t uuid[16];
+	size_t total = 0;
+	if (total_out)
+		*total_out = 0;
+	if (!e->d.DeviceGetUuid || !e->d.DeviceTotalMem || e->d.DeviceGetUuid(uuid, (CUdevice)ordinal) != CUDA_SUCCESS ||
+	    e->d.DeviceTotalMem(&total, (CUdevice)ordinal) != CUDA_SUCCESS)
+		return -1;
+	if (total_out)
+		*total_out = total;
+	return nvs_gl_device(uuid, total);
+}
+
+int nvs_gpu_account_query(nvs_engine *e, int which, nvs_gpu_account *out)
+{
+	if (!e || !out || which < -1 || which >= e->cfg.n_peers)
+		return NVS_E_BAD_ARG;
+	memset(out, 0, sizeof(*out));
+	const int gl = which < 0 ? e->gl_dev : e->peer_pools[which].gl_dev;
+	out->device = which < 0 ? e->device : e->peer_pools[which].device;
+	out->tracked = gl >= 0;
+	out->reserve_bytes = e->gl_reserve;
+	if (which < 0)
+		out->total_bytes = e->gl_total;
+	out->lent_bytes = nvs_gl_lent(gl);
+	out->max_own_bytes = nvs_gl_max_own(gl);
+	out->my_lent_bytes = nvs_gl_mine(gl, NVS_GL_LENT);
+	out->my_own_bytes = nvs_gl_mine(gl, NVS_GL_OWN);
+	if (which >= 0) {
+		pthread_mutex_lock(&e->mu);
+		out->refusals = e->peer_pools[which].gl_refusals;
+		pthread_mutex_unlock(&e->mu);
+	}
+	return 0;
+}
+
+uint64_t nvs_gpu_lent_bytes(nvs_engine *e)
+{
+	return e ? nvs_gl_lent(e->gl_dev) : 0;
+}
+
 /* Create one arena of peer HBM mapped into this context.  Called with e->mu held. */
 static int peer_pool_grow(nvs_engine *e, int pi)
 {
@@ -1094,9 +1147,19 @@ static int peer_pool_grow(nvs_engine *e, int pi)
 	uint64_t bytes = e->cfg.host_arena_bytes;
 	if (p->capacity && p->bytes + bytes > p->capacity)
 		return NVS_E_HOST_OOM;
-	struct arena *a = arena_new(bytes);
-	if (!a)
+	/* That GPU's HBM is not ours alone: other clients back their slabs there too, and it may have
+	 * clients of its own.  Claim the arena in the cross-process ledger first; no room to lend means
+	 * the chunk goes to the next peer or to the host tier, like a peer that is simply full. */
+	if (nvs_gl_lend(p->gl_dev, bytes, e->gl_reserve) != 0) {
+		if (p->gl_refusals++ == 0)
+			nvs_debug("engine: GPU %d has no HBM left to lend (ledger): spilling", p->device);
 		return NVS_E_HOST_OOM;
+	}
+	struct arena *a = arena_new(bytes);
+	if (!a) {
+		nvs_gl_return(p->gl_dev, bytes);
+		return NVS_E_HOST_OOM;
+	}
 	CUmemAllocationProp prop;
 	memset(&prop, 0, sizeof(prop));
 	prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
@@ -1130,6 +1193,7 @@ static int peer_pool_grow(nvs_engine *e, int pi)
 	e->st.peer_pool_bytes += bytes;
 	return 0;
 fail:
+	nvs_gl_return(p->gl_dev, bytes);
 	arena_free(a);
 	return NVS_E_HOST_OOM;
 }
@@ -1261,6 +1325,7 @@ static void backing_release(nvs_engine *e, struct chunk *c)
 			e->d.MemUnmap(a->dev_base, a->bytes);
 			e->d.MemAddressFree(a->dev_base, a->bytes);
 			e->d.MemRelease(a->handle);
+			nvs_gl_return(p->gl_dev, a->bytes);
 			p->bytes -= a->bytes;
 			e->st.peer_pool_bytes -= a->bytes;
 			arena_free(a);
@@ -2041,7 +2106,7 @@ static int cmp_chunk_victim(const void *a, const void *b)
 	return x->va < y->va ? -1 : x->va > y->va;
 }
 
-static void report_emit(nvs_engine *e, const char *what, const nvs_xfer_report *r)
+static void report_emit(nvs_engine *e, const char *what, const nvs_xfer_report *r, int favour)
 {
 	nvs_debug("engine: %s %" PRIu64 " MiB (+%" PRIu64 " MiB same-filled, +%" PRIu64 " MiB clean: not moved) in %.1f ms "
 		  "(copy %.1f ms = %.1f GB/s, map %.1f ms, wait %.1f ms, scan %.1f ms)", what, r->bytes >> 20,
@@ -2054,10 +2119,10 @@ static void report_emit(nvs_engine *e, const char *what, const nvs_xfer_report *
 		",\"chunks\":%" PRIu64 ",\"launches\":%" PRIu64 ",\"ce_calls\":%" PRIu64 ",\"wall_ms\":%.3f,\"copy_ms\":%.3f,"
 		"\"map_ms\":%.3f,\"wait_ms\":%.3f,\"scan_ms\":%.3f,\"host_bytes\":%" PRIu64 ",\"peer_bytes\":%" PRIu64
 		",\"elided_bytes\":%" PRIu64 ",\"clean_bytes\":%" PRIu64 ",\"scanned_bytes\":%" PRIu64
-		",\"scan_launches\":%" PRIu64 ",\"retained_bytes\":%" PRIu64 ",\"pool_used\":%" PRIu64 "}\n",
+		",\"scan_launches\":%" PRIu64 ",\"retained_bytes\":%" PRIu64 ",\"pool_used\":%" PRIu64 ",\"favour\":%d}\n",
 		what, wall_s(), (int)getpid(), r->bytes, r->slabs, r->chunks, r->launches, r->ce_calls, r->wall_ms, r->copy_ms,
 		r->map_ms, r->wait_ms, r->scan_ms, r->host_bytes, r->peer_bytes, r->elided_bytes, r->clean_bytes,
-		r->scanned_bytes, r->scan_launches, e->st.retained_bytes, e->host_pool.used);
+		r->scanned_bytes, r->scan_launches, e->st.retained_bytes, e->host_pool.used, favour);
 	fflush(e->stats_file);
 }
 
@@ -2374,7 +2439,7 @@ out:
 	ctx_leave(e);
 	free(victims);
 	if (rc == 0 && (rep.bytes || rep.elided_bytes || rep.clean_bytes))
-		report_emit(e, "evict", &rep);
+		report_emit(e, "evict", &rep, best_effort); /* favour: done on a pressure hint, not at a hand-off */
 	if (rep_out)
 		*rep_out = rep;
 	return rc;
@@ -2637,7 +2702,7 @@ out:
 	pthread_mutex_unlock(&e->api_mu);
 	ctx_leave(e);
 	if (rc == 0 && (rep.bytes || rep.chunks || rep.elided_bytes))
-		report_emit(e, "fetch", &rep);
+		report_emit(e, "fetch", &rep, 0);
 	if (rep_out)
 		*rep_out = rep;
 	return rc;
@@ -2886,6 +2951,7 @@ int nvs_alloc(nvs_engine *e, uint64_t *dptr, uint64_t bytes)
 		}
 	}
 	e->st.va_bytes += a->va_bytes;
+	nvs_gl_own(e->gl_dev, (int64_t)a->va_bytes); /* what this process needs resident here when it holds the lock */
 	table_insert(e, a);
 	*dptr = va;
 	/* keep the pinned pool ahead of what may have to be swapped out (private pool:
@@ -2965,6 +3031,7 @@ int nvs_free_sized(nvs_engine *e, uint64_t dptr, uint64_t *req_bytes)
 		}
 		e->d.MemAddressFree(a->va, a->va_bytes);
 		e->st.va_bytes -= a->va_bytes;
+		nvs_gl_own(e->gl_dev, -(int64_t)a->va_bytes);
 		if (e->cfg.prepin && e->cfg.n_peers == 0 && !e->shp && e->pin_target >= a->va_bytes)
 			e->pin_target -= a->va_bytes;
 	}
@@ -3378,6 +3445,9 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 		return CUDA_ERROR_OUT_OF_MEMORY;
 	int rc = 0;
 	int ctx_pushed = 0;
+	e->gl_dev = e->host_pool.gl_dev = -1;
+	for (int i = 0; i < NVS_MAX_PEERS; ++i)
+		e->peer_pools[i].gl_dev = -1;
 	if (cfg_in && cfg_in->struct_size == sizeof(e->cfg))
 		e->cfg = *cfg_in;
 	else if (cfg_in)
@@ -3418,6 +3488,10 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	/* optional entry points (older drivers / the test double do without) */
 	*(void **)&e->d.StreamCreateWithPriority = resolve("cuStreamCreateWithPriority");
 	*(void **)&e->d.CtxGetStreamPriorityRange = resolve("cuCtxGetStreamPriorityRange");
+	*(void **)&e->d.DeviceGetUuid = resolve("cuDeviceGetUuid_v2");
+	if (!e->d.DeviceGetUuid)
+		*(void **)&e->d.DeviceGetUuid = resolve("cuDeviceGetUuid");
+	*(void **)&e->d.DeviceTotalMem = resolve("cuDeviceTotalMem_v2");
 	pthread_mutex_init(&e->api_mu, NULL);
 	pthread_mutex_init(&e->mu, NULL);
 	pthread_cond_init(&e->pre_cv, NULL);
@@ -3505,6 +3579,7 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	}
 
 	e->host_pool.device = -1;
+	e->host_pool.gl_dev = -1;
 	if (e->cfg.shared_pool_path && *e->cfg.shared_pool_path) {
 		size_t free_b = 0, total_b = 0;
 		uint64_t cap = e->cfg.shared_pool_bytes;
@@ -3526,6 +3601,11 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 			goto out;
 		}
 	}
+	/* cross-process accounting per GPU (gpu_ledger.h): the GPU we compute on and every peer we lend from */
+	e->gl_reserve = env_u64("NVSHARE_GPU_RESERVE_MIB", 1536) << 20; /* the slice the reference hides too, src/hook.c:45 */
+	e->gl_dev = gl_register(e, e->device, &e->gl_total);
+	for (int i = 0; i < e->cfg.n_peers; ++i)
+		e->peer_pools[i].gl_dev = gl_register(e, e->cfg.peers[i], NULL);
 	if (e->cfg.stats_path && *e->cfg.stats_path)
 		e->stats_file = fopen(e->cfg.stats_path, "a");
 	if (e->cfg.prepin && e->cfg.n_peers == 0) {
@@ -3605,6 +3685,7 @@ void nvs_engine_destroy(nvs_engine *e)
 				e->d.MemUnmap(a->dev_base, a->bytes);
 				e->d.MemAddressFree(a->dev_base, a->bytes);
 				e->d.MemRelease(a->handle);
+				nvs_gl_return(e->peer_pools[i].gl_dev, a->bytes);
 				arena_free(a);
 			}
 		slots_free(e);

@@ -743,7 +743,18 @@ CUresult cuInit(unsigned flags)
 	return r;
 }
 
-CUresult cuMemGetInfo_v2(size_t *free_b, size_t *total_b)
+/* HBM of the GPU this process computes on that clients of OTHER GPUs use as backing right now (the
+ * peer tier of their engines; gpu_ledger.h).  The reference knows one GPU and one kind of tenant
+ * (src/hook.c:662); here what a GPU has lent is not there for its own clients, so it comes off what
+ * they are told is free and off their cap.  0 until this process has an engine, and whenever nobody
+ * lends -- the reference's numbers exactly. */
+static size_t lent_now(void)
+{
+	nvs_engine *e = __atomic_load_n(&engine, __ATOMIC_ACQUIRE);
+	return e ? (size_t)nvs_gpu_lent_bytes(e) : 0;
+}
+
+static CUresult meminfo(size_t *free_b, size_t *total_b, size_t lent)
 {
 	if (!real_cuMemGetInfo)
 		return CUDA_ERROR_NOT_INITIALIZED;
@@ -753,9 +764,15 @@ CUresult cuMemGetInfo_v2(size_t *free_b, size_t *total_b)
 		  *total_b / 1048576.0);
 	/* hide a fixed slice for contexts and libraries, whatever is really free */
 	*free_b = *total_b - (size_t)MEMINFO_RESERVE_BYTES;
+	*free_b = *free_b > lent ? *free_b - lent : 0;
 	nvs_debug("nvshare's cuMemGetInfo returning free=%.2f MiB, total=%.2f MiB", *free_b / 1048576.0,
 		  *total_b / 1048576.0);
 	return r;
+}
+
+CUresult cuMemGetInfo_v2(size_t *free_b, size_t *total_b)
+{
+	return meminfo(free_b, total_b, lent_now());
 }
 
 CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize)
@@ -765,12 +782,14 @@ CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize)
 	pthread_mutex_lock(&acct_mu);
 	if (!cap_known) {
 		size_t total = 0;
-		CUresult r = cuMemGetInfo_v2(&cap_bytes, &total);
+		CUresult r = meminfo(&cap_bytes, &total, 0); /* the fixed part; what the GPU has lent is looked up per request */
 		warn_if_error(r, "cuMemGetInfo_v2");
 		cap_known = 1;
 	}
 	/* (the reference's `sum_allocated + bytesize > cap`, src/hook.c:662, without the wrap-around of a huge request) */
-	if (sum_allocated > cap_bytes || bytesize > cap_bytes - sum_allocated) {
+	const size_t lent = lent_now();
+	const size_t cap_now = cap_bytes > lent ? cap_bytes - lent : 0;
+	if (sum_allocated > cap_now || bytesize > cap_now - sum_allocated) {
 		if (!single_oversub) {
 			pthread_mutex_unlock(&acct_mu);
 			return CUDA_ERROR_OUT_OF_MEMORY;

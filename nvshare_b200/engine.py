@@ -65,6 +65,15 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class GpuAccount(C.Structure):
+    """nvs_gpu_account (include/nvshare_engine.h): one GPU's row of the cross-process ledger."""
+    _fields_ = [("tracked", C.c_int32), ("device", C.c_int32)] + [(n, C.c_uint64) for n in (
+        "total_bytes", "reserve_bytes", "lent_bytes", "max_own_bytes", "my_lent_bytes", "my_own_bytes", "refusals")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class ScanOut(C.Structure):
     _fields_ = [("value", C.c_uint64), ("is_const", C.c_uint64), ("h0", C.c_uint64), ("h1", C.c_uint64)]
 
@@ -104,6 +113,9 @@ def load():
     lib.nvs_evict.argtypes = [C.c_void_p, C.c_uint64, P(XferReport)]
     lib.nvs_evict_best_effort.argtypes = [C.c_void_p, C.c_uint64, P(XferReport)]
     lib.nvs_get_stats.argtypes = [C.c_void_p, P(Stats)]
+    lib.nvs_gpu_account_query.argtypes = [C.c_void_p, C.c_int, P(GpuAccount)]
+    lib.nvs_gpu_lent_bytes.argtypes = [C.c_void_p]
+    lib.nvs_gpu_lent_bytes.restype = C.c_uint64
     lib.nvs_host_io.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
     lib.nvs_touch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     lib.nvs_copy_slabs.argtypes = [C.c_void_p, P(CopyDesc), C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_float)]
@@ -190,6 +202,15 @@ class Engine:
         st = Stats()
         _check(load().nvs_get_stats(self._h, C.byref(st)), "nvs_get_stats")
         return st.as_dict()
+
+    def gpu_account(self, which: int = -1) -> dict:
+        """which = -1: the GPU this engine computes on; i >= 0: peer i of the configuration."""
+        acc = GpuAccount()
+        _check(load().nvs_gpu_account_query(self._h, which, C.byref(acc)), "nvs_gpu_account_query")
+        return acc.as_dict()
+
+    def gpu_lent_bytes(self) -> int:
+        return load().nvs_gpu_lent_bytes(self._h)
 
     def touch(self, dptr: int, nbytes: int):
         _check(load().nvs_touch(self._h, dptr, nbytes), "nvs_touch")

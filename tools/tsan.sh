@@ -16,9 +16,9 @@ CF="-O1 -g -std=gnu11 -fPIC -I$ROOT/include $TS -DNVS_NO_DLSYM_EXPORT"
 rm -rf "$OUT"; mkdir -p "$OUT/logs"
 make -C "$SRC" -s
 make -C "$ROOT/oracle" -s
-for f in hook client nvs_wire engine nvs_log; do gcc $CF -c "$SRC/$f.c" -o "$OUT/$f.o"; done
-gcc -shared $TS -Wl,-soname=libnvshare.so "$OUT"/{hook,client,nvs_wire,engine,nvs_log}.o -o "$OUT/libnvshare.so" -ldl -lpthread
-gcc -shared $TS -Wl,-soname=libnvs_engine.so -Wl,--version-script="$SRC/libnvs_engine.ld" "$OUT"/{engine,nvs_log}.o -o "$OUT/libnvs_engine.so" -ldl -lpthread
+for f in hook client nvs_wire engine gpu_ledger nvs_log; do gcc $CF -c "$SRC/$f.c" -o "$OUT/$f.o"; done
+gcc -shared $TS -Wl,-soname=libnvshare.so "$OUT"/{hook,client,nvs_wire,engine,gpu_ledger,nvs_log}.o -o "$OUT/libnvshare.so" -ldl -lpthread
+gcc -shared $TS -Wl,-soname=libnvs_engine.so -Wl,--version-script="$SRC/libnvs_engine.ld" "$OUT"/{engine,gpu_ledger,nvs_log}.o -o "$OUT/libnvs_engine.so" -ldl -lpthread
 cp "$ROOT/nvshare_b200/_build/slab_copy.cubin" "$OUT/" 2>/dev/null || true
 echo "called_from_lib:libcuda.so.1" > "$OUT/supp.txt"
 LIBTSAN=$(gcc -print-file-name=libtsan.so)
