@@ -3714,7 +3714,16 @@ void nvs_engine_destroy(nvs_engine *e)
 		if (e->module)
 			e->d.ModuleUnload(e->module);
 		ctx_leave(e);
+	} else {
+		/* no context to tear the arenas down in: the driver takes them back with the process,
+		 * the ledger must not keep counting them for as long as the process lives on */
+		for (int i = 0; i < NVS_MAX_PEERS; ++i)
+			nvs_gl_return(e->peer_pools[i].gl_dev, e->peer_pools[i].bytes);
 	}
+	/* allocations whose free the driver refused (or that had no context to be freed in) are no
+	 * longer this engine's to claim */
+	if (e->st.va_bytes)
+		nvs_gl_own(e->gl_dev, -(int64_t)e->st.va_bytes);
 	if (e->stats_file)
 		fclose(e->stats_file);
 	pthread_mutex_destroy(&e->mu);
