@@ -663,6 +663,7 @@ def run_rank0(args, world):
             line["cpu_baseline"] = cpu
         if not args.no_extras:
             extras(args, line, probe, world, total_b, frac, out_dir, T_START)
+            config1(args, line, world, out_dir)
     else:
         line["value"] = e2e
         line["gpu_launches"] = 0
@@ -671,6 +672,8 @@ def run_rank0(args, world):
         line["cpu_baseline"] = {"value": e2e, "unit": "GB/s", "cores": ncpu, "kind": "reference",
                                 "sample": "the reference has no CPU compute path: this is its UVM page-fault path "
                                           "(cuMemAllocManaged) on the same box, same workload; host cores only service faults"}
+        if not args.no_extras:
+            config1(args, line, world, out_dir)
     line["wall_s_total"] = time.time() - t0
     if not args.keep:
         shutil.rmtree(out_dir, ignore_errors=True)
@@ -742,6 +745,22 @@ def extras(args, line, probe, world, total_b, frac, out_dir, t_bench_start):
             line["configs"][name] = brief(exp)
         except Exception as ex:
             line["configs"][name] = {"error": repr(ex), "verified": False}
+
+
+def config1(args, line, world, out_dir):
+    """BASELINE config #1, the reference's own CPU-runnable case: this arm's daemon under scripted clients
+    (harness.scheduler_pingpong; a few seconds, no GPU).  Both arms carry it, so that the pair is in the
+    driver's record; N = 1 only, where nothing else competes for the host cores."""
+    if world != 1 or args.kind != "add":
+        return
+    if time.time() - T_START > TOTAL_BUDGET_S - 60:
+        line.setdefault("configs", {})["config1_scheduler_cpu_2_clients"] = {"skipped": "the run's time budget is spent"}
+        return
+    try:
+        rec = harness.scheduler_pingpong(args.impl, out_dir / "config1", clients=2, cycles=20000, trials=5)
+    except Exception as ex:
+        rec = {"error": repr(ex)}
+    line.setdefault("configs", {})["config1_scheduler_cpu_2_clients"] = rec
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 /*
- * gpu_ledger.c -- see gpu_ledger.h.  Host-side bookkeeping only: a 40 KiB file in /dev/shm,
+ * gpu_ledger.c -- see gpu_ledger.h.  Host-side bookkeeping only: a ~50 KiB file in /dev/shm,
  * a robust process-shared mutex, a table of claims.  No CUDA calls here.
  */
 #define _GNU_SOURCE
@@ -21,7 +21,7 @@
 #include "nvs_log.h"
 
 #define GL_MAGIC 0x6e7673684750554cull /* "nvshGPUL" */
-#define GL_VERSION 1u
+#define GL_VERSION 2u /* 2: claims carry their owner's start time */
 #define GL_MAX_DEVS 32
 #define GL_MAX_CLAIMS 2048
 
@@ -37,6 +37,8 @@ struct gl_claim {
 	uint16_t dev;
 	uint16_t kind;
 	uint64_t bytes;
+	uint64_t start; /* when that pid started (clock ticks since boot, /proc/<pid>/stat field 22): a pid
+	                 * that has been recycled by an unrelated long-lived process must not keep the claim */
 };
 
 struct gl_file {
@@ -66,6 +68,47 @@ static uint64_t gl_pid_ns(void)
 	return stat("/proc/self/ns/pid", &st) == 0 ? (uint64_t)st.st_ino : 0;
 }
 
+/* Field 22 of /proc/<pid>/stat; 0 = no such process (or no /proc: then pids alone decide). */
+static uint64_t gl_start_time(int32_t pid)
+{
+	char path[64], buf[1024];
+	snprintf(path, sizeof(path), "/proc/%d/stat", (int)pid);
+	int fd = open(path, O_RDONLY | O_CLOEXEC);
+	if (fd < 0)
+		return 0;
+	ssize_t n = read(fd, buf, sizeof(buf) - 1);
+	close(fd);
+	if (n <= 0)
+		return 0;
+	buf[n] = '\0';
+	char *p = strrchr(buf, ')'); /* the command name may contain anything, parentheses included */
+	if (!p)
+		return 0;
+	p++;
+	for (int field = 3; field < 22; ++field) { /* p is in front of field 3 (state) */
+		while (*p == ' ')
+			p++;
+		while (*p && *p != ' ')
+			p++;
+	}
+	return strtoull(p, NULL, 10);
+}
+
+static uint64_t g_my_start; /* of this process, re-read after a fork (see gl_me) */
+static int32_t g_my_pid;
+
+static int32_t gl_me(uint64_t *start)
+{
+	const int32_t me = (int32_t)getpid();
+	if (me != g_my_pid) { /* first call, or a child of the process that opened the ledger */
+		g_my_start = gl_start_time(me);
+		g_my_pid = me;
+	}
+	if (start)
+		*start = g_my_start;
+	return me;
+}
+
 static void gl_lock(void)
 {
 	int r = pthread_mutex_lock(&g_gl->mu);
@@ -84,6 +127,7 @@ static unsigned gl_reap_locked(void)
 	unsigned n = 0;
 	int32_t last = 0;
 	int last_dead = 0;
+	uint64_t last_start = 0;
 	for (unsigned i = 0; i < GL_MAX_CLAIMS; ++i) {
 		struct gl_claim *c = &g_gl->claims[i];
 		if (c->pid <= 0)
@@ -91,8 +135,10 @@ static unsigned gl_reap_locked(void)
 		if (c->pid != last) {
 			last = c->pid;
 			last_dead = kill(c->pid, 0) != 0 && errno == ESRCH;
+			last_start = last_dead ? 0 : gl_start_time(c->pid);
 		}
-		if (last_dead) {
+		/* gone, or the pid now belongs to somebody who started at another time */
+		if (last_dead || (last_start && c->start && last_start != c->start)) {
 			memset(c, 0, sizeof(*c));
 			n++;
 		}
@@ -182,7 +228,7 @@ static void gl_open_once(void)
 	g_gl = f;
 	/* a recycled pid: whatever the table says about "us" was written by somebody who is gone */
 	gl_lock();
-	const int32_t me = (int32_t)getpid();
+	const int32_t me = gl_me(NULL);
 	for (unsigned i = 0; i < GL_MAX_CLAIMS; ++i)
 		if (g_gl->claims[i].pid == me)
 			memset(&g_gl->claims[i], 0, sizeof(g_gl->claims[i]));
@@ -221,10 +267,13 @@ int nvs_gl_device(const uint8_t uuid[16], uint64_t total_bytes)
 /* this process's claim of `kind` on `dev`, created on demand (mutex held) */
 static struct gl_claim *gl_mine_locked(int dev, int kind, int create)
 {
-	const int32_t me = (int32_t)getpid();
+	uint64_t my_start = 0;
+	const int32_t me = gl_me(&my_start);
 	struct gl_claim *spare = NULL;
 	for (unsigned i = 0; i < GL_MAX_CLAIMS; ++i) {
 		struct gl_claim *c = &g_gl->claims[i];
+		if (c->pid == me && c->start && my_start && c->start != my_start)
+			memset(c, 0, sizeof(*c)); /* left behind by an earlier owner of this pid */
 		if (c->pid == me && c->dev == dev && c->kind == kind)
 			return c;
 		if (c->pid == 0 && !spare)
@@ -236,6 +285,7 @@ static struct gl_claim *gl_mine_locked(int dev, int kind, int create)
 		return gl_mine_locked(dev, kind, create);
 	if (spare) {
 		spare->pid = me;
+		spare->start = my_start;
 		spare->dev = (uint16_t)dev;
 		spare->kind = (uint16_t)kind;
 		spare->bytes = 0;

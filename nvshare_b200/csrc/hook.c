@@ -871,7 +871,11 @@ CUresult cuMemAllocPitch_v2(CUdeviceptr *dptr, size_t *pitch, size_t width_bytes
 	if (!dptr || !pitch || width_bytes == 0 || height == 0 || !(elem == 4 || elem == 8 || elem == 16))
 		return CUDA_ERROR_INVALID_VALUE;
 	/* what the driver does on every GPU that has VMM: rows padded to 512 bytes */
+	if (width_bytes > SIZE_MAX - 511)
+		return CUDA_ERROR_OUT_OF_MEMORY;
 	const size_t p = (width_bytes + 511) & ~(size_t)511;
+	if (p > SIZE_MAX / height) /* (a product that wraps must not come back as a small allocation) */
+		return CUDA_ERROR_OUT_OF_MEMORY;
 	CUresult r = cuMemAlloc_v2(dptr, p * height);
 	if (r == CUDA_SUCCESS)
 		*pitch = p;

@@ -19,12 +19,11 @@ extern int nvs_debug_enabled __attribute__((visibility("hidden")));
 extern volatile int nvs_process_exiting __attribute__((visibility("hidden")));
 #define NVS_EXITING() __atomic_load_n(&nvs_process_exiting, __ATOMIC_RELAXED)
 
-#define nvs_log_at(level, ...)                               \
-	do {                                                 \
-		fputs("[NVSHARE][" level "]: ", stderr);     \
-		fprintf(stderr, __VA_ARGS__);                \
-		fputc('\n', stderr);                         \
-	} while (0)
+/* One line = one write: the prefix, the text and the newline are put together first, so that lines of
+ * different threads (the hook runs inside multi-threaded applications) never interleave and a daemon that
+ * logs every frame pays one system call per line on its unbuffered stderr, not three. */
+void nvs_log_line(const char *level, const char *fmt, ...) __attribute__((format(printf, 2, 3), visibility("hidden")));
+#define nvs_log_at(level, ...) nvs_log_line(level, __VA_ARGS__)
 
 #define nvs_info(...)  nvs_log_at("INFO", __VA_ARGS__)
 #define nvs_warn(...)  nvs_log_at("WARN", __VA_ARGS__)

@@ -191,16 +191,21 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def start_scheduler(impl, sock_dir, log_path, tq):
+def start_scheduler(impl, sock_dir, log_path, tq, debug=True, cpus=None):
     paths = impl_paths(impl)
-    env = dict(os.environ, NVSHARE_DEBUG="1")
+    env = dict(os.environ)
+    if debug:
+        env["NVSHARE_DEBUG"] = "1"
+    else:
+        env.pop("NVSHARE_DEBUG", None)
     if impl == "ours":
         env["NVSHARE_SOCK_DIR"] = str(sock_dir)
     sock = Path(sock_dir) / "scheduler.sock"
     if sock.exists():
         sock.unlink()
     log = open(log_path, "wb")
-    p = subprocess.Popen([str(paths["sched"])], env=env, stdout=log, stderr=subprocess.STDOUT)
+    p = subprocess.Popen([str(paths["sched"])], env=env, stdout=log, stderr=subprocess.STDOUT,
+                         preexec_fn=(lambda: os.sched_setaffinity(0, cpus)) if cpus else None)
     deadline = time.time() + 10
     while not sock.exists():
         if p.poll() is not None or time.time() > deadline:
@@ -212,6 +217,56 @@ def start_scheduler(impl, sock_dir, log_path, tq):
         p.kill()
         raise RuntimeError(f"nvsharectl -T failed: {r.stderr}")
     return p
+
+
+def scheduler_pingpong(impl, out_dir, clients=2, cycles=20000, trials=5):
+    """BASELINE config #1 (CPU only): the daemon of `impl` and `clients` scripted clients that do nothing but
+    REQ_LOCK -> LOCK_OK -> LOCK_RELEASED (tools/pingpong.c, the same binary against both daemons).  No GPU, no
+    library of ours or of the reference in the clients: what is timed is the daemon's hand-off path.
+
+    Where the kernel puts three mostly-sleeping threads decides the result more than the daemon does (a wake-up
+    across cores costs ~20 us on a virtual machine, a context switch on one core ~2 us: the same daemon does
+    20 k or 85 k hand-offs/s depending on it), so the placement is fixed and both are measured:
+      same_core       daemon and clients on one core     -> the daemon's own path length
+      separate_cores  daemon on one core, clients on two -> wake-up latency dominated
+    Several trials per placement against one daemon; the median trial is the record, all of them are listed."""
+    from .build import ORACLE_OUT
+    tool = ORACLE_OUT / "pingpong"
+    if not tool.exists():
+        raise RuntimeError(f"{tool} is missing: run __graft_entry__.build()")
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    sock_dir = out_dir / "sock" if impl == "ours" else Path("/var/run/nvshare")
+    sock_dir.mkdir(parents=True, exist_ok=True)
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)
+    cpus = sorted(os.sched_getaffinity(0))
+    placements = {"same_core": ({cpus[-1]}, {cpus[-1]})}
+    if len(cpus) >= 3:
+        placements["separate_cores"] = ({cpus[-1]}, set(cpus[-3:-1]))
+    out = {"impl": impl, "clients": clients, "cycles_per_client": cycles, "trials": trials, "host_cores": os.cpu_count(),
+           "what": "REQ_LOCK -> LOCK_OK -> LOCK_RELEASED cycles of scripted clients against this arm's nvshare-scheduler "
+                   "over the Unix socket (537-byte frames), CPU only; per placement the median of the trials"}
+    for name, (sched_cpus, client_cpus) in placements.items():
+        sched = start_scheduler(impl, sock_dir, out_dir / f"scheduler_{name}.log", 30, debug=False, cpus=sched_cpus)
+        runs = []
+        try:
+            for _ in range(trials):
+                r = subprocess.run([str(tool), str(sock_dir / "scheduler.sock"), str(clients), str(cycles)], env=env,
+                                   capture_output=True, text=True, timeout=120,
+                                   preexec_fn=lambda c=client_cpus: os.sched_setaffinity(0, c))
+                if r.returncode != 0:
+                    raise RuntimeError(f"pingpong against the {impl} daemon failed: {r.stderr[-500:]}")
+                runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+        finally:
+            stop_process(sched)
+        runs.sort(key=lambda x: x["handoffs_per_s"])
+        med = runs[len(runs) // 2]
+        out[name] = {"handoffs_per_s": med["handoffs_per_s"], "req_to_lock_ok_us": med["req_to_lock_ok_us"],
+                     "handoffs_per_s_all_trials": [x["handoffs_per_s"] for x in runs],
+                     "daemon_cpus": sorted(sched_cpus), "client_cpus": sorted(client_cpus)}
+    out["handoffs_per_s"] = out["same_core"]["handoffs_per_s"]
+    return out
 
 
 def stop_process(p, timeout=10):

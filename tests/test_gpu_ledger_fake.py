@@ -10,6 +10,7 @@ import os
 import subprocess
 import sys
 import time
+from pathlib import Path
 
 import pytest
 
@@ -208,3 +209,38 @@ def test_hooked_client_sees_what_its_gpu_has_lent(artefacts, workers, sock_dir, 
         app.wait(timeout=30)
     finally:
         d.stop()
+
+
+# layout of the ledger file (gpu_ledger.c): header 24 bytes, pthread_mutex_t 40, 32 devices x 32 bytes, then the
+# claims: {i32 pid, u16 dev, u16 kind, u64 bytes, u64 start time of the pid}
+_CLAIMS_AT, _CLAIM, _DEVS_AT, _DEV = 24 + 40 + 32 * 32, 24, 24 + 40, 32
+
+
+def _start_time(pid):
+    return int(Path(f"/proc/{pid}/stat").read_text().rsplit(")", 1)[1].split()[19])
+
+
+def _plant_claim(path, gpu, kind, nbytes, pid, start):
+    import struct
+    raw = bytearray(Path(path).read_bytes())
+    dev = next(i for i in range(32) if raw[_DEVS_AT + i * _DEV + 15] == gpu and raw[_DEVS_AT + i * _DEV + 24])
+    slot = next(i for i in range(2048) if struct.unpack_from("<i", raw, _CLAIMS_AT + i * _CLAIM)[0] == 0)
+    with open(path, "r+b") as f:
+        f.seek(_CLAIMS_AT + slot * _CLAIM)
+        f.write(struct.pack("<iHHQQ", pid, dev, kind, nbytes, start))
+
+
+def test_a_recycled_pid_does_not_keep_a_dead_clients_claim(workers, tmp_path):
+    """Owners are pids, and pids are recycled: a claim whose pid is alive again but started at another time
+    than the claim says belongs to nobody.  Planted by hand: one claim of a live pid (this test process) with
+    the wrong start time, one with the right one.  Only the second is counted."""
+    a = workers(tmp_path, peers=[1])
+    assert a("alloc", 64)["ok"] and a("evict")["peer_bytes"] == 64 * MiB
+    me = os.getpid()
+    _plant_claim(tmp_path / "gpus", 1, 1, 100 * MiB, me, _start_time(me) + 12345)      # kind 1 = lent
+    time.sleep(1.1)                                                                     # (the dead are looked for once a second)
+    assert a("account", 0)["lent_bytes"] == 64 * MiB
+    _plant_claim(tmp_path / "gpus", 1, 1, 50 * MiB, me, _start_time(me))
+    time.sleep(1.1)
+    assert a("account", 0)["lent_bytes"] == (64 + 50) * MiB
+    assert a("fetch")["mismatches"] == 0
