@@ -590,20 +590,21 @@ static nvs_engine *engine_get(void)
 			const char *pool = getenv("NVSHARE_POOL");
 			if (!(pool && strcmp(pool, "private") == 0) && nvs_pool_path(pool_path, sizeof(pool_path)) == 0)
 				cfg.shared_pool_path = pool_path;
-			int rc = nvs_engine_create(&cfg, &engine);
+			nvs_engine *made = NULL; /* published below: lock-free readers (lent_now, the copy bypass) load `engine` atomically */
+			int rc = nvs_engine_create(&cfg, &made);
 			if (rc == NVS_E_NO_KERNEL || rc == NVS_E_NO_DRIVER) {
 				/* not a B200 (only the sm_100a image is embedded), or a driver without the VMM entry
 				 * points: the drop-in still has to work, so this process runs on the reference's
 				 * managed-memory mechanism (cuMemAllocManaged + UVM faults) like NVSHARE_ENGINE=uvm */
 				nvs_warn("swap engine unavailable on this GPU/driver (%s): falling back to the reference's "
 					 "managed-memory mechanism for this process", nvs_strerror(rc));
-				engine = NULL;
 				uvm_mode = 1;
 			} else if (rc != 0) {
 				nvs_fatal("swap engine could not start (%s); set NVSHARE_ENGINE=uvm to run with "
 					  "the reference's managed-memory mechanism instead", nvs_strerror(rc));
 			} else {
-				nvs_set_resident_mode(engine, holds_lock);
+				nvs_set_resident_mode(made, holds_lock);
+				__atomic_store_n(&engine, made, __ATOMIC_RELEASE);
 			}
 		}
 	}
