@@ -143,7 +143,9 @@ def test_bench_main_under_torchrun_world_size_2(tmp_path, impl):
         b.run_rank0 = fake_rank0
         sys.argv = ["bench.py", "--gpus", "2", "--steps", "3", "--warmup", "3", "--impl", {impl!r}]
         rc = b.main()
-        print("RANK", os.environ["RANK"], "rc", rc, file=sys.stderr, flush=True)    # (stdout belongs to rank 0's one line)
+        # (stdout belongs to rank 0's one line; one write per rank: print() writes its pieces one by one and the
+        # two ranks share the pipe)
+        os.write(2, ("RANK " + os.environ["RANK"] + " rc " + str(rc) + chr(10)).encode())
         sys.exit(rc)
     """)
     script = tmp_path / "w2bench.py"
