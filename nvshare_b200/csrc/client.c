@@ -409,13 +409,40 @@ static void *message_thread(void *arg)
 	return NULL;
 }
 
+/* The NVML handle of the GPU the application's context is on (mutex held, context known).  NVML numbers
+ * the physical GPUs whatever CUDA_VISIBLE_DEVICES says, so the driver is asked for the device's UUID and NVML
+ * for the handle of that UUID.  Returns 0 and leaves *dev alone when any link of that chain is missing: the
+ * caller then stays with index 0, the reference's choice. */
+static int nvml_device_of_app(nvmlDevice_t *dev)
+{
+	CUdevice d = 0;
+	uint8_t u[16];
+	char name[48];
+	nvmlDevice_t h = NULL;
+	if (!drv.nvmlDeviceGetHandleByUUID || !drv.cuCtxGetDevice || !drv.cuDeviceGetUuid || !app_ctx_known)
+		return 0;
+	if (drv.cuCtxSetCurrent(app_ctx) != CUDA_SUCCESS || drv.cuCtxGetDevice(&d) != CUDA_SUCCESS ||
+	    drv.cuDeviceGetUuid(u, d) != CUDA_SUCCESS)
+		return 0;
+	snprintf(name, sizeof(name), "GPU-%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", u[0], u[1], u[2],
+		 u[3], u[4], u[5], u[6], u[7], u[8], u[9], u[10], u[11], u[12], u[13], u[14], u[15]);
+	if (drv.nvmlDeviceGetHandleByUUID(name, &h) != NVML_SUCCESS || !h) {
+		nvs_debug("NVML does not know %s (CUDA device %d): watching NVML device 0 like the reference", name, (int)d);
+		return 0;
+	}
+	nvs_debug("Early release watches the utilisation of %s (CUDA device %d)", name, (int)d);
+	*dev = h;
+	return 1;
+}
+
 static void *idle_thread(void *arg)
 {
 	(void)arg;
 	nvmlDevice_t nvml_dev = NULL;
+	int nvml_dev_settled = 0; /* the application's own GPU has been looked up (it has no context before its first gated call) */
 	block_all_signals();
 	if (nvml_ok) {
-		/* device index 0, like the reference (src/client.c:386) */
+		/* device index 0, like the reference (src/client.c:386), until the application's GPU is known */
 		if (drv.nvmlInit() != NVML_SUCCESS || drv.nvmlDeviceGetHandleByIndex(0, &nvml_dev) != NVML_SUCCESS) {
 			nvs_warn("NVML initialisation failed; falling back to timing cuCtxSynchronize");
 			nvml_ok = 0;
@@ -440,6 +467,10 @@ static void *idle_thread(void *arg)
 		if (!scheduler_on || !own_lock || did_work)
 			continue;
 		/* nothing was submitted for a whole interval; is the GPU still busy with earlier work? */
+		if (nvml_ok && !nvml_dev_settled && app_ctx_known) {
+			nvml_device_of_app(&nvml_dev);
+			nvml_dev_settled = 1;
+		}
 		if (nvml_ok) {
 			nvmlUtilization_t u;
 			if (drv.nvmlDeviceGetUtilizationRates(nvml_dev, &u) != NVML_SUCCESS) {

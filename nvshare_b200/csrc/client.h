@@ -24,6 +24,12 @@ struct nvs_client_driver {
 	nvmlReturn_t (*nvmlInit)(void);
 	nvmlReturn_t (*nvmlDeviceGetHandleByIndex)(unsigned, nvmlDevice_t *);
 	nvmlReturn_t (*nvmlDeviceGetUtilizationRates)(nvmlDevice_t, nvmlUtilization_t *);
+	/* Optional, all three or the reference's device 0: which physical GPU the application's context is
+	 * on.  NVML numbers the physical GPUs and does not know CUDA_VISIBLE_DEVICES, so "index 0"
+	 * (reference src/client.c:386) is somebody else's GPU for every client that computes elsewhere. */
+	nvmlReturn_t (*nvmlDeviceGetHandleByUUID)(const char *, nvmlDevice_t *);
+	CUresult (*cuCtxGetDevice)(CUdevice *);
+	CUresult (*cuDeviceGetUuid)(uint8_t uuid[16], CUdevice);
 };
 
 /* Data-path callbacks; either may be NULL (pure UVM mode). Return 0 on success. */

@@ -404,6 +404,8 @@ static void bootstrap(void)
 			(nvmlReturn_t(*)(unsigned, nvmlDevice_t *))real_dlsym(nvml, "nvmlDeviceGetHandleByIndex_v2");
 		client_drv.nvmlDeviceGetUtilizationRates =
 			(nvmlReturn_t(*)(nvmlDevice_t, nvmlUtilization_t *))real_dlsym(nvml, "nvmlDeviceGetUtilizationRates");
+		client_drv.nvmlDeviceGetHandleByUUID =
+			(nvmlReturn_t(*)(const char *, nvmlDevice_t *))real_dlsym(nvml, "nvmlDeviceGetHandleByUUID");
 	}
 	if (client_drv.nvmlInit && client_drv.nvmlDeviceGetHandleByIndex && client_drv.nvmlDeviceGetUtilizationRates) {
 		nvs_debug("Found NVML");
@@ -455,6 +457,11 @@ static void bootstrap(void)
 	client_drv.cuCtxGetCurrent = real_cuCtxGetCurrent;
 	client_drv.cuCtxSetCurrent = real_cuCtxSetCurrent;
 	client_drv.cuCtxSynchronize = real_cuCtxSynchronize;
+	/* optional: which physical GPU the application is on (the idle detector's NVML query) */
+	*(void **)&client_drv.cuCtxGetDevice = real_dlsym(cuda_lib, "cuCtxGetDevice");
+	*(void **)&client_drv.cuDeviceGetUuid = real_dlsym(cuda_lib, "cuDeviceGetUuid_v2");
+	if (!client_drv.cuDeviceGetUuid)
+		*(void **)&client_drv.cuDeviceGetUuid = real_dlsym(cuda_lib, "cuDeviceGetUuid");
 }
 
 /* ----------------------------------------------- data path adapters ----- */
