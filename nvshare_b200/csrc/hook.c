@@ -111,6 +111,7 @@ static int sync_window = 1;
 
 static pthread_mutex_t engine_mu = PTHREAD_MUTEX_INITIALIZER;
 static nvs_engine *engine;
+static CUcontext engine_ctx; /* the context the engine lives in: the first one an allocation was made from */
 static int holds_lock;
 
 /* ------------------------------------------------- the real dlsym ------- */
@@ -611,6 +612,7 @@ static nvs_engine *engine_get(void)
 					  "the reference's managed-memory mechanism instead", nvs_strerror(rc));
 			} else {
 				nvs_set_resident_mode(made, holds_lock);
+				engine_ctx = ctx;
 				__atomic_store_n(&engine, made, __ATOMIC_RELEASE);
 			}
 		}
@@ -811,7 +813,23 @@ CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize)
 	nvs_debug("cuMemAlloc requested %zu bytes", bytesize);
 	CUresult r;
 	nvs_engine *e = uvm_mode ? NULL : engine_get(); /* may switch uvm_mode on (no usable engine here) */
-	if (uvm_mode) {
+	int foreign = 0;
+	if (e) {
+		/* One engine, one context, one GPU -- the reference's "single context / single device" (its
+		 * README) with the difference that managed memory does not care which context asks for it and
+		 * ours does: an allocation made from ANOTHER context (a second GPU in the same process) must
+		 * not come out of the first GPU's engine.  It gets what the reference would have given it. */
+		CUcontext cur = NULL;
+		if (real_cuCtxGetCurrent(&cur) == CUDA_SUCCESS && cur != NULL && cur != engine_ctx) {
+			static int warned;
+			if (!__atomic_exchange_n(&warned, 1, __ATOMIC_RELAXED))
+				nvs_warn("allocation from a second CUDA context: only the first context's memory is swapped explicitly, "
+					 "this one is managed memory like under the reference");
+			foreign = 1;
+		}
+	}
+	if (uvm_mode || foreign) {
+		e = NULL;
 		r = real_cuMemAllocManaged(dptr, bytesize, CU_MEM_ATTACH_GLOBAL);
 		warn_if_error(r, "cuMemAllocManaged");
 	} else if (e) {

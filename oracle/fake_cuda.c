@@ -203,7 +203,20 @@ CUresult cuDeviceGetAttribute(int *v, int attr, CUdevice d)
 CUresult cuDeviceCanAccessPeer(int *can, CUdevice a, CUdevice b) { *can = (a != b); return OK; }
 CUresult cuDevicePrimaryCtxRetain(CUcontext *ctx, CUdevice d) { (void)d; *ctx = &g_ctx_token; return OK; }
 CUresult cuDevicePrimaryCtxRelease_v2(CUdevice d) { (void)d; return OK; }
-CUresult cuCtxCreate_v2(CUcontext *ctx, unsigned f, CUdevice d) { (void)f; (void)d; *ctx = &g_ctx_token; t_ctx_stack[0] = *ctx; if (!t_ctx_depth) t_ctx_depth = 1; return OK; }
+/* One context per process, on FAKE_CUDA_DEVICE -- except that cuCtxCreate for ANOTHER ordinal hands out a
+ * second, distinct context (a process that uses two GPUs).  Nothing in here depends on which context is
+ * current; the interposer under test does (one swap engine = one context). */
+static int g_ctx_token_other;
+CUresult cuCtxCreate_v2(CUcontext *ctx, unsigned f, CUdevice d)
+{
+	(void)f;
+	setup_once();
+	*ctx = d == g_cur_ordinal ? (void *)&g_ctx_token : (void *)&g_ctx_token_other;
+	if (!t_ctx_depth)
+		t_ctx_depth = 1;
+	t_ctx_stack[t_ctx_depth - 1] = *ctx; /* (the new context becomes current, like in the driver) */
+	return OK;
+}
 CUresult cuCtxGetCurrent(CUcontext *ctx)
 {
 	*ctx = t_ctx_depth ? t_ctx_stack[t_ctx_depth - 1] : NULL;

@@ -332,3 +332,23 @@ def test_stream_capture_breaks_under_the_reference_library(artefacts, default_so
     # ignored that, the capture would have ended as invalidated)
     assert rc != 0 and ("cuLaunchKernel" in out and "-> 900" in out or "END_CAPTURE rc=901" in out), out + err[-2000:]
     assert "cuCtxSynchronize during capture" in trace
+
+
+def test_allocation_from_a_second_context_is_not_served_by_the_first_contexts_engine(artefacts, sock_dir, tmp_path):
+    """The reference assumes one context and one device, but its managed memory does not care which context asks
+    for it; an engine of ours lives in ONE context on ONE GPU.  A process that creates a second context (a second
+    GPU) gets managed memory there, like under the reference, loudly -- never memory of the wrong GPU."""
+    d = Daemon("ours", sock_dir)
+    try:
+        env = fake_env(total_mib=4096, devices=2, trace=tmp_path / "trace.txt",
+                       extra={"NVSHARE_HOST_ARENA_MIB": 64, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_SOCK_DIR": sock_dir,
+                              "NVSHARE_POOL": "private"})
+        env["LD_PRELOAD"] = preload("ours")
+        r = subprocess.run([str(ORACLE / "two_ctx_app")], env=env, capture_output=True, text=True, timeout=60)
+    finally:
+        d.stop()
+    assert r.returncode == 0 and "RESULT PASS" in r.stdout, r.stdout + r.stderr[-2000:]
+    assert r.stderr.count("allocation from a second CUDA context") == 1
+    trace = (tmp_path / "trace.txt").read_text()
+    assert trace.count("cuMemAllocManaged 4194304") == 1          # the second context's buffer, and only that one
+    assert trace.count("cuMemCreate") >= 2                        # the first context's two buffers: engine memory
