@@ -476,6 +476,15 @@ def run_experiment(impl, kind, pattern, clients, oversub, tq, warmup, steps, tot
             res["device"]["link_bytes_over_algorithmic"] = {
                 "in": res["device"]["bytes_fetched"] / len(fe) / algo_bytes_dir,
                 "out": res["device"]["bytes_evicted"] / len(ev) / algo_bytes_dir}
+        led = [r for r in recs if "gl_lent" in r]
+        if led:         # peer tier: the cross-process GPU ledger as the engines saw it at their transfers (gpu_ledger.c)
+            res["device"]["gpu_ledger"] = {
+                "tracked_peers": max(r["gl_tracked_peers"] for r in led),
+                "lent_bytes_max": max(r["gl_lent"] for r in led),              # all clients' arenas on the peers, per the ledger
+                "one_client_lent_bytes_max": max(r["gl_my_lent"] for r in led),
+                "one_client_arena_bytes_max": max(r["peer_pool_bytes"] for r in led),   # what that engine itself holds mapped
+                "own_claim_matches_arenas": all(r["gl_my_lent"] == r["peer_pool_bytes"] for r in led if r["gl_tracked_peers"]),
+                "refusals": max(r["gl_refusals"] for r in led)}
         pins = [r for r in harness.engine_records(paths, 0, 1e18) if r["op"] == "pin"]
         if pins:        # where the pinned pool's pages ended up (engine.c numa_init): the last report covers the whole pool
             last = max(pins, key=lambda r: r["t"])
@@ -696,7 +705,7 @@ def brief(exp):
         d = exp["device"]
         out["device"] = {k: d[k] for k in ("evict_GBps", "fetch_GBps", "bytes_evicted", "bytes_fetched", "bytes_skipped_clean",
                                            "bytes_elided_same_filled", "peer_bytes", "host_bytes", "kernel_launches", "ce_calls",
-                                           "map_ms_mean", "wait_ms_mean", "wall_ms_mean") if k in d}
+                                           "map_ms_mean", "wait_ms_mean", "wall_ms_mean", "gpu_ledger") if k in d}
     return out
 
 

@@ -2114,15 +2114,31 @@ static void report_emit(nvs_engine *e, const char *what, const nvs_xfer_report *
 		  r->copy_ms > 0 ? r->bytes / 1e6 / r->copy_ms : 0.0, r->map_ms, r->wait_ms, r->scan_ms);
 	if (!e->stats_file)
 		return;
+	/* peer tier: what the cross-process ledger says about the GPUs we back our slabs on, next to what we
+	 * hold there ourselves (all clients' arenas together must be what those GPUs have "lent") */
+	char gl[160] = "";
+	if (e->cfg.n_peers > 0) {
+		uint64_t lent = 0, mine = 0, refused = 0;
+		int tracked = 0;
+		for (int i = 0; i < e->cfg.n_peers; ++i) {
+			const struct pool *p = &e->peer_pools[i];
+			tracked += p->gl_dev >= 0;
+			lent += nvs_gl_lent(p->gl_dev);
+			mine += nvs_gl_mine(p->gl_dev, NVS_GL_LENT);
+			refused += p->gl_refusals;
+		}
+		snprintf(gl, sizeof(gl), ",\"peer_pool_bytes\":%" PRIu64 ",\"gl_tracked_peers\":%d,\"gl_lent\":%" PRIu64
+			 ",\"gl_my_lent\":%" PRIu64 ",\"gl_refusals\":%" PRIu64, e->st.peer_pool_bytes, tracked, lent, mine, refused);
+	}
 	fprintf(e->stats_file,
 		"{\"op\":\"%s\",\"t\":%.6f,\"pid\":%d,\"bytes\":%" PRIu64 ",\"slabs\":%" PRIu64
 		",\"chunks\":%" PRIu64 ",\"launches\":%" PRIu64 ",\"ce_calls\":%" PRIu64 ",\"wall_ms\":%.3f,\"copy_ms\":%.3f,"
 		"\"map_ms\":%.3f,\"wait_ms\":%.3f,\"scan_ms\":%.3f,\"host_bytes\":%" PRIu64 ",\"peer_bytes\":%" PRIu64
 		",\"elided_bytes\":%" PRIu64 ",\"clean_bytes\":%" PRIu64 ",\"scanned_bytes\":%" PRIu64
-		",\"scan_launches\":%" PRIu64 ",\"retained_bytes\":%" PRIu64 ",\"pool_used\":%" PRIu64 ",\"favour\":%d}\n",
+		",\"scan_launches\":%" PRIu64 ",\"retained_bytes\":%" PRIu64 ",\"pool_used\":%" PRIu64 ",\"favour\":%d%s}\n",
 		what, wall_s(), (int)getpid(), r->bytes, r->slabs, r->chunks, r->launches, r->ce_calls, r->wall_ms, r->copy_ms,
 		r->map_ms, r->wait_ms, r->scan_ms, r->host_bytes, r->peer_bytes, r->elided_bytes, r->clean_bytes,
-		r->scanned_bytes, r->scan_launches, e->st.retained_bytes, e->host_pool.used, favour);
+		r->scanned_bytes, r->scan_launches, e->st.retained_bytes, e->host_pool.used, favour, gl);
 	fflush(e->stats_file);
 }
 

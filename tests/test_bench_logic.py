@@ -197,6 +197,7 @@ def test_run_experiment_post_processing_on_synthetic_records(tmp_path, monkeypat
     assert exp["verified"] and abs(exp["stall_ms_per_handoff"] - 1e3 * stall) < 60
     dev = exp["device"]
     assert dev["fetches"] >= 4 and dev["evicts"] >= 4 and dev["scan_GBps"] > 1000
+    assert "gpu_ledger" not in dev                        # host tier: the engines say nothing about peers
     ratio = dev["link_bytes_over_algorithmic"]            # per transfer, not per timed step
     assert abs(ratio["in"] - (50 << 30) / exp["algorithmic_bytes_per_handoff_per_direction"]) < 1e-9
     assert abs(ratio["out"] - (5 << 30) / exp["algorithmic_bytes_per_handoff_per_direction"]) < 1e-9
@@ -205,6 +206,15 @@ def test_run_experiment_post_processing_on_synthetic_records(tmp_path, monkeypat
     assert roof["roofline_link"]["fetch"]["frac"] > 0 and roof["roofline_link"]["evict"]["peak"] == 52.0
     brief = b.brief(exp)
     assert brief["verified"] and "stall_ms_per_handoff" in brief
+    # peer tier: the engines' view of the cross-process GPU ledger travels with their transfer records
+    for i in (0, 1):
+        for r in recs[i]:
+            r.update({"peer_pool_bytes": 30 << 30, "gl_tracked_peers": 1, "gl_lent": 55 << 30, "gl_my_lent": 30 << 30, "gl_refusals": 0})
+    exp_p = b.run_experiment("ours", "add", "pos", 2, 1.5, tq, 2, 4, HBM, 1.0, 2, tmp_path / "y", time_limit_s=300)
+    led = exp_p["device"]["gpu_ledger"]
+    assert led == {"tracked_peers": 1, "lent_bytes_max": 55 << 30, "one_client_lent_bytes_max": 30 << 30,
+                   "one_client_arena_bytes_max": 30 << 30, "own_claim_matches_arenas": True, "refusals": 0}
+    assert b.brief(exp_p)["device"]["gpu_ledger"] == led
     roof2 = b.roofline_objects(exp, {"link": {"h2d": 55.0, "d2h": 52.0}, "peer": {"out": 781.0, "in": 780.0}}, 2)
     assert roof2["roofline"]["bound"] == "nvlink" and roof2["roofline"]["peak"] == 780.5 and "roofline_scan" in roof2
 

@@ -244,3 +244,23 @@ def test_a_recycled_pid_does_not_keep_a_dead_clients_claim(workers, tmp_path):
     time.sleep(1.1)
     assert a("account", 0)["lent_bytes"] == (64 + 50) * MiB
     assert a("fetch")["mismatches"] == 0
+
+
+def test_transfer_records_carry_the_ledgers_view_of_the_peers(workers, tmp_path):
+    """What bench.py puts into the N >= 2 line (`device.gpu_ledger`): every evict / fetch record of an engine with a
+    peer tier says what the ledger holds for its peers -- all clients' arenas, its own claim -- next to what the
+    engine itself has mapped there."""
+    import json
+    a = workers(tmp_path, peers=[1], extra={"NVSHARE_STATS_FILE": tmp_path / "a.jsonl"})
+    b = workers(tmp_path, peers=[1], extra={"NVSHARE_STATS_FILE": tmp_path / "b.jsonl"})
+    assert a("alloc", 96)["ok"] and a("evict")["peer_bytes"] == 96 * MiB
+    assert b("alloc", 64)["ok"] and b("evict")["peer_bytes"] == 64 * MiB
+    ra = [json.loads(l) for l in (tmp_path / "a.jsonl").read_text().splitlines() if '"op":"evict"' in l][-1]
+    rb = [json.loads(l) for l in (tmp_path / "b.jsonl").read_text().splitlines() if '"op":"evict"' in l][-1]
+    assert ra["gl_tracked_peers"] == rb["gl_tracked_peers"] == 1
+    assert ra["gl_my_lent"] == ra["peer_pool_bytes"] == 96 * MiB and ra["gl_lent"] == 96 * MiB      # a was alone then
+    assert rb["gl_my_lent"] == rb["peer_pool_bytes"] == 64 * MiB and rb["gl_lent"] == (96 + 64) * MiB
+    assert ra["gl_refusals"] == rb["gl_refusals"] == 0
+    assert a("fetch")["mismatches"] == 0 and b("fetch")["mismatches"] == 0
+    fa = [json.loads(l) for l in (tmp_path / "a.jsonl").read_text().splitlines() if '"op":"fetch"' in l][-1]
+    assert fa["gl_my_lent"] == fa["peer_pool_bytes"] == 0                                            # arenas went back
