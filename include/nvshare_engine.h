@@ -73,6 +73,7 @@ extern "C" {
 #define NVS_E_NOT_SWAPPED (-9) /* nvs_host_io: the range is not (entirely) off the GPU */
 
 #define NVS_MAX_PEERS 7
+#define NVS_PEERS_AUTO (-1)
 
 typedef struct nvs_engine nvs_engine;
 
@@ -98,7 +99,9 @@ typedef struct nvs_engine_config {
 	uint32_t ldg_threads;        /* threads per CTA (LDG variant)                      */
 	uint32_t oom_wait_ms;        /* how long fetch/alloc wait for HBM to be released   */
 	uint32_t prepin;             /* 1 = grow the pinned pool in the background on alloc */
-	int32_t  n_peers;            /* peer-HBM backing tier: devices, in striping order  */
+	int32_t  n_peers;            /* peer-HBM backing tier: devices, in striping order;
+	                              * NVS_PEERS_AUTO = every other visible GPU this one can
+	                              * reach over NVLink/PCIe P2P (NVSHARE_PEERS=auto)      */
 	int32_t  peers[NVS_MAX_PEERS];
 	uint64_t peer_capacity_bytes; /* per peer; 0 = none                                */
 	const char *stats_path;      /* JSON lines, one per evict/fetch; NULL = off        */

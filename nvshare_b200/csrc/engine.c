@@ -101,6 +101,7 @@ struct drv {
 	CUresult (*CtxGetStreamPriorityRange)(int *, int *);                    /* optional */
 	CUresult (*DeviceGetUuid)(uint8_t uuid[16], CUdevice);                  /* optional (gpu ledger) */
 	CUresult (*DeviceTotalMem)(size_t *, CUdevice);                         /* optional (gpu ledger) */
+	CUresult (*DeviceGetCount)(int *);                                      /* optional (NVSHARE_PEERS=auto) */
 	CUresult (*StreamDestroy)(CUstream);
 	CUresult (*StreamSynchronize)(CUstream);
 	CUresult (*EventCreate)(CUevent *, unsigned);
@@ -552,8 +553,10 @@ int nvs_engine_default_config(nvs_engine_config *cfg)
 	cfg->shared_pool_bytes = env_u64("NVSHARE_POOL_GIB", 0) << 30;
 	if (getenv("NVSHARE_POOL_MIB")) /* finer grain, for tests of a tight pool */
 		cfg->shared_pool_bytes = env_u64("NVSHARE_POOL_MIB", 0) << 20;
-	const char *peers = getenv("NVSHARE_PEERS"); /* "1,2,3" */
-	if (peers && *peers) {
+	const char *peers = getenv("NVSHARE_PEERS"); /* "1,2,3", or "auto" */
+	if (peers && !strcmp(peers, "auto")) {
+		cfg->n_peers = NVS_PEERS_AUTO;
+	} else if (peers && *peers) {
 		char buf[128];
 		snprintf(buf, sizeof(buf), "%s", peers);
 		char *save = NULL; /* strtok_r: this library lives inside arbitrary applications */
@@ -3479,7 +3482,7 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	    e->cfg.tma_stages < 2 || e->cfg.tma_stages > 8 || (e->cfg.tma_tile_bytes & 15) || e->cfg.tma_tile_bytes == 0 ||
 	    (uint64_t)e->cfg.tma_warps * e->cfg.tma_stages * e->cfg.tma_tile_bytes > 200u * 1024u ||
 	    e->cfg.ldg_threads == 0 || e->cfg.ldg_threads > 1024 || (e->cfg.ldg_threads & 31) ||
-	    e->cfg.n_peers < 0 || e->cfg.n_peers > NVS_MAX_PEERS) {
+	    e->cfg.n_peers < NVS_PEERS_AUTO || e->cfg.n_peers > NVS_MAX_PEERS) {
 		free(e);
 		return NVS_E_BAD_ARG;
 	}
@@ -3508,6 +3511,7 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 	if (!e->d.DeviceGetUuid)
 		*(void **)&e->d.DeviceGetUuid = resolve("cuDeviceGetUuid");
 	*(void **)&e->d.DeviceTotalMem = resolve("cuDeviceTotalMem_v2");
+	*(void **)&e->d.DeviceGetCount = resolve("cuDeviceGetCount");
 	pthread_mutex_init(&e->api_mu, NULL);
 	pthread_mutex_init(&e->mu, NULL);
 	pthread_cond_init(&e->pre_cv, NULL);
@@ -3604,6 +3608,19 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 		if (shp_open(e, e->cfg.shared_pool_path, cap) != 0)
 			nvs_warn("engine: cannot use the shared host pool %s (%s); using a private pinned pool",
 				 e->cfg.shared_pool_path, strerror(errno));
+	}
+	if (e->cfg.n_peers == NVS_PEERS_AUTO) {
+		/* every other GPU this process can see and this GPU can reach: with the GPU ledger such a
+		 * GPU only lends what its own clients do not need, so "all of them" is a safe answer */
+		int count = 0;
+		e->cfg.n_peers = 0;
+		if (e->d.DeviceGetCount && e->d.DeviceGetCount(&count) == CUDA_SUCCESS)
+			for (int d = 0; d < count && e->cfg.n_peers < NVS_MAX_PEERS; ++d) {
+				int can = 0;
+				if (d != e->device && e->d.DeviceCanAccessPeer(&can, e->device, d) == CUDA_SUCCESS && can)
+					e->cfg.peers[e->cfg.n_peers++] = d;
+			}
+		nvs_debug("engine: NVSHARE_PEERS=auto: %d peer GPU(s) of device %d can back its slabs", e->cfg.n_peers, e->device);
 	}
 	for (int i = 0; i < e->cfg.n_peers; ++i) {
 		int can = 0;

@@ -149,6 +149,9 @@ class Engine:
         for k, v in overrides.items():
             if k in ("evict_variant", "fetch_variant", "peer_evict_variant", "peer_fetch_variant") and isinstance(v, str):
                 v = VARIANTS[v]
+            if k == "peers" and v == "auto":          # NVS_PEERS_AUTO: every other visible GPU this one can reach
+                cfg.n_peers = -1
+                continue
             if k == "peers":
                 cfg.n_peers = len(v)
                 for i, d in enumerate(v):

@@ -29,7 +29,8 @@ def main():
     ctx = C.c_void_p()
     assert fake.cuDevicePrimaryCtxRetain(C.byref(ctx), dev.value) == 0 and fake.cuCtxSetCurrent(ctx) == 0
     from nvshare_b200 import engine as E
-    peers = [int(x) for x in os.environ.get("WORKER_PEERS", "").split(",") if x]
+    wp = os.environ.get("WORKER_PEERS", "")
+    peers = "auto" if wp == "auto" else [int(x) for x in wp.split(",") if x]
     e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=32 * MiB, batch_bytes=32 * MiB, peers=peers, prepin=0,
                  elide_constant=0, retain=0, oom_wait_ms=2000)
     allocs = []

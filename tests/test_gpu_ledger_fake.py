@@ -24,7 +24,7 @@ class Worker:
     def __init__(self, tmp_path, peers=(), device=0, visible=None, total_mib=256, reserve_mib=16, extra=None):
         env = fake_env(total_mib=total_mib, ledger=tmp_path / "hbm", devices=4,
                        extra={"NVSHARE_GPU_LEDGER": tmp_path / "gpus", "NVSHARE_GPU_RESERVE_MIB": reserve_mib,
-                              "WORKER_PEERS": ",".join(map(str, peers)), "FAKE_CUDA_DEVICE": device,
+                              "WORKER_PEERS": peers if peers == "auto" else ",".join(map(str, peers)), "FAKE_CUDA_DEVICE": device,
                               "NVSHARE_POOL": "private", **(extra or {})})
         if visible:
             env["FAKE_CUDA_VISIBLE"] = visible
@@ -264,3 +264,20 @@ def test_transfer_records_carry_the_ledgers_view_of_the_peers(workers, tmp_path)
     assert a("fetch")["mismatches"] == 0 and b("fetch")["mismatches"] == 0
     fa = [json.loads(l) for l in (tmp_path / "a.jsonl").read_text().splitlines() if '"op":"fetch"' in l][-1]
     assert fa["gl_my_lent"] == fa["peer_pool_bytes"] == 0                                            # arenas went back
+
+
+def test_peers_auto_uses_every_other_reachable_gpu_and_respects_their_tenants(workers, tmp_path):
+    """NVSHARE_PEERS=auto (NVS_PEERS_AUTO): every other visible GPU the engine's GPU can reach backs its slabs,
+    striped; the ledger is what makes "all of them" safe -- a GPU with a tenant lends only what the tenant leaves."""
+    tenant = workers(tmp_path, device=2)                           # physical GPU 2 has a client of its own
+    assert tenant("alloc", 192)["ok"]                              # of 256 MiB: 16 reserved, 192 its own, 48 to lend
+    guest = workers(tmp_path, peers="auto")                        # computes on GPU 0; peers 1, 2, 3 (four fake GPUs)
+    assert guest("alloc", 240)["ok"]
+    rep = guest("evict")
+    assert rep["peer_bytes"] == 240 * MiB and rep["host_bytes"] == 0      # the three peers hold it all
+    accs = [guest("account", i) for i in range(3)]
+    assert [a["device"] for a in accs] == [1, 2, 3] and all(a["tracked"] == 1 for a in accs)
+    assert sum(a["my_lent_bytes"] for a in accs) >= 240 * MiB
+    assert accs[1]["my_lent_bytes"] <= 48 * MiB and accs[1]["max_own_bytes"] == 192 * MiB   # GPU 2 kept its tenant's room
+    assert accs[0]["my_lent_bytes"] >= 64 * MiB and accs[2]["my_lent_bytes"] >= 64 * MiB    # striping used the others
+    assert guest("fetch")["mismatches"] == 0 and tenant("fetch")["mismatches"] == 0
