@@ -67,3 +67,23 @@ def test_backing_on_a_peer_is_accounted_on_that_peer(torch0, artefacts):
         assert e.pattern_verify(p, size // 8, seed=9) == 0
         assert e.gpu_account(0)["my_lent_bytes"] == 0            # empty arenas go back at once
         e.free(p)
+
+
+def test_peers_auto_on_whatever_this_box_has(torch0, artefacts):
+    """NVSHARE_PEERS=auto: with one GPU there is no peer and everything goes to pinned host memory; with more,
+    the other GPUs hold it (they are idle here, the ledger lets them lend)."""
+    from nvshare_b200 import engine as E
+    size = 1 * GiB
+    with E.Engine(peers="auto", elide_constant=0) as e:
+        p = e.alloc(size)
+        e.fetch_all()
+        e.pattern_fill(p, size // 8, seed=13)
+        ev = e.evict(0)
+        assert ev["bytes"] + ev["clean_bytes"] == size
+        if torch0.cuda.device_count() > 1:
+            assert ev["peer_bytes"] == size and e.gpu_account(0)["tracked"] == 1
+        else:
+            assert ev["peer_bytes"] == 0
+        e.fetch_all()
+        assert e.pattern_verify(p, size // 8, seed=13) == 0
+        e.free(p)
