@@ -6,7 +6,8 @@
                    -gencode arch=compute_100a,code=sm_100a -lineinfo
   build_oracle()   oracle/Makefile -> oracle/_ref/ (test infrastructure: the
                    unmodified reference when /root/reference is present, the fake
-                   driver, the C restatement, the test application)
+                   driver, the C restatement, the test applications, and the
+                   reference's hook + client bound to our C-ABI: libnvshare_bound.so)
 """
 from __future__ import annotations
 
@@ -49,6 +50,11 @@ def build_product(force: bool = False) -> Path:
 def build_oracle() -> Path:
     """Build the test infrastructure (never part of the product path)."""
     _run(["make", "-C", str(ORACLE), "all"], ROOT)
+    # INTEGRATION.md section B made executable: the unmodified reference hook + client bound to our C-ABI library
+    # (only where the reference's sources and our product are present; the result travels like the rest of _ref)
+    if (BUILD / "libnvs_engine.so").exists():
+        import sys
+        _run([sys.executable, str(ORACLE / "bind_reference.py")], ROOT)
     return ORACLE_OUT
 
 

@@ -66,6 +66,7 @@ int main(int argc, char **argv)
 		h[i] = mix(i, seed);
 	CK(cuMemcpyHtoD_v2(buf[0], h, bytes));
 
+	const int no_launch = getenv("DRIVER_APP_NO_LAUNCH") != NULL; /* copies only: runs on the real driver too */
 	struct timespec t0, t;
 	clock_gettime(CLOCK_MONOTONIC, &t0);
 	unsigned long iters = 0;
@@ -73,7 +74,8 @@ int main(int argc, char **argv)
 		/* rotate the payload through every buffer, "compute" in between */
 		int src = (int)(iters % (unsigned)nbuf), dst = (int)((iters + 1) % (unsigned)nbuf);
 		CK(cuMemcpyDtoD_v2(buf[dst], buf[src], bytes));
-		CK(cuLaunchKernel((void *)0x1234, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+		if (!no_launch) /* (the handle only means something to the fake driver) */
+			CK(cuLaunchKernel((void *)0x1234, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
 		iters++;
 		clock_gettime(CLOCK_MONOTONIC, &t);
 		if ((t.tv_sec - t0.tv_sec) + (t.tv_nsec - t0.tv_nsec) * 1e-9 >= seconds)
