@@ -41,8 +41,8 @@ def test_the_bound_library_is_the_references_plus_our_c_abi(bound):
 def test_two_oversubscribed_clients_under_the_reference_daemon(bound, default_sock_lock, tmp_path):
     d = Daemon("reference", default_sock_lock, log_path=tmp_path / "sched.log")
     try:
-        d.ctl("-T", "1")
         procs = []
+        d.ctl("-T", "1")
         for i in (1, 2):
             env = fake_env(total_mib=200, ledger=tmp_path / "hbm", trace=tmp_path / f"trace{i}.txt",
                            extra={"NVSHARE_HOST_ARENA_MIB": 64, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_BATCH_MIB": 32, "NVSHARE_DEBUG": 1,
@@ -52,6 +52,9 @@ def test_two_oversubscribed_clients_under_the_reference_daemon(bound, default_so
                                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
         outs = [p.communicate(timeout=120) for p in procs]
     finally:
+        for p in procs:                     # (a client that is still there after a failure must not outlive the test)
+            if p.poll() is None:
+                p.kill()
         d.stop()
     for i, (p, (out, err)) in enumerate(zip(procs, outs), 1):
         assert p.returncode == 0 and re.search(r"RESULT PASS iters=\d+ mismatches=0", out), out + err[-2500:]

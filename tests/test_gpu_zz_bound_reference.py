@@ -26,8 +26,8 @@ def test_reference_hook_and_client_over_our_engine_on_the_gpu(artefacts, default
         pytest.skip("oracle/_ref/libnvshare_bound.so was not built (reference sources absent at build time)")
     d = Daemon("reference", default_sock_lock, log_path=tmp_path / "sched.log")
     try:
-        d.ctl("-T", "1")
         procs = []
+        d.ctl("-T", "1")
         for i in (1, 2):
             env = dict(os.environ, LD_PRELOAD=str(BOUND), NVSHARE_DEBUG="1", DRIVER_APP_NO_LAUNCH="1",
                        NVSHARE_STATS_FILE=str(tmp_path / f"stats{i}.jsonl"))
@@ -35,6 +35,9 @@ def test_reference_hook_and_client_over_our_engine_on_the_gpu(artefacts, default
                                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
         outs = [p.communicate(timeout=300) for p in procs]
     finally:
+        for p in procs:                     # (a client that is still there after a failure must not outlive the test)
+            if p.poll() is None:
+                p.kill()
         d.stop()
     for i, (p, (out, err)) in enumerate(zip(procs, outs), 1):
         assert p.returncode == 0 and re.search(r"RESULT PASS iters=\d+ mismatches=0", out), out + err[-2500:]
