@@ -55,6 +55,7 @@ def build_oracle() -> Path:
     if (BUILD / "libnvs_engine.so").exists():
         import sys
         _run([sys.executable, str(ORACLE / "bind_reference.py")], ROOT)
+        _run([sys.executable, str(ORACLE / "bind_reference.py"), "--optional"], ROOT)
     return ORACLE_OUT
 
 

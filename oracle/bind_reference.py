@@ -12,7 +12,9 @@ Nothing of the reference is copied into the repository: the edits below name sho
 reference's code (file:line in the comments) and the only output is the shared object in oracle/_ref/.
 tests/test_bound_reference.py runs two oversubscribed clients under the REFERENCE daemon with it.
 
-    python oracle/bind_reference.py [reference root] [output .so]
+    python oracle/bind_reference.py [--optional] [reference root] [output .so]
+--optional adds the one-line optional calls of that section (copies that need no lock, recency hint, hand-over
+announcement, the cap that follows what the GPU has lent) -> oracle/_ref/libnvshare_bound_opt.so
 """
 from __future__ import annotations
 
@@ -23,8 +25,8 @@ import tempfile
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-REF = Path(sys.argv[1]) if len(sys.argv) > 1 else Path("/root/reference")
-OUT = Path(sys.argv[2]) if len(sys.argv) > 2 else ROOT / "oracle" / "_ref" / "libnvshare_bound.so"
+REF = Path("/root/reference")
+OUT = ROOT / "oracle" / "_ref" / "libnvshare_bound.so"
 BUILD = ROOT / "nvshare_b200" / "_build"
 
 HOOK_STATE = r'''
@@ -96,7 +98,44 @@ def bind_client(src):
     return src
 
 
+def bind_optional(hook, client):
+    """The optional calls of INTEGRATION.md B (one line each): copies that do not need the GPU, the recency hint,
+    the hand-over announcement, and the cap that follows what this GPU has lent."""
+    # src/hook.c:909 / :878 -- cuMemcpyHtoD / cuMemcpyDtoH on memory that is swapped out: host <-> pinned backing, no lock
+    hook = edit(hook, "nvs_engine *nvshare_engine;", "nvs_engine *nvshare_engine;\nextern int own_lock;           /* src/client.c:50 */",
+                "own_lock")
+    a = "continue_with_lock();\n\tresult = real_cuMemcpyHtoD(dstDevice, srcHost, ByteCount);"
+    hook = edit(hook, a, "if (nvshare_engine) nvs_touch(nvshare_engine, dstDevice, ByteCount);\n"
+                         "\tif (!own_lock && nvshare_engine && nvs_host_io(nvshare_engine, dstDevice, (void *)srcHost, ByteCount, 1) == 0)\n"
+                         "\t\treturn CUDA_SUCCESS;\n\t" + a, "HtoD bypass")
+    a = "continue_with_lock();\n\tresult = real_cuMemcpyDtoH(dstHost, srcDevice, ByteCount);"
+    hook = edit(hook, a, "if (!own_lock && nvshare_engine && nvs_host_io(nvshare_engine, srcDevice, dstHost, ByteCount, 0) == 0)\n"
+                         "\t\treturn CUDA_SUCCESS;\n\t" + a, "DtoH bypass")
+    # the same for the asynchronous flavours (src/hook.c:925, :893): for pageable-style semantics the copy may be done on return
+    a = "continue_with_lock();\n\tresult = real_cuMemcpyHtoDAsync(dstDevice, srcHost, ByteCount, hStream);"
+    hook = edit(hook, a, "if (nvshare_engine) nvs_touch(nvshare_engine, dstDevice, ByteCount);\n"
+                         "\tif (!own_lock && nvshare_engine && nvs_host_io(nvshare_engine, dstDevice, (void *)srcHost, ByteCount, 1) == 0)\n"
+                         "\t\treturn CUDA_SUCCESS;\n\t" + a, "HtoDAsync bypass")
+    a = "continue_with_lock();\n\tresult = real_cuMemcpyDtoHAsync(dstHost, srcDevice, ByteCount, hStream);"
+    hook = edit(hook, a, "if (!own_lock && nvshare_engine && nvs_host_io(nvshare_engine, srcDevice, dstHost, ByteCount, 0) == 0)\n"
+                         "\t\treturn CUDA_SUCCESS;\n\t" + a, "DtoHAsync bypass")
+    # src/hook.c:662 -- the cap follows what this GPU has lent to clients of other GPUs
+    a = "if ((sum_allocated + bytesize) > nvshare_size_mem_allocatable) {"
+    hook = edit(hook, a, "if ((sum_allocated + bytesize) > nvshare_size_mem_allocatable - "
+                         "(nvshare_engine ? nvs_gpu_lent_bytes(nvshare_engine) : 0)) {", "cap")
+    # src/client.c:313 -- DROP_LOCK, before LOCK_RELEASED is written
+    a = "out_msg.type = LOCK_RELEASED;"
+    client = edit(client, a, "if (nvshare_engine) nvs_evict_announce(nvshare_engine);\n\t\t\t\t" + a, "announce", after="case DROP_LOCK:")
+    return hook, client
+
+
 def main():
+    optional = "--optional" in sys.argv
+    if optional:
+        sys.argv.remove("--optional")
+    global REF, OUT
+    REF = Path(sys.argv[1]) if len(sys.argv) > 1 else REF
+    OUT = Path(sys.argv[2]) if len(sys.argv) > 2 else (OUT.with_name("libnvshare_bound_opt.so") if optional else OUT)
     src = REF / "src"
     if not (src / "hook.c").exists():
         print(f"reference sources not present ({src}): nothing to bind")
@@ -106,8 +145,11 @@ def main():
         return 1
     tmp = Path(tempfile.mkdtemp(prefix="nvs_bind_"))
     try:
-        (tmp / "hook.c").write_text(bind_hook((src / "hook.c").read_text()))
-        (tmp / "client.c").write_text(bind_client((src / "client.c").read_text()))
+        hook, client = bind_hook((src / "hook.c").read_text()), bind_client((src / "client.c").read_text())
+        if optional:
+            hook, client = bind_optional(hook, client)
+        (tmp / "hook.c").write_text(hook)
+        (tmp / "client.c").write_text(client)
         OUT.parent.mkdir(parents=True, exist_ok=True)
         cmd = ["gcc", "-O2", "-g", "-fPIC", "-w", "-D_GNU_SOURCE", f"-I{src}", f"-I{ROOT / 'include'}",
                str(tmp / "hook.c"), str(tmp / "client.c"), str(src / "common.c"), str(src / "comm.c"),
