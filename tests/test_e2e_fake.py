@@ -352,3 +352,38 @@ def test_allocation_from_a_second_context_is_not_served_by_the_first_contexts_en
     trace = (tmp_path / "trace.txt").read_text()
     assert trace.count("cuMemAllocManaged 4194304") == 1          # the second context's buffer, and only that one
     assert trace.count("cuMemCreate") >= 2                        # the first context's two buffers: engine memory
+
+
+@pytest.mark.parametrize("peers", ["1", "auto"])
+def test_hooked_clients_on_the_peer_tier(artefacts, sock_dir, tmp_path, peers):
+    """The peer-HBM backing tier through the interposer (NVSHARE_PEERS in the application's environment, the way
+    bench.py --gpus N sets it): two oversubscribed clients of "GPU 0" back their slabs on "GPU 1" of the fake driver
+    (a list of ordinals, or `auto` = every other GPU it can reach) and get every word back."""
+    import json
+    d = Daemon("ours", sock_dir, log_path=tmp_path / "sched.log")
+    procs = []
+    try:
+        d.ctl("-T", "1")
+        for i in (1, 2):
+            env = fake_env(total_mib=200, ledger=tmp_path / "ledger", devices=2,
+                           extra={"NVSHARE_HOST_ARENA_MIB": 32, "NVSHARE_CHUNK_MIB": 8, "NVSHARE_BATCH_MIB": 32, "NVSHARE_DEBUG": 1,
+                                  "NVSHARE_SOCK_DIR": sock_dir, "NVSHARE_PEERS": peers, "NVSHARE_GPU_LEDGER": tmp_path / "gpus",
+                                  "NVSHARE_GPU_RESERVE_MIB": 8, "NVSHARE_STATS_FILE": tmp_path / f"stats{i}.jsonl"})
+            env["LD_PRELOAD"] = preload("ours")
+            procs.append(subprocess.Popen([str(ORACLE / "driver_app"), "40", "4.0", str(i), "3"], env=env,
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=120) for p in procs]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        d.stop()
+    check([(p.returncode, o, e) for p, (o, e) in zip(procs, outs)])
+    for i in (1, 2):
+        recs = [json.loads(l) for l in (tmp_path / f"stats{i}.jsonl").read_text().splitlines()]
+        ev = [r for r in recs if r["op"] == "evict"]
+        assert ev and sum(r["peer_bytes"] for r in ev) > 0                    # slabs went to the other GPU's HBM
+        assert all(r["gl_tracked_peers"] == 1 for r in ev)                    # and the ledger knows whose it is
+        assert max(r["gl_lent"] for r in ev) <= (200 - 8) << 20
+    if peers == "auto":
+        assert "NVSHARE_PEERS=auto: 1 peer GPU(s) of device 0" in outs[0][1]

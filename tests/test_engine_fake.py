@@ -418,6 +418,26 @@ def test_host_io_load_before_first_residency_reads_zero_elsewhere(fake):
         e.close()
 
 
+def test_host_io_large_copies_are_split_over_threads(fake):
+    """A run of 32 MiB or more inside one chunk is copied by several threads (par_memcpy): with the production chunk
+    size (256 MiB) that is every model-sized upload.  Ragged ends, both directions, then the device's view."""
+    from nvshare_b200 import engine as E
+    e = E.Engine(chunk_bytes=128 * MiB, host_arena_bytes=128 * MiB, oom_wait_ms=300, prepin=0, elide_constant=0, retain=0)
+    try:
+        p = e.alloc(128 * MiB)
+        src = np.random.default_rng(7).integers(0, 256, 101 * MiB + 4099, dtype=np.uint8)
+        lo = 5 * MiB + 17
+        assert e.host_io(p + lo, src.ctypes.data, len(src), True) == 0
+        back = np.empty(len(src), dtype=np.uint8)
+        assert e.host_io(p + lo, back.ctypes.data, len(back), False) == 0
+        assert np.array_equal(back, src)
+        e.fetch_all()
+        got = view(p, 128 * MiB)
+        assert np.array_equal(got[lo:lo + len(src)], src) and not got[:lo].any() and not got[lo + len(src):].any()
+    finally:
+        e.close()
+
+
 def test_host_io_on_same_filled_slabs(fake):
     from nvshare_b200 import engine as E
     e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, oom_wait_ms=300, prepin=0, elide_constant=1)
