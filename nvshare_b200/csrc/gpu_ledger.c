@@ -156,7 +156,9 @@ static void gl_open_once(void)
 	if (env && *env)
 		snprintf(path, sizeof(path), "%s", env);
 	else
-		snprintf(path, sizeof(path), "/dev/shm/nvshare-gpus-%u", (unsigned)geteuid());
+		/* the layout version is part of the name: clients of two versions on one node keep two ledgers
+		 * instead of the newer one finding a file it cannot use */
+		snprintf(path, sizeof(path), "/dev/shm/nvshare-gpus-%u-v%u", (unsigned)geteuid(), GL_VERSION);
 
 	int creator = 1;
 	int fd = open(path, O_RDWR | O_CREAT | O_EXCL | O_CLOEXEC | O_NOFOLLOW, 0600);
@@ -185,7 +187,9 @@ static void gl_open_once(void)
 		return;
 	}
 	if (!creator) { /* the creator sizes the file, then publishes the magic */
-		for (int i = 0; i < 2000 && (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(struct gl_file)); ++i)
+		/* (a short file that nobody has touched for seconds is not being created: it is another layout) */
+		for (int i = 0; i < 2000 && (fstat(fd, &st) != 0 || ((size_t)st.st_size < sizeof(struct gl_file) &&
+									 time(NULL) - st.st_mtime < 3)); ++i)
 			usleep(1000);
 		if ((size_t)st.st_size != sizeof(struct gl_file)) {
 			nvs_warn("gpu ledger: %s has an unexpected size (another version?): per-GPU accounting across processes is off", path);

@@ -281,3 +281,22 @@ def test_peers_auto_uses_every_other_reachable_gpu_and_respects_their_tenants(wo
     assert accs[1]["my_lent_bytes"] <= 48 * MiB and accs[1]["max_own_bytes"] == 192 * MiB   # GPU 2 kept its tenant's room
     assert accs[0]["my_lent_bytes"] >= 64 * MiB and accs[2]["my_lent_bytes"] >= 64 * MiB    # striping used the others
     assert guest("fetch")["mismatches"] == 0 and tenant("fetch")["mismatches"] == 0
+
+
+def test_a_ledger_of_another_layout_is_left_alone(workers, tmp_path):
+    """An explicitly named ledger (NVSHARE_GPU_LEDGER) that is ours by owner and mode but has another layout's size
+    -- an older client's -- is not used and not waited for: the accounting is off, loudly, at once; the data path works.
+    (The default name carries the layout version, so two versions on one node keep two files.)"""
+    old = tmp_path / "gpus"
+    old.write_bytes(b"\0" * 33856)
+    os.chmod(old, 0o600)
+    os.utime(old, (time.time() - 60, time.time() - 60))
+    t0 = time.time()
+    a = workers(tmp_path, peers=[1])
+    assert time.time() - t0 < 1.9                                 # (a young short file is waited for up to 2 s: its creator is sizing it)
+    assert a("alloc", 64)["ok"] and a("evict")["peer_bytes"] == 64 * MiB
+    assert a("account", 0)["tracked"] == 0
+    assert a("fetch")["mismatches"] == 0
+    a.quit()
+    assert "unexpected size" in a.p.stderr.read()
+    assert old.stat().st_size == 33856                            # untouched
