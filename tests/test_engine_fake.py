@@ -225,6 +225,41 @@ def test_fetch_times_out_when_hbm_never_frees(fake, tmp_path):
     assert "RC -6" in r.stdout, r.stdout + r.stderr         # NVS_E_TIMEOUT
 
 
+def test_resident_allocation_that_cannot_get_hbm_fails_clean(fake, tmp_path):
+    """The lock holder asks for more than the GPU can give (cuMemAlloc -> nvs_alloc in resident mode): the call
+    fails with CUDA_ERROR_OUT_OF_MEMORY after the wait, what it had mapped so far goes back, the counters return
+    to where they were, and the engine goes on working."""
+    ledger = tmp_path / "ledger"
+    code = textwrap.dedent(f"""
+        import ctypes as C, sys
+        sys.path.insert(0, {str(ROOT)!r})
+        fake = C.CDLL({str(FAKE_DIR / 'libcuda.so.1')!r}, mode=C.RTLD_GLOBAL)
+        fake.fake_cuda_phys_used.restype = C.c_uint64
+        fake.cuInit(0); ctx = C.c_void_p(); fake.cuDevicePrimaryCtxRetain(C.byref(ctx), 0); fake.cuCtxSetCurrent(ctx)
+        from nvshare_b200 import engine as E
+        MiB = 1 << 20
+        e = E.Engine(chunk_bytes=8 * MiB, host_arena_bytes=64 * MiB, oom_wait_ms=200, prepin=0, shared_pool_path=None)
+        e.set_resident_mode(True)
+        keep = e.alloc(24 * MiB)                       # resident at once: the holder's allocations are usable immediately
+        before = e.stats()
+        used = fake.fake_cuda_phys_used()
+        try:
+            e.alloc(64 * MiB); print("UNEXPECTED")
+        except E.EngineError as ex:
+            print("RC", ex.rc)
+        after = e.stats()
+        print("SAME", all(after[k] == before[k] for k in ("resident_bytes", "unbacked_bytes", "swapped_bytes", "va_bytes")))
+        print("PHYS", fake.fake_cuda_phys_used() == used)
+        e.pattern_fill(keep, 24 * MiB // 8, seed=5); e.evict(0); e.fetch_all()
+        print("BAD", e.pattern_verify(keep, 24 * MiB // 8, seed=5))
+        small = e.alloc(16 * MiB); print("LATER", e.stats()["resident_bytes"] // MiB)
+    """)
+    env = dict(__import__("os").environ, FAKE_CUDA_TOTAL_MIB="64", FAKE_CUDA_LEDGER=str(ledger))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=60)
+    assert "RC 2" in r.stdout and "UNEXPECTED" not in r.stdout, r.stdout + r.stderr       # CUDA_ERROR_OUT_OF_MEMORY
+    assert "SAME True" in r.stdout and "PHYS True" in r.stdout and "BAD 0" in r.stdout and "LATER 40" in r.stdout, r.stdout + r.stderr
+
+
 def test_timed_out_fetch_leaves_a_consistent_table(fake, tmp_path):
     """A fetch that gives up half-way must not mark a chunk resident before its
     data is back: after the HBM hog goes away a second fetch restores everything."""
