@@ -67,7 +67,9 @@ def test_need_based_eviction_moves_only_what_the_next_client_needs(artefacts, so
         d = Daemon("ours", sock_dir, log_path=run / "sched.log")
         try:
             d.ctl("-T", "1")
-            res = finish([spawn(sock_dir, run, i, 80, 6.0) for i in (1, 2)])
+            # (patience of 2 s before a waiting fetch presses: the fake driver's "scan kernel" hashes 240 MiB on this
+            # CPU in about the product's 300 ms, and which side of that a run lands on is the load of the box)
+            res = finish([spawn(sock_dir, run, i, 80, 6.0, extra={"NVSHARE_PRESSURE_AFTER_MS": 2000}) for i in (1, 2)])
         finally:
             d.stop()
         ev = {i: [r for r in stats(run, i) if r["op"] == "evict"] for i in (1, 2)}
@@ -320,10 +322,10 @@ def test_background_precleaning_makes_the_first_handoff_cheap(artefacts, sock_di
         seen.append((pre >> 20, first_evict["clean_bytes"] >> 20))
         # two of A's three buffers are not written any more once the payload has gone round; the first
         # eviction finds their background copies still valid.  Without the pre-cleaner NOTHING is clean at a
-        # first eviction, so one chunk is proof enough; how many of the copies were taken after the buffers had
+        # first eviction, so one slab is proof enough; how many of the copies were taken after the buffers had
         # settled (160 MiB when all were) is a race between the application's start-up and the pre-cleaner's
-        # one pass per residency -- in the middle of the whole suite usually 16-40 MiB
-        if pre >= 160 * MiB and first_evict["clean_bytes"] >= 8 * MiB:
+        # one pass per residency -- in the middle of the whole suite usually 6-40 MiB
+        if pre >= 160 * MiB and first_evict["clean_bytes"] >= 2 * MiB:       # one slab
             return
         note_retry("preclean", seen[-1])
     pytest.fail(f"(pre-cleaned MiB, clean MiB at the first eviction) per attempt: {seen}")
