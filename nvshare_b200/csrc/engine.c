@@ -382,7 +382,6 @@ struct nvs_engine {
 	int gl_dev;          /* the GPU we compute on, in the cross-process ledger (-1 = not tracked) */
 	uint64_t gl_reserve; /* bytes of every GPU that are nobody's to claim (contexts, libraries)  */
 	uint64_t gl_total;   /* cuDeviceTotalMem of the GPU we compute on                            */
-	double pressure_after_ms;
 	uint64_t epoch;
 	int resident_mode;
 	nvs_stats st;
@@ -408,9 +407,7 @@ struct nvs_engine {
 /* Memory pressure is only signalled once the free HBM has not grown for this long: while
  * the previous holder is evicting for us it grows every few tens of ms, and a pressure
  * message sent then would be handled AFTER that eviction and evict the same amount again. */
-/* how long a fetch / an allocation watches free HBM not growing before it tells the other clients (through the
- * daemon) how much it still misses; NVSHARE_PRESSURE_AFTER_MS */
-#define PRESSURE_AFTER_MS (e->pressure_after_ms)
+#define PRESSURE_AFTER_MS 300.0
 /* how long an eviction waits for units of a full shared pool before it pins an overflow arena */
 #define POOL_FULL_GRACE_MS 2000.0
 
@@ -3638,7 +3635,6 @@ int nvs_engine_create(const nvs_engine_config *cfg_in, nvs_engine **out)
 		}
 	}
 	/* cross-process accounting per GPU (gpu_ledger.h): the GPU we compute on and every peer we lend from */
-	e->pressure_after_ms = (double)env_u64("NVSHARE_PRESSURE_AFTER_MS", 300);
 	e->gl_reserve = env_u64("NVSHARE_GPU_RESERVE_MIB", 1536) << 20; /* the slice the reference hides too, src/hook.c:45 */
 	e->gl_dev = gl_register(e, e->device, &e->gl_total);
 	for (int i = 0; i < e->cfg.n_peers; ++i)

@@ -67,9 +67,9 @@ def test_need_based_eviction_moves_only_what_the_next_client_needs(artefacts, so
         d = Daemon("ours", sock_dir, log_path=run / "sched.log")
         try:
             d.ctl("-T", "1")
-            # (patience of 2 s before a waiting fetch presses: the fake driver's "scan kernel" hashes 240 MiB on this
-            # CPU in about the product's 300 ms, and which side of that a run lands on is the load of the box)
-            res = finish([spawn(sock_dir, run, i, 80, 6.0, extra={"NVSHARE_PRESSURE_AFTER_MS": 2000}) for i in (1, 2)])
+            # (the fake driver's "scan kernel" hashes 240 MiB on this CPU in about the 300 ms a waiting fetch watches
+            # free HBM not growing before it presses: which side of that a run lands on is the load of the box)
+            res = finish([spawn(sock_dir, run, i, 80, 6.0) for i in (1, 2)])
         finally:
             d.stop()
         ev = {i: [r for r in stats(run, i) if r["op"] == "evict"] for i in (1, 2)}
